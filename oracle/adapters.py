@@ -1,0 +1,124 @@
+"""Oracle: the two plug-in denoiser adapters, incl. the online fine-tune.
+
+Test infrastructure.  CPU restatements of
+  * ``ffdnet_rgb_denoise_full_tensor``      packages/ffdnet/test_ffdnet_ipol.py:240-359
+  * ``fastdvdnet_seqdenoise``               packages/fastdvdnet/fastdvdnet.py:82-146
+  * ``fastdvdnet_denoiser_full_tensor_v2``  packages/fastdvdnet/test_fastdvdnet.py:325-500
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .sci_ops import fourCh2OneCh, gen_bayer_img, rgb_to_bayer4
+
+NUM_IN_FR_EXT = 5   # test_fastdvdnet.py:23
+
+
+def _ffdnet_frames(x, sigma, model):
+    """8 x model(img[1,3,H,W], sigma[1,1,1,1]) -> [H,W,3,B] (:266-273 / :344-354)."""
+    outs = []
+    for t in range(x.shape[3]):
+        img = x[:, :, :, t].permute(2, 0, 1).float().unsqueeze(0)
+        s = torch.full((1, 1, 1, 1), sigma).type_as(img)
+        outs.append(model(img, s)[0].permute(1, 2, 0))
+    return torch.stack(outs, dim=3)
+
+
+def ffdnet_rgb_denoise_full_tensor(x, yall, Phiall, sigma, model, useGPU=True, lr_=1e-6,
+                                   updata_=False, update_per_iter=4, losses=None):
+    """x[H,W,3,B], yall[h,w,4], Phiall[h,w,B,4].  With ``updata_`` runs
+    ``update_per_iter`` Adam steps on the measurement loss first (fresh optimizer
+    per call, :251) and returns ``(outv, model)``."""
+    if updata_:
+        model.train()
+        opt = torch.optim.Adam(model.parameters(), lr=lr_)
+        mse = nn.MSELoss()
+        for _ in range(update_per_iter):
+            xb = _ffdnet_frames(x, sigma, model)
+            xall = rgb_to_bayer4(xb)                                  # :275-278
+            up_meas = torch.sum(xall * Phiall, dim=2)                 # :289
+            loss = mse(up_meas, yall)                                 # :291
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            if losses is not None:
+                losses.append(float(loss.detach()))
+        model.eval()
+        with torch.no_grad():                                          # reference keeps autograd on (:303-315); values equal
+            outv = _ffdnet_frames(x, sigma, model)
+            if losses is not None:
+                losses.append(float(mse(torch.sum(rgb_to_bayer4(outv) * Phiall, dim=2), yall)))
+        return outv, model
+    with torch.no_grad():
+        return _ffdnet_frames(x, sigma, model)
+
+
+def fastdvdnet_seqdenoise(seq, noise_std, windsize, model):
+    """fastdvdnet.py:82-146 — circular temporal window, reflect pad to x4."""
+    N, C, H, W = seq.shape
+    hw = (windsize - 1) // 2
+    out = torch.empty((N, C, H, W))
+    noise_map = noise_std.expand((1, 1, H, W))
+    wpad, hpad = (-W) % 4, (-H) % 4
+    if wpad or hpad:
+        noise_map = F.pad(noise_map, (0, wpad, 0, hpad), mode="reflect")
+    for f in range(N):
+        idx = (torch.arange(f, f + windsize) - hw) % N                 # :115
+        ns = seq[idx].reshape((1, -1, H, W))
+        if wpad or hpad:
+            ns = F.pad(ns, (0, wpad, 0, hpad), mode="reflect")
+        den = model(ns, noise_map)
+        out[f] = den[0, :, :H, :W]
+    return out
+
+
+def fastdvdnet_denoiser_full_tensor_v2(vnoisy, sigma, y_bayer=None, Phi=None, model=None, useGPU=True,
+                                       lr_=1e-6, updata_=False, update_per_iter=1, gray=False,
+                                       update_times=-1, losses=None):
+    """vnoisy[H,W,3,B]; y_bayer[h,w,4]; Phi[h,w,B,4]; ``model`` exposes ``.module``.
+
+    Fine-tune quirk reproduced verbatim (test_fastdvdnet.py:359 with
+    utils/utils_image.py:183-192): the helper returns ``meas + noise``, so the
+    training input is ``vnoisy + float32(float64(vnoisy) + N(0,(5/255)^2))``
+    = 2*vnoisy + noise, the noise drawn from the GLOBAL numpy RNG."""
+    noisestd = torch.FloatTensor([sigma])
+    if updata_:
+        n_update_iter, lr_all = ([update_per_iter], [lr_]) if isinstance(update_per_iter, int) else (update_per_iter, lr_)
+        mse = nn.MSELoss()
+        v = vnoisy.permute(3, 2, 0, 1)                                   # [B,3,H,W]
+        noise = np.random.normal(0, 5 / 255, tuple(v.shape))             # utils_image.py:186
+        v_plus = v + torch.from_numpy(v.detach().numpy() + noise).float()  # :359
+        Phi_bayer = fourCh2OneCh(Phi)                                     # :362
+        y_one = fourCh2OneCh(y_bayer)                                     # :363
+        model.train()
+        for m in model.module.modules():                                  # :376-379 BN frozen
+            if isinstance(m, nn.BatchNorm2d):
+                m.eval()
+        for lr_i, nit in zip(lr_all, n_update_iter):
+            opt = torch.optim.Adam(filter(lambda p: p.requires_grad, model.parameters()), lr=lr_i)
+            for _ in range(nit):
+                N, C, H, W = v.shape
+                noise_map = noisestd.expand((1, 1, H, W))
+                frames = []
+                for f in range(N):
+                    idx = (torch.arange(f, f + NUM_IN_FR_EXT) - 2) % N
+                    frames.append(model(v_plus[idx].reshape((1, -1, H, W)), noise_map)[0])
+                outv = torch.stack(frames, 0).permute(2, 3, 1, 0)          # [H,W,3,B]
+                x_bayer = gen_bayer_img(outv, 1)                           # :428
+                up_meas = torch.sum(x_bayer * Phi_bayer, dim=2)            # :430
+                loss = mse(up_meas, y_one)                                 # :431
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+                if losses is not None:
+                    losses.append(float(loss.detach()))
+        with torch.no_grad():                                              # :453-458, on the CLEAN input
+            outv = fastdvdnet_seqdenoise(v, noisestd, NUM_IN_FR_EXT, model).permute(2, 3, 1, 0)
+            if losses is not None:
+                losses.append(float(mse(torch.sum(rgb_to_bayer4(outv) * Phi, dim=2), y_bayer)))
+        return outv, model
+    model.eval()
+    with torch.no_grad():
+        v = vnoisy.permute(3, 2, 0, 1)
+        return fastdvdnet_seqdenoise(v, noisestd, NUM_IN_FR_EXT, model).permute(2, 3, 1, 0)

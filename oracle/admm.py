@@ -1,0 +1,162 @@
+"""Oracle: the two ADMM solvers (the hot loop), restated on CPU.
+
+Test infrastructure.  Restates
+  * ``admm_denoise_bayer_demosaic_pre``  dvp_linear_inv_2_stage_ADMM_tensor_online.py:326-552 (stage 1, 'tv')
+  * ``twoStageAdmm_denoise_bayer``       dvp_linear_inv_2_stage_ADMM_tensor_online.py:40-324  (stage 2)
+including the iteration-0 aliasing of ``xall``/``theta_all``:
+both names are bound to ``x0all`` until ``torch.clip`` / the TV result rebinds
+``theta_all``, so in stage 2 the k=0 assignment ``theta_all[...,c] = ...``
+also overwrites ``xall`` and ``b`` receives ``theta_unclipped - theta_clipped``.
+Only the branches reachable from the three scripts are restated
+('tv', 'ffdnet_color', 'fastdvd_color', Malvar demosaic, model_demosaic=None).
+"""
+import numpy as np
+import torch
+
+from . import BAYER
+from .adapters import fastdvdnet_denoiser_full_tensor_v2, ffdnet_rgb_denoise_full_tensor
+from .demosaic import malvar2004_tensor
+from .iqa import compare_psnr, compare_ssim
+from .sci_ops import (bayer_merge, bayer_split_init, masks_CFA_Bayer_tensor, project_stage1, project_stage2)
+from .tv_chambolle import denoise_tv_chambolle
+
+
+def _listify(sigma, iter_max):
+    if not isinstance(sigma, list):
+        sigma = [sigma]
+    if not isinstance(iter_max, list):
+        iter_max = [iter_max] * len(sigma)
+    return sigma, iter_max
+
+
+def _tv(cube4, nrow, ncol, nmask, stops=None):
+    v = cube4.reshape([nrow // 2, ncol // 2, nmask * 4]).numpy()
+    out, st = denoise_tv_chambolle(v, 0.1, n_iter_max=5, multichannel=True, return_stops=True)
+    if stops is not None:
+        stops.append(st)
+    return torch.from_numpy(out).reshape([nrow // 2, ncol // 2, nmask, 4])
+
+
+def _final_iqa(X_orig, x_bayer_np, nmask):
+    psnr_, ssim_ = [], []
+    if X_orig is not None:
+        for t in range(nmask):
+            psnr_.append(compare_psnr(X_orig[:, :, t], x_bayer_np[:, :, t], data_range=1.))
+            ssim_.append(compare_ssim(X_orig[:, :, t], x_bayer_np[:, :, t], data_range=1.))
+    return psnr_, ssim_
+
+
+def admm_denoise_bayer_demosaic_pre(y_bayer, Phi_bayer, _lambda=1, gamma=0.01, denoiser='tv', iter_max=50,
+                                    noise_estimate=True, sigma=None, x0_bayer=None, X_orig=None, model=None,
+                                    show_iqa=True, trace=None, **_unused):
+    """Stage 1 (TV warm start).  Returns (x_bayer_np[H,W,B], psnr_, ssim_, psnr_all)."""
+    if denoiser != 'tv':
+        raise ValueError('oracle restates only the tv branch of stage 1 (the only one the scripts reach)')
+    y_bayer = torch.from_numpy(np.ascontiguousarray(y_bayer))
+    Phi_bayer = torch.from_numpy(np.ascontiguousarray(Phi_bayer))
+    sigma, iter_max = _listify(sigma, iter_max)
+    nrow, ncol, nmask = Phi_bayer.shape
+    yall, Phiall, Phi_sumall, x0all = bayer_split_init(y_bayer, Phi_bayer, x0_bayer)
+    xall = x0all
+    ball = torch.zeros_like(x0all)
+    theta_all = x0all
+    psnr_all = []
+    k = 0
+    for idx, nsig in enumerate(sigma):
+        for it in range(iter_max[idx]):
+            project_stage1(theta_all, ball, yall, Phiall, Phi_sumall, _lambda, gamma, out=xall)   # :389-391
+            theta_all = _tv(xall - ball, nrow, ncol, nmask,
+                            None if trace is None else trace.setdefault('tv_stops', []))          # :403-407
+            theta_all = torch.clip(theta_all, 0, 1)                                               # :501
+            ball = ball - (xall - theta_all)                                                      # :503
+            if show_iqa and X_orig is not None:
+                psnr_all.append(compare_psnr(X_orig, bayer_merge(xall).numpy(), data_range=1.))   # :507-512
+            k += 1
+    x_bayer_np = bayer_merge(xall).numpy()
+    psnr_, ssim_ = _final_iqa(X_orig, x_bayer_np, nmask)
+    if trace is not None:
+        trace.update(theta=theta_all.clone(), b=ball.clone(), x=xall.clone())
+    return x_bayer_np, psnr_, ssim_, psnr_all
+
+
+def twoStageAdmm_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, gamma=0.01, denoiser='tv', iter_max=50,
+                               noise_estimate=True, sigma=None, x0_bayer=None, X_orig=None, model_denoise=None,
+                               model_demosaic=None, show_iqa=True, demosaic_method='malvar2004', lr_=1e-6,
+                               inital_iter=1, interval_iter=5, logf=None, useGPU=True, update_=False,
+                               update_per_iter=1, close_form_demosaic=False, large=False, update_times=-1,
+                               args=None, trace=None):
+    """Stage 2.  'tv' -> 4-tuple; deep denoisers -> (xbgr3_np[H,W,3,B], x_bayer_np, psnr_, ssim_,
+    psnr_all, model_denoise, model_demosaic)."""
+    if model_demosaic is not None or close_form_demosaic:
+        raise NotImplementedError('oracle: DDnet / closed-form demosaic are SURVEY §8(f) "next" rows')
+    y_bayer = torch.from_numpy(np.ascontiguousarray(y_bayer))
+    Phi_bayer = torch.from_numpy(np.ascontiguousarray(Phi_bayer))
+    sigma, iter_max = _listify(sigma, iter_max)
+    nrow, ncol, nmask = Phi_bayer.shape
+    yall, Phiall, Phi_sumall, x0all = bayer_split_init(y_bayer, Phi_bayer, x0_bayer)
+    xall = x0all                                                     # :87
+    ball = torch.zeros_like(x0all)
+    theta_all = x0all                                                # :89 (same tensor)
+    R_m, G_m, B_m = masks_CFA_Bayer_tensor((nrow, ncol))
+    w = torch.zeros([nrow, ncol, 3, nmask])
+    alpha = 0.01 if denoiser == 'tv' else 1                          # :101-104
+    rou = 0.55 if denoiser == 'fastdvd_color' else 1                 # :106-109
+    tau = 100
+    psnr_all = []
+    k = 0
+    update_i = 0
+    xbgr3 = None
+    for idx, nsig in enumerate(sigma):
+        for it in range(iter_max[idx]):
+            project_stage2(theta_all, ball, yall, Phiall, Phi_sumall, alpha, rou, out=xall)      # :128-140
+            if denoiser == 'tv':
+                TV = True
+                theta_all = _tv(xall + (1 / rou) * ball, nrow, ncol, nmask)                      # :153-160
+            elif denoiser.lower() in ('ffdnet_color', 'fastdvd_color'):
+                TV = False
+                x_rgb = torch.zeros([nrow, ncol, 3, nmask])
+                x_bayer = bayer_merge(xall + (1 / rou) * ball)                                   # :169-172
+                if demosaic_method == 'malvar2004':                                              # :185-191 (App. D.2)
+                    for t in range(nmask):
+                        x_rgb[:, :, :, t] = malvar2004_tensor(x_bayer[:, :, t], R_m, G_m, B_m)
+                x_rgb_w = x_rgb - (1 / tau) * w                                                  # :198
+                do_update = update_ and k > inital_iter and k % interval_iter == 0
+                losses = None if trace is None else trace.setdefault('losses', [])
+                if denoiser.lower() == 'ffdnet_color':
+                    if do_update:
+                        xbgr3, model_denoise = ffdnet_rgb_denoise_full_tensor(
+                            x_rgb_w, yall, Phiall, nsig, model_denoise, useGPU, lr_, update_, update_per_iter,
+                            losses=losses)
+                    else:
+                        xbgr3 = ffdnet_rgb_denoise_full_tensor(x_rgb_w, yall, Phiall, nsig, model_denoise, useGPU, lr_)
+                else:
+                    if do_update and (update_i < update_times or update_times < 0):             # :247
+                        xbgr3, model_denoise = fastdvdnet_denoiser_full_tensor_v2(
+                            x_rgb_w, nsig, yall, Phiall, model_denoise, useGPU, lr_, update_, update_per_iter,
+                            update_times=update_times, losses=losses)
+                        update_i += 1
+                    else:
+                        xbgr3 = fastdvdnet_denoiser_full_tensor_v2(x_rgb_w, nsig, yall, Phiall, model_denoise,
+                                                                   useGPU, lr_)
+                theta_all[..., 0] = xbgr3[0::2, 0::2, 0, :]                                      # :206-209
+                theta_all[..., 1] = xbgr3[0::2, 1::2, 1, :]
+                theta_all[..., 2] = xbgr3[1::2, 0::2, 1, :]
+                theta_all[..., 3] = xbgr3[1::2, 1::2, 2, :]
+            else:
+                raise ValueError('Unsupported denoiser {}!'.format(denoiser))
+            theta_all = torch.clip(theta_all, 0, 1)                                              # :265
+            ball = ball + (xall - theta_all)                                                     # :267
+            if not TV:
+                w = w + (x_rgb - xbgr3)                                                          # :271
+            if show_iqa and X_orig is not None:
+                psnr_all.append(compare_psnr(X_orig, bayer_merge(theta_all).numpy(), data_range=1.))  # :275-280
+            if trace is not None and trace.get('per_iter') is not None:
+                trace['per_iter'].append(dict(theta=theta_all.clone(), b=ball.clone(), x=xall.clone()))
+            k += 1
+    x_bayer_np = bayer_merge(theta_all).numpy()
+    psnr_, ssim_ = _final_iqa(X_orig, x_bayer_np, nmask)
+    if trace is not None:
+        trace.update(theta=theta_all.clone(), b=ball.clone(), x=xall.clone(), w=w.clone())
+    if denoiser == 'tv':
+        return x_bayer_np, psnr_, ssim_, psnr_all
+    return xbgr3.detach().numpy(), x_bayer_np, psnr_, ssim_, psnr_all, model_denoise, model_demosaic
