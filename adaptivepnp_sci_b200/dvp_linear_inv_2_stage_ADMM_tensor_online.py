@@ -1,0 +1,237 @@
+"""The two ADMM solvers of AdaptivePnP_SCI, B200-native.
+
+Drop-in for the reference module of the same name: ``admm_denoise_bayer_demosaic_pre``
+(dvp_linear_inv_2_stage_ADMM_tensor_online.py:326-552, stage 1 / TV warm start) and
+``twoStageAdmm_denoise_bayer`` (:40-324, stage 2 / plug-and-play deep denoiser with
+online adaptation) keep the reference's names, argument order, defaults, array
+layouts at the boundary, return tuples and ``ValueError`` for unknown denoisers.
+
+What differs is everything between the boundary and the hardware:
+
+* the solver state (theta, b, x, Phi, w, x_rgb) lives on the device in frame-planar
+  layout for the whole reconstruction; the host sees scalars only (the reference
+  copies the cube D2H every iteration for PSNR and D2H+H2D for TV);
+* one fused kernel per ADMM step instead of ~40 ATen launches:
+  ``sci_project_stage1/2`` (A, At, projection, optional PSNR),
+  ``sci_tv_chambolle2d`` (TV prior + clip + dual update, early stop on device),
+  ``sci_malvar2004`` (merge + demosaic of all frames + ``-w/tau``),
+  ``sci_dual_update_rgb`` (Bayer sampling + clip + both dual updates + PSNR);
+* the denoisers run through the native conv kernels (see ``ffdnet_adapter`` /
+  ``fastdvdnet_adapter``).
+
+There is no CPU or PyTorch-op fallback: without the CUDA library the import fails.
+"""
+import numpy as np
+import torch
+
+from . import iqa, ops
+from .utils_image import cuda2np, np2tch_cuda  # noqa: F401  (np2tch_cuda is imported from here by the scripts)
+
+__all__ = ["admm_denoise_bayer_demosaic_pre", "twoStageAdmm_denoise_bayer", "np2tch_cuda", "cuda2np"]
+
+
+def _as_list(sigma, iter_max):
+    if not isinstance(sigma, list):
+        sigma = [sigma]
+    if not isinstance(iter_max, list):
+        iter_max = [iter_max] * len(sigma)
+    return sigma, iter_max
+
+
+def _to_device(a):
+    if torch.is_tensor(a):
+        return a.to(device="cuda", dtype=torch.float32).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+
+
+class _Problem:
+    """Device-resident problem data shared by both stages (K0)."""
+
+    def __init__(self, y_bayer, Phi_bayer, x0_bayer, X_orig):
+        y = _to_device(y_bayer)
+        phi_hwb = _to_device(Phi_bayer)
+        x0 = None if x0_bayer is None else _to_device(x0_bayer)
+        self.H, self.W, self.B = phi_hwb.shape
+        if self.H % 2 or self.W % 2:
+            raise ValueError("Bayer measurements need even height and width, got %dx%d" % (self.H, self.W))
+        self.y = y
+        self.phi, self.phisum, self.theta = ops.bayer_split_init(y, phi_hwb, x0)
+        self.x = torch.empty_like(self.theta)
+        self.b = torch.zeros_like(self.theta)
+        self.npix = self.H * self.W
+        self.orig = None
+        if X_orig is not None:
+            self.orig = ops.pixlast_to_planar(_to_device(X_orig), 1, self.B).view(self.B, self.H, self.W)
+
+    def to_hwb(self, cube):
+        """planar [B,H,W] -> numpy [H,W,B] (the layout the reference returns)."""
+        return cuda2np(ops.planar_to_pixlast(cube, 1, self.B).view(self.H, self.W, self.B))
+
+    def frame_iqa(self, cube, x_np, X_orig):
+        psnr_, ssim_ = [], []
+        if X_orig is not None:
+            sse = torch.zeros(self.B, dtype=torch.float64, device=cube.device)
+            ops.psnr_accum(cube, self.orig, sse)
+            p = iqa.psnr_from_sse(sse.cpu().numpy(), self.npix)
+            for t in range(self.B):
+                psnr_.append(p[t])
+                ssim_.append(iqa.ssim(X_orig[:, :, t], x_np[:, :, t], data_range=1.))
+        return psnr_, ssim_
+
+
+def _log_iterations(denoiser, sched, psnr_all, noise_estimate, logf):
+    """Same lines as dvp...online.py:282-304 / :513-535, emitted after the loop (the PSNRs are
+    accumulated on the device; reading them per iteration would force a sync per iteration)."""
+    for k, nsig in enumerate(sched):
+        if (k + 1) % 2 != 0 or k >= len(psnr_all):
+            continue
+        if not noise_estimate and nsig is not None:
+            if nsig < 1:
+                msg = '  ADMM-{0} iteration {1: 3d}, sigma {2: 3g}/255, PSNR {3:2.2f} dB.'.format(
+                    denoiser.upper(), k + 1, nsig * 255, psnr_all[k])
+            else:
+                msg = '  ADMM-{0} iteration {1: 3d}, sigma {2: 3g}, PSNR {3:2.2f} dB.'.format(
+                    denoiser.upper(), k + 1, nsig, psnr_all[k])
+        else:
+            msg = '  ADMM-{0} iteration {1: 3d}, PSNR {2:2.2f} dB.'.format(denoiser.upper(), k + 1, psnr_all[k])
+        print(msg)
+        if logf is not None:
+            logf.write(msg + ' \n')
+
+
+def admm_denoise_bayer_demosaic_pre(y_bayer, Phi_bayer, _lambda=1, gamma=0.01,
+                                    denoiser='tv', iter_max=50, noise_estimate=True, sigma=None,
+                                    x0_bayer=None,
+                                    X_orig=None, model=None, show_iqa=True, demosaic_method='malvar2004', lr_=0.000001,
+                                    inital_iter=1, interval_iter=5, logf=None, useGPU=True, device=0, update_=False,
+                                    update_per_iter=1):
+    """Stage 1: ADMM/GAP with the TV prior (warm start).
+
+    y_bayer [H,W], Phi_bayer [H,W,B] float32 numpy.  Returns
+    ``(x_bayer_np[H,W,B], psnr_[B], ssim_[B], psnr_all[iters])`` like the reference's
+    'tv' branch (:548-549).  Only 'tv' is reachable from ADMM_TV_Warm_Start_save.py; the deep
+    branches of this function in the reference duplicate stage 2 without the second dual
+    variable and are served by ``twoStageAdmm_denoise_bayer``.
+    """
+    if denoiser != 'tv':
+        raise ValueError('Unsupported denoiser {}!'.format(denoiser))
+    sigma, iter_max = _as_list(sigma, iter_max)
+    pb = _Problem(y_bayer, Phi_bayer, x0_bayer, X_orig)
+    ws = ops.TvWorkspace(pb.H, pb.W, pb.B, pb.y.device)
+    n_total = int(sum(iter_max))
+    want_iqa = bool(show_iqa and X_orig is not None)
+    sse = torch.zeros(max(n_total, 1), dtype=torch.float64, device=pb.y.device) if want_iqa else None
+    b_next = torch.empty_like(pb.b)
+    theta, b, x = pb.theta, pb.b, pb.x
+    sched = []
+    k = 0
+    for idx, nsig in enumerate(sigma):
+        for _ in range(iter_max[idx]):
+            # x = (theta+b) + lambda*At((y - A(theta+b))/(Phi_sum+gamma))            (:389-391) [+ PSNR of x, :507-512]
+            ops.project_stage1(theta, b, pb.phi, pb.y, pb.phisum, x, _lambda, gamma,
+                               orig=pb.orig if want_iqa else None, sse=sse[k:k + 1] if want_iqa else None)
+            # theta = clip(TV(x - b)); b = b - (x - theta)                               (:403-407, :501-503)
+            ops.tv_chambolle(x, b, -1.0, theta, b_next, -1.0, True, ws, weight=0.1, n_iter_max=5)
+            b, b_next = b_next, b
+            sched.append(nsig)
+            k += 1
+    psnr_all = []
+    if want_iqa:
+        psnr_all = list(iqa.psnr_from_sse(sse.cpu().numpy()[:n_total], pb.npix * pb.B))
+        _log_iterations(denoiser, sched, psnr_all, noise_estimate, logf)
+    x_bayer_np = pb.to_hwb(x)                                           # stage 1 returns x, not theta (:538-541)
+    psnr_, ssim_ = pb.frame_iqa(x, x_bayer_np, X_orig)
+    return x_bayer_np, psnr_, ssim_, psnr_all
+
+
+def twoStageAdmm_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, gamma=0.01,
+                               denoiser='tv', iter_max=50, noise_estimate=True, sigma=None,
+                               x0_bayer=None,
+                               X_orig=None, model_denoise=None, model_demosaic=None, show_iqa=True,
+                               demosaic_method='malvar2004', lr_=0.000001,
+                               inital_iter=1, interval_iter=5, logf=None, useGPU=True, update_=False, update_per_iter=1,
+                               close_form_demosaic=False,
+                               large=False, update_times=-1, args=None, grad_sync=None):
+    """Stage 2: ADMM with a plug-in denoiser ('tv', 'ffdnet_color', 'fastdvd_color') and optional
+    online fine-tuning of the denoiser on the measurement-consistency loss.
+
+    Returns the reference's tuples: 'tv' -> ``(x_bayer_np, psnr_, ssim_, psnr_all)`` (:322-323),
+    otherwise ``(xbgr3_np[H,W,3,B], x_bayer_np[H,W,B], psnr_, ssim_, psnr_all, model_denoise,
+    model_demosaic)`` (:324).  ``grad_sync`` (extension, default None) is a callable applied to the
+    flat gradient bucket before each Adam step; the multi-GPU driver passes an NCCL all-reduce.
+    """
+    name = denoiser if denoiser == 'tv' else str(denoiser).lower()
+    if name not in ('tv', 'ffdnet_color', 'fastdvd_color'):
+        raise ValueError('Unsupported denoiser {}!'.format(denoiser))
+    if model_demosaic is not None or close_form_demosaic:
+        raise NotImplementedError("deep demosaicking (DDnet) and the closed-form demosaic branch are not built yet "
+                                  "(SURVEY §8(f) rows 1 and 3); pass model_demosaic=None")
+    sigma, iter_max = _as_list(sigma, iter_max)
+    pb = _Problem(y_bayer, Phi_bayer, x0_bayer, X_orig)
+    dev = pb.y.device
+    H, W, B = pb.H, pb.W, pb.B
+    alpha = 0.01 if name == 'tv' else 1                                  # :101-104
+    rou = 0.55 if name == 'fastdvd_color' else 1                         # :106-109
+    tau = 100                                                            # :110
+    inv_rou = float(np.float32(1 / rou))
+    n_total = int(sum(iter_max))
+    want_iqa = bool(show_iqa and X_orig is not None)
+    sse = torch.zeros(max(n_total, 1), dtype=torch.float64, device=dev) if want_iqa else None
+    theta, b, x = pb.theta, pb.b, pb.x
+    xhat = None
+    if name == 'tv':
+        ws = ops.TvWorkspace(H, W, B, dev)
+        b_next = torch.empty_like(b)
+    else:
+        from . import fastdvdnet_adapter, ffdnet_adapter
+        w = torch.zeros((B, 3, H, W), dtype=torch.float32, device=dev)
+        x_rgb = torch.empty_like(w)
+        u = torch.empty_like(w)
+        if demosaic_method != 'malvar2004':
+            # In the reference every other value silently leaves x_rgb at zeros (``.lower`` is compared
+            # unbound, :187,:233 — SURVEY App. D.2); that degenerate loop is refused rather than reproduced.
+            raise ValueError("demosaic_method must be 'malvar2004'")
+    sched = []
+    k = 0
+    update_i = 0
+    for idx, nsig in enumerate(sigma):
+        for _ in range(iter_max[idx]):
+            # p = theta - b/rho ; x = p + Phi*((y - A p)/(alpha*rho + Phi_sum))                     (:128-140)
+            ops.project_stage2(theta, b, pb.phi, pb.y, pb.phisum, x, alpha, rou)
+            if name == 'tv':
+                # theta = clip(TV(x + b/rho)); b = b + (x - theta)                                   (:153-160, :265-267)
+                ops.tv_chambolle(x, b, inv_rou, theta, b_next, 1.0, True, ws, weight=0.1, n_iter_max=5)
+                b, b_next = b_next, b
+                if want_iqa:
+                    ops.psnr_accum(theta.view(1, -1), pb.orig.view(1, -1), sse[k:k + 1])
+            else:
+                # x_rgb = Malvar(merge(x + b/rho)) for all frames ; u = x_rgb - w/tau                 (:169-198)
+                ops.malvar2004(x, b, inv_rou, w, 1 / tau, x_rgb, u)
+                do_update = bool(update_ and k > inital_iter and k % interval_iter == 0)
+                if name == 'ffdnet_color':
+                    xhat = ffdnet_adapter.denoise_planar(u, pb, nsig, model_denoise, lr_, do_update, update_per_iter,
+                                                         grad_sync=grad_sync)
+                else:
+                    do_update = do_update and (update_i < update_times or update_times < 0)   # :247
+                    xhat = fastdvdnet_adapter.denoise_planar(u, pb, nsig, model_denoise, lr_, do_update,
+                                                             update_per_iter, grad_sync=grad_sync)
+                    update_i += int(do_update)
+                # theta = clip(RGGB samples of xhat) ; b += x - theta ; w += x_rgb - xhat [+ PSNR]    (:206-209, :265-280)
+                ops.dual_update_rgb(xhat, x_rgb, w, x, b, theta, first_iter=(k == 0),
+                                    orig=pb.orig if want_iqa else None, sse=sse[k:k + 1] if want_iqa else None)
+            sched.append(nsig)
+            k += 1
+    psnr_all = []
+    if want_iqa:
+        psnr_all = list(iqa.psnr_from_sse(sse.cpu().numpy()[:n_total], pb.npix * B))
+        _log_iterations(denoiser, sched, psnr_all, noise_estimate, logf)
+    elif X_orig is None and logf is not None:
+        for kk, nsig in enumerate(sched):                                                        # :307-309
+            if (kk + 2) % 2 == 0 and nsig is not None:
+                logf.write('  ADMM-{0} iteration {1: 3d}, sigma {2: 3g}/255 \n'.format(denoiser.upper(), kk + 2, nsig * 255))
+    x_bayer_np = pb.to_hwb(theta)                                        # stage 2 returns theta (:312-315)
+    psnr_, ssim_ = pb.frame_iqa(theta, x_bayer_np, X_orig)
+    if name == 'tv':
+        return x_bayer_np, psnr_, ssim_, psnr_all
+    xbgr3_np = cuda2np(ops.planar_to_pixlast(xhat, 3, B).view(H, W, 3, B))
+    return xbgr3_np, x_bayer_np, psnr_, ssim_, psnr_all, model_denoise, model_demosaic

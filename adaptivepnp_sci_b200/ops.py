@@ -1,0 +1,123 @@
+"""Thin tensor-level wrappers over the C ABI (planar device layouts).
+
+Every function launches hand-written sm_100a kernels on the current CUDA stream
+through ``_lib``; nothing here computes with PyTorch ops.  Layouts: Bayer-domain
+cubes ``[B,H,W]``, RGB cubes ``[B,3,H,W]``, planes ``[H,W]`` (see
+``include/sci_b200.h``).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr, require_cuda_f32, stream
+
+
+def pixlast_to_planar(t_in, C, B):
+    """[P..., C, B] (reference pixel-last) -> [B, C, P...] planar.  Bit-exact remap."""
+    require_cuda_f32(t_in)
+    P = t_in.numel() // (C * B)
+    out = torch.empty((B, C, P), dtype=torch.float32, device=t_in.device)
+    call("sci_pixlast_to_planar", ptr(t_in), ptr(out), P, C, B, stream())
+    return out
+
+
+def planar_to_pixlast(t_in, C, B):
+    """[B, C, P] planar -> [P, C, B] pixel-last.  Bit-exact remap."""
+    require_cuda_f32(t_in)
+    P = t_in.numel() // (C * B)
+    out = torch.empty((P, C, B), dtype=torch.float32, device=t_in.device)
+    call("sci_planar_to_pixlast", ptr(t_in), ptr(out), P, C, B, stream())
+    return out
+
+
+def bayer_split_init(y, phi_hwb, x0_hwb=None):
+    """K0.  y [H,W], phi_hwb [H,W,B], optional warm start x0_hwb [H,W,B] ->
+    (phi [B,H,W], phisum [H,W], theta0 [B,H,W])."""
+    require_cuda_f32(y, phi_hwb, x0_hwb)
+    H, W, B = phi_hwb.shape
+    dev = y.device
+    phi = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+    phisum = torch.empty((H, W), dtype=torch.float32, device=dev)
+    theta0 = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+    call("sci_bayer_split_init", ptr(y), ptr(phi_hwb), ptr(x0_hwb), ptr(phi), ptr(phisum), ptr(theta0), H, W, B, stream())
+    return phi, phisum, theta0
+
+
+def project_stage1(theta, b, phi, y, phisum, x_out, lambda_, gamma, orig=None, sse=None):
+    require_cuda_f32(theta, b, phi, y, phisum, x_out, orig)
+    B = phi.shape[0]
+    npix = y.numel()
+    call("sci_project_stage1", ptr(theta), ptr(b), ptr(phi), ptr(y), ptr(phisum), ptr(x_out), npix, B,
+         float(lambda_), float(gamma), ptr(orig), ptr(sse), stream())
+    return x_out
+
+
+def project_stage2(theta, b, phi, y, phisum, x_out, alpha, rho):
+    require_cuda_f32(theta, b, phi, y, phisum, x_out)
+    B = phi.shape[0]
+    npix = y.numel()
+    call("sci_project_stage2", ptr(theta), ptr(b), ptr(phi), ptr(y), ptr(phisum), ptr(x_out), npix, B,
+         float(alpha), float(rho), stream())
+    return x_out
+
+
+class TvWorkspace:
+    """Scratch for sci_tv_chambolle2d (per-block energy partials + stop indices)."""
+
+    def __init__(self, H, W, B, device):
+        self.nbytes = int(_lib.lib.sci_tv_workspace_bytes(H, W, B))
+        self.buf = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
+        self.shape = (H, W, B)
+
+
+def tv_chambolle(x, b, c_b, theta_out, b_out, s_b, clip, ws, weight=0.1, eps=2.0e-4, n_iter_max=5, nstop_out=None):
+    """K4 fused:  theta = [clip] TV(x + c_b*b);  b_out = b + s_b*(x - theta).  b/b_out may be None."""
+    require_cuda_f32(x, b, theta_out, b_out)
+    B, H, W = x.shape
+    assert ws.shape == (H, W, B)
+    call("sci_tv_chambolle2d", ptr(x), ptr(b), float(c_b), ptr(theta_out), ptr(b_out), float(s_b), int(bool(clip)),
+         H, W, B, float(weight), float(eps), int(n_iter_max), ptr(ws.buf), ctypes.c_size_t(ws.nbytes),
+         ptr(nstop_out), stream())
+    return theta_out
+
+
+def malvar2004(x, b, c_b, w, inv_tau, x_rgb_out, u_out):
+    """K6.  mosaic = x + c_b*b (b may be None) -> x_rgb [B,3,H,W]; u = x_rgb - inv_tau*w (if w given)."""
+    require_cuda_f32(x, b, w, x_rgb_out, u_out)
+    B, H, W = x.shape
+    call("sci_malvar2004", ptr(x), ptr(b), float(c_b), ptr(w), float(inv_tau), ptr(x_rgb_out), ptr(u_out), H, W, B,
+         stream())
+    return x_rgb_out, u_out
+
+
+def dual_update_rgb(xhat, x_rgb, w, x, b, theta, first_iter, orig=None, sse=None):
+    """K3/K5 fused, in place on (w, b, theta)."""
+    require_cuda_f32(xhat, x_rgb, w, x, b, theta, orig)
+    B, H, W = x.shape
+    call("sci_dual_update_rgb", ptr(xhat), ptr(x_rgb), ptr(w), ptr(x), ptr(b), ptr(theta), int(bool(first_iter)),
+         H, W, B, ptr(orig), ptr(sse), stream())
+
+
+def rgb_to_bayer(rgb):
+    require_cuda_f32(rgb)
+    B, _, H, W = rgb.shape
+    out = torch.empty((B, H, W), dtype=torch.float32, device=rgb.device)
+    call("sci_rgb_to_bayer", ptr(rgb), ptr(out), H, W, B, stream())
+    return out
+
+
+def bayer_to_rgb_sparse(mosaic):
+    require_cuda_f32(mosaic)
+    B, H, W = mosaic.shape
+    out = torch.empty((B, 3, H, W), dtype=torch.float32, device=mosaic.device)
+    call("sci_bayer_to_rgb_sparse", ptr(mosaic), ptr(out), H, W, B, stream())
+    return out
+
+
+def psnr_accum(a, orig, sse_per_frame):
+    """sse_per_frame[t] += sum (a[t]-orig[t])^2  (float64 [B] device tensor)."""
+    require_cuda_f32(a, orig)
+    B = a.shape[0]
+    npix = a.numel() // B
+    call("sci_psnr_accum", ptr(a), ptr(orig), npix, B, ptr(sse_per_frame), stream())

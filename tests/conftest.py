@@ -1,0 +1,33 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # The C-ABI library is a build artefact (git-ignored); make sure it exists before anything imports the package.
+    lib = os.path.join(ROOT, "adaptivepnp_sci_b200", "libsci_b200.so")
+    if not os.path.exists(lib):
+        sys.path.insert(0, os.path.join(ROOT, "adaptivepnp_sci_b200", "csrc"))
+        import build as _build
+        _build.build()
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return GOLDEN
+
+
+@pytest.fixture(scope="session")
+def cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
