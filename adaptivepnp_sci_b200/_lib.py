@@ -26,6 +26,7 @@ _i = ctypes.c_int
 _l = ctypes.c_long
 _f = ctypes.c_float
 _sz = ctypes.c_size_t
+_d = ctypes.c_double
 
 # name -> argtypes (restype int unless noted).  tests/test_capi_symbols.py checks this table against
 # include/sci_b200.h so a symbol cannot be declared without being bound, or bound without being declared.
@@ -46,6 +47,26 @@ PROTOTYPES = {
     "sci_bayer4_to_mosaic": [_p, _p, _i, _i, _i, _p],
     "sci_mosaic_to_bayer4": [_p, _p, _i, _i, _i, _p],
     "sci_psnr_accum": [_p, _p, _l, _i, _p, _p],
+    "sci_conv3x3_fwd": [_p, _i, _p],
+    "sci_conv3x3_dgrad": [_p, _i, _p],
+    "sci_conv3x3_wgrad": [_p, _i, _p],
+    "sci_conv_pack_weights": [_p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _p],
+    "sci_conv_unpack_wgrad": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "sci_bn_fold": [_p, _p, _p, _p, _f, _p, _p, _i, _i, _p],
+    "sci_act_bwd": [_p, _p, _p, _l, _i, _i, _p, _p, _p],
+    "sci_bn_param_grad": [_p, _p, _p, _p, _p, _p, _i, _p],
+    "sci_nhwc_pixel_unshuffle": [_p, _p, _i, _i, _i, _i, _p],
+    "sci_nhwc_dilate2": [_p, _p, _i, _i, _i, _i, _p],
+    "sci_ffdnet_pack_input": [_p, _f, _p, _i, _i, _i, _i, _i, _p],
+    "sci_ffdnet_unpack_output": [_p, _p, _i, _i, _i, _i, _p],
+    "sci_ffdnet_unpack_output_grad": [_p, _p, _i, _i, _i, _i, _p],
+    "sci_fastdvd_pack_input": [_p, _f, _p, _i, _i, _i, _i, _i, _p],
+    "sci_fastdvd_output": [_p, _p, _p, _i, _i, _i, _i, _p],
+    "sci_fastdvd_output_grad": [_p, _p, _i, _i, _i, _i, _p],
+    "sci_fastdvd_pack_input_grad": [_p, _p, _i, _i, _i, _i, _i, _p],
+    "sci_fastdvd_noisy_input": [_p, _p, _p, _l, _p],
+    "sci_meas_loss_fwd_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "sci_adam_step": [_p, _p, _p, _p, _l, _d, _d, _d, _d, _i, _p],
 }
 _SPECIAL_RESTYPE = {"sci_last_error": ctypes.c_char_p, "sci_tv_workspace_bytes": _sz}
 

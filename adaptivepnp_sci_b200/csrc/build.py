@@ -23,7 +23,7 @@ COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-st
 SOURCES = [
     ("sci_ops.cu", ["--fmad=false"]),
     ("sci_tv.cu", ["--fmad=false"]),
-    ("sci_conv_ref.cu", ["--fmad=false"]),
+    ("sci_conv_ref.cu", []),
     ("sci_conv_tc.cu", []),
     ("sci_train.cu", ["--fmad=false"]),
 ]

@@ -174,45 +174,75 @@ extern "C" int sci_At(const float* y, long syh, long syw, const float* phi, long
 // frame: 3*B independent 128-bit loads in flight, v and phi stay in registers,
 // a single pass over the cubes (algorithmic 4 cubes + 2 planes).
 // ---------------------------------------------------------------------------
-template <int B>
-__global__ void __launch_bounds__(256) project_kernel_v4(const float* __restrict__ theta, const float* __restrict__ b,
-                                                          const float* __restrict__ phi, const float* __restrict__ y,
-                                                          const float* __restrict__ phisum, float* __restrict__ x,
-                                                          long npix, float c_b, float c_l, float c_den,
-                                                          const float* __restrict__ orig, double* __restrict__ sse) {
+template <int VEC> struct VecT;
+template <> struct VecT<1> { using type = float; };
+template <> struct VecT<2> { using type = float2; };
+template <> struct VecT<4> { using type = float4; };
+
+template <int VEC>
+__device__ __forceinline__ void load_vec(const float* p, float (&r)[VEC]) {
+    *reinterpret_cast<typename VecT<VEC>::type*>(r) = *reinterpret_cast<const typename VecT<VEC>::type*>(p);
+}
+template <int VEC>
+__device__ __forceinline__ void load_vec_stream(const float* p, float (&r)[VEC]) {
+    if constexpr (VEC == 4) {
+        const float4 t = ldg_stream4(p);
+        r[0] = t.x; r[1] = t.y; r[2] = t.z; r[3] = t.w;
+    } else {
+        *reinterpret_cast<typename VecT<VEC>::type*>(r) = __ldg(reinterpret_cast<const typename VecT<VEC>::type*>(p));
+    }
+}
+template <int VEC>
+__device__ __forceinline__ void store_vec(float* p, const float (&r)[VEC]) {
+    *reinterpret_cast<typename VecT<VEC>::type*>(p) = *reinterpret_cast<const typename VecT<VEC>::type*>(r);
+}
+
+// One thread owns VEC consecutive pixels of every frame: 3*B independent vector loads in flight,
+// v and phi stay in registers, a single pass over the cubes.  VEC is chosen by the launcher so that
+// small cubes still fill the 148 SMs (more, narrower threads) and large ones use 128-bit accesses.
+template <int B, int VEC>
+__global__ void __launch_bounds__(256) project_kernel_vec(const float* __restrict__ theta, const float* __restrict__ b,
+                                                           const float* __restrict__ phi, const float* __restrict__ y,
+                                                           const float* __restrict__ phisum, float* __restrict__ x,
+                                                           long npix, float c_b, float c_l, float c_den,
+                                                           const float* __restrict__ orig, double* __restrict__ sse) {
     __shared__ double red[32];
-    const long q = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const long q = ((long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
     double err = 0.0;
     if (q < npix) {
-        float4 v[B], ph[B];
+        float v[B][VEC], ph[B][VEC];
 #pragma unroll
         for (int t = 0; t < B; ++t) {
-            const float4 th = *reinterpret_cast<const float4*>(theta + t * npix + q);
-            const float4 bb = *reinterpret_cast<const float4*>(b + t * npix + q);
-            ph[t] = ldg_stream4(phi + t * npix + q);
-            v[t] = make_float4(th.x + c_b * bb.x, th.y + c_b * bb.y, th.z + c_b * bb.z, th.w + c_b * bb.w);
+            float th[VEC], bb[VEC];
+            load_vec<VEC>(theta + t * npix + q, th);
+            load_vec<VEC>(b + t * npix + q, bb);
+            load_vec_stream<VEC>(phi + t * npix + q, ph[t]);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) v[t][e] = th[e] + c_b * bb[e];
         }
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float acc[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
+#pragma unroll
+        for (int t = 0; t < B; ++t)
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[e] += v[t][e] * ph[t][e];
+        float yy[VEC], ps[VEC], r[VEC];
+        load_vec_stream<VEC>(y + q, yy);
+        load_vec_stream<VEC>(phisum + q, ps);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) r[e] = (yy[e] - acc[e]) / (ps[e] + c_den);
 #pragma unroll
         for (int t = 0; t < B; ++t) {
-            acc.x += v[t].x * ph[t].x; acc.y += v[t].y * ph[t].y;
-            acc.z += v[t].z * ph[t].z; acc.w += v[t].w * ph[t].w;
-        }
-        const float4 yy = ldg_stream4(y + q);
-        const float4 ps = ldg_stream4(phisum + q);
-        float4 r;
-        r.x = (yy.x - acc.x) / (ps.x + c_den); r.y = (yy.y - acc.y) / (ps.y + c_den);
-        r.z = (yy.z - acc.z) / (ps.z + c_den); r.w = (yy.w - acc.w) / (ps.w + c_den);
+            float o[VEC];
 #pragma unroll
-        for (int t = 0; t < B; ++t) {
-            float4 o;
-            o.x = v[t].x + c_l * (ph[t].x * r.x); o.y = v[t].y + c_l * (ph[t].y * r.y);
-            o.z = v[t].z + c_l * (ph[t].z * r.z); o.w = v[t].w + c_l * (ph[t].w * r.w);
-            *reinterpret_cast<float4*>(x + t * npix + q) = o;
+            for (int e = 0; e < VEC; ++e) o[e] = v[t][e] + c_l * (ph[t][e] * r[e]);
+            store_vec<VEC>(x + t * npix + q, o);
             if (orig) {
-                const float4 og = ldg_stream4(orig + t * npix + q);
-                const float d0 = o.x - og.x, d1 = o.y - og.y, d2 = o.z - og.z, d3 = o.w - og.w;
-                err += (double)(d0 * d0) + (double)(d1 * d1) + (double)(d2 * d2) + (double)(d3 * d3);
+                float og[VEC];
+                load_vec_stream<VEC>(orig + t * npix + q, og);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) { const float d = o[e] - og[e]; err += (double)(d * d); }
             }
         }
     }
@@ -255,19 +285,27 @@ static int project_launch(const float* theta, const float* b, const float* phi, 
     SCI_REQUIRE(theta && b && phi && y && phisum && x && npix > 0 && B > 0, "project: null/shape");
     SCI_REQUIRE(!orig || sse, "project: orig given without sse");
     cudaStream_t st = sci_stream(stream);
-    const bool vec = (npix % 4 == 0) && ((((uintptr_t)theta | (uintptr_t)b | (uintptr_t)phi | (uintptr_t)y |
-                                           (uintptr_t)phisum | (uintptr_t)x | (uintptr_t)orig) & 15) == 0);
-    const int grid4 = sci_ceil_div(npix / 4, 256);
-#define SCI_PROJ_CASE(BB) case BB: project_kernel_v4<BB><<<grid4, 256, 0, st>>>(theta, b, phi, y, phisum, x, npix, c_b, c_l, c_den, orig, sse); break;
+    const bool aligned = (npix % 4 == 0) && ((((uintptr_t)theta | (uintptr_t)b | (uintptr_t)phi | (uintptr_t)y |
+                                               (uintptr_t)phisum | (uintptr_t)x | (uintptr_t)orig) & 15) == 0);
+    // narrower threads for small cubes: keep >= ~4 blocks per SM in flight
+    const long want_threads = (long)SCI_NUM_SMS * 4 * 256;
+    const int vecw = (npix / 4 >= want_threads) ? 4 : (npix / 2 >= want_threads ? 2 : 1);
+#define SCI_PROJ_LAUNCH(BB, VV) project_kernel_vec<BB, VV><<<sci_ceil_div(npix / VV, 256), 256, 0, st>>>( \
+        theta, b, phi, y, phisum, x, npix, c_b, c_l, c_den, orig, sse)
+#define SCI_PROJ_CASE(BB) case BB: if (vecw == 4) SCI_PROJ_LAUNCH(BB, 4); else if (vecw == 2) SCI_PROJ_LAUNCH(BB, 2); \
+                                   else SCI_PROJ_LAUNCH(BB, 1); break;
     bool done = false;
-    if (vec) {
+    if (aligned) {
         done = true;
         switch (B) {
             SCI_PROJ_CASE(4) SCI_PROJ_CASE(8) SCI_PROJ_CASE(10) SCI_PROJ_CASE(12) SCI_PROJ_CASE(16)
+            case 24: if (vecw >= 2) SCI_PROJ_LAUNCH(24, 2); else SCI_PROJ_LAUNCH(24, 1); break;
+            case 32: SCI_PROJ_LAUNCH(32, 1); break;
             default: done = false;
         }
     }
 #undef SCI_PROJ_CASE
+#undef SCI_PROJ_LAUNCH
     if (!done)
         project_kernel_generic<<<sci_ceil_div(npix, 256), 256, 0, st>>>(theta, b, phi, y, phisum, x, npix, B, c_b, c_l,
                                                                          c_den, orig, sse);

@@ -1,0 +1,444 @@
+// Glue kernels of the denoiser engine: weight packing, BatchNorm folding, activation backward,
+// network-boundary packers (FFDNet pixel-(un)shuffle + sigma map, FastDVDnet circular frame
+// triples + residual output), the fused measurement-consistency loss, and Adam.
+// All HBM-bound elementwise / index-remap work; compiled with --fmad=false.
+#include "sci_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float rna_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
+// column of the GEMM output that holds PyTorch output channel co
+__device__ __forceinline__ int out_column(int co, int Co, int ps) {
+    return ps ? (co & 3) * (Co >> 2) + (co >> 2) : co;
+}
+
+__global__ void pack_weights_kernel(const float* __restrict__ w, float* __restrict__ packed, int Co, int Ci, int groups,
+                                    int Co_pad, int Ci_pad, int ps, const float* __restrict__ oscale, int tflip,
+                                    int round_tf32) {
+    const long total = (long)9 * Co_pad * Ci_pad;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int tap, col, ci;
+    if (!tflip) { ci = (int)(idx % Ci_pad); col = (int)((idx / Ci_pad) % Co_pad); tap = (int)(idx / ((long)Ci_pad * Co_pad)); }
+    else        { col = (int)(idx % Co_pad); ci = (int)((idx / Co_pad) % Ci_pad); tap = (int)(idx / ((long)Ci_pad * Co_pad)); }
+    float v = 0.f;
+    if (col < Co && ci < Ci) {
+        // invert the column permutation: which torch channel lives in this column?
+        const int co = ps ? (col % (Co >> 2)) * 4 + col / (Co >> 2) : col;
+        const int cig = Ci / groups, cog = Co / groups, g = co / cog;
+        if (ci / cig == g) {
+            const int src_tap = tflip ? 8 - tap : tap;
+            v = w[((long)co * cig + (ci - g * cig)) * 9 + src_tap];
+            if (tflip && oscale) v = v * oscale[col];
+        }
+    }
+    if (round_tf32) v = rna_tf32(v);
+    packed[idx] = v;
+}
+
+__global__ void unpack_wgrad_kernel(const float* __restrict__ packed, float* __restrict__ dw, int Co, int Ci, int groups,
+                                    int Co_pad, int Ci_pad, int ps) {
+    const int cig = Ci / groups, cog = Co / groups;
+    const long total = (long)Co * cig * 9;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int tap = (int)(idx % 9), cil = (int)((idx / 9) % cig), co = (int)(idx / (9L * cig));
+    const int ci = (co / cog) * cig + cil;
+    const int col = out_column(co, Co, ps);
+    dw[idx] = packed[((long)tap * Co_pad + col) * Ci_pad + ci];
+}
+
+__global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                               float* __restrict__ scale, float* __restrict__ shift, int C, int C_pad) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C_pad) return;
+    float s = 0.f, t = 0.f;
+    if (c < C) {
+        s = gamma[c] / sqrtf(var[c] + eps);
+        t = beta[c] - mean[c] * s;
+    }
+    scale[c] = s; shift[c] = t;
+}
+
+// dz = dy * (y > 0); s1[c] += sum dz; s2[c] += sum dz*y.   blockDim = (C, rows)
+__global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dz,
+                               long n_pix, int C, int relu, float* __restrict__ s1, float* __restrict__ s2) {
+    extern __shared__ float sm[];
+    const int c = threadIdx.x, row = threadIdx.y, rows = blockDim.y;
+    float a1 = 0.f, a2 = 0.f;
+    for (long p = (long)blockIdx.x * rows + row; p < n_pix; p += (long)gridDim.x * rows) {
+        const long o = p * C + c;
+        const float yv = y ? y[o] : 0.f;
+        float g = dy[o];
+        if (relu && !(yv > 0.f)) g = 0.f;
+        dz[o] = g;
+        a1 += g; a2 += g * yv;
+    }
+    if (s1 || s2) {
+        sm[(row * C + c) * 2] = a1; sm[(row * C + c) * 2 + 1] = a2;
+        __syncthreads();
+        if (row == 0) {
+            for (int r = 1; r < rows; ++r) { a1 += sm[(r * C + c) * 2]; a2 += sm[(r * C + c) * 2 + 1]; }
+            if (s1) atomicAdd(s1 + c, a1);
+            if (s2) atomicAdd(s2 + c, a2);
+        }
+    }
+}
+
+__global__ void bn_param_grad_kernel(const float* __restrict__ s1, const float* __restrict__ s2,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     float* __restrict__ dgamma, float* __restrict__ dbeta, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    dbeta[c] = s1[c];
+    const float g = gamma[c];
+    dgamma[c] = (g != 0.f) ? (s2[c] - beta[c] * s1[c]) / g : 0.f;
+}
+
+__global__ void pixel_unshuffle_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int H, int W, int C) {
+    // in [N][2H][2W][C] -> out [N][H][W][4C], column q*C + c, q = dy*2+dx
+    const long total = (long)N * H * W * 4 * C;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int col = (int)(idx % (4 * C));
+    const long p = idx / (4 * C);
+    const int w = (int)(p % W), h = (int)((p / W) % H), n = (int)(p / ((long)W * H));
+    const int q = col / C, c = col % C;
+    out[idx] = in[(((long)n * 2 * H + 2 * h + (q >> 1)) * 2 * W + 2 * w + (q & 1)) * C + c];
+}
+
+__global__ void dilate2_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int H, int W, int C) {
+    // out [N][2H][2W][C]: out[2h][2w] = in[h][w], zeros elsewhere
+    const long total = (long)N * 4 * H * W * C;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = (int)(idx % C);
+    const long p = idx / C;
+    const int w2 = (int)(p % (2 * W)), h2 = (int)((p / (2 * W)) % (2 * H)), n = (int)(p / (4L * W * H));
+    float v = 0.f;
+    if (!(w2 & 1) && !(h2 & 1)) v = in[(((long)n * H + (h2 >> 1)) * W + (w2 >> 1)) * C + c];
+    out[idx] = v;
+}
+
+// ---- FFDNet boundary -----------------------------------------------------------------------------
+__global__ void ffdnet_pack_kernel(const float* __restrict__ u, float sigma, float* __restrict__ out, int B, int H, int W,
+                                   int Cpad, int round_tf32) {
+    const int h2 = H >> 1, w2 = W >> 1;
+    const long total = (long)B * h2 * w2 * Cpad;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int k = (int)(idx % Cpad);
+    const long p = idx / Cpad;
+    const int w = (int)(p % w2), h = (int)((p / w2) % h2), n = (int)(p / ((long)w2 * h2));
+    float v = 0.f;
+    if (k < 12) {
+        const int c = k >> 2, dy = (k >> 1) & 1, dx = k & 1;
+        v = u[(((long)n * 3 + c) * H + 2 * h + dy) * W + 2 * w + dx];
+    } else if (k == 12) {
+        v = sigma;
+    }
+    if (round_tf32) v = rna_tf32(v);
+    out[idx] = v;
+}
+
+// xhat[n][c][2h+dy][2w+dx] = y[n][h][w][c*4+dy*2+dx]   (nn.PixelShuffle(2), network_ffdnet.py:66)
+__global__ void ffdnet_unpack_kernel(const float* __restrict__ y, float* __restrict__ xhat, int B, int H, int W, int Cpad) {
+    const long total = (long)B * 3 * H * W;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int wf = (int)(idx % W), hf = (int)((idx / W) % H), c = (int)((idx / ((long)W * H)) % 3);
+    const int n = (int)(idx / (3L * W * H));
+    const int k = c * 4 + (hf & 1) * 2 + (wf & 1);
+    xhat[idx] = y[(((long)n * (H >> 1) + (hf >> 1)) * (W >> 1) + (wf >> 1)) * Cpad + k];
+}
+
+// adjoint: dy[n][h][w][k] = dxhat[n][k>>2][2h+dy][2w+dx] for k < 12, 0 in the padded columns
+__global__ void ffdnet_unpack_grad_kernel(const float* __restrict__ dxhat, float* __restrict__ dy, int B, int H, int W,
+                                          int Cpad) {
+    const int h2 = H >> 1, w2 = W >> 1;
+    const long total = (long)B * h2 * w2 * Cpad;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int k = (int)(idx % Cpad);
+    const long p = idx / Cpad;
+    const int w = (int)(p % w2), h = (int)((p / w2) % h2), n = (int)(p / ((long)w2 * h2));
+    float v = 0.f;
+    if (k < 12) {
+        const int c = k >> 2, dy_ = (k >> 1) & 1, dx_ = k & 1;
+        v = dxhat[(((long)n * 3 + c) * H + 2 * h + dy_) * W + 2 * w + dx_];
+    }
+    dy[idx] = v;
+}
+
+// ---- FastDVDnet boundary --------------------------------------------------------------------------
+__global__ void fastdvd_pack_kernel(const float* __restrict__ frames, float sigma, float* __restrict__ out, int B, int H,
+                                    int W, int Cpad, int round_tf32) {
+    const long plane = (long)H * W;
+    const long total = (long)B * plane * Cpad;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int k = (int)(idx % Cpad);
+    const long p = (idx / Cpad) % plane;
+    const int f = (int)(idx / (Cpad * plane));
+    float v = 0.f;
+    if (k < 12) {
+        const int slot = k >> 2, c = k & 3;
+        if (c == 3) v = sigma;
+        else {
+            const int src = (f + slot - 1 + B) % B;      // circular window (fastdvdnet.py:115)
+            v = frames[((long)src * 3 + c) * plane + p];
+        }
+    }
+    if (round_tf32) v = rna_tf32(v);
+    out[idx] = v;
+}
+
+__global__ void fastdvd_pack_grad_kernel(const float* __restrict__ din, float* __restrict__ dframes, int B, int H, int W,
+                                         int Cpad, int accumulate) {
+    // dframes[j][c][p] (+)= sum_{slot} din[(j - slot + 1) mod B][p][slot*4 + c]
+    const long plane = (long)H * W;
+    const long total = (long)B * 3 * plane;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const long p = idx % plane;
+    const int c = (int)((idx / plane) % 3), j = (int)(idx / (3 * plane));
+    float v = accumulate ? dframes[idx] : 0.f;
+#pragma unroll
+    for (int slot = 0; slot < 3; ++slot) {
+        const int f = (j - slot + 1 + B) % B;
+        v += din[((long)f * plane + p) * Cpad + slot * 4 + c];
+    }
+    dframes[idx] = v;
+}
+
+__global__ void fastdvd_output_kernel(const float* __restrict__ frames, const float* __restrict__ y, float* __restrict__ out,
+                                      int B, int H, int W, int Cpad, int to_grad) {
+    const long plane = (long)H * W;
+    if (!to_grad) {
+        const long total = (long)B * 3 * plane;
+        const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+        if (idx >= total) return;
+        const long p = idx % plane;
+        const int c = (int)((idx / plane) % 3), f = (int)(idx / (3 * plane));
+        out[idx] = frames[idx] - y[((long)f * plane + p) * Cpad + c];            // models.py:196
+    } else {
+        // dy[f][p][c] = -dout[f][c][p] for c < 3, 0 for the padded columns   (frames = dout here)
+        const long total = (long)B * plane * Cpad;
+        const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+        if (idx >= total) return;
+        const int k = (int)(idx % Cpad);
+        const long p = (idx / Cpad) % plane;
+        const int f = (int)(idx / (Cpad * plane));
+        out[idx] = (k < 3) ? -frames[((long)f * 3 + k) * plane + p] : 0.f;
+    }
+}
+
+__global__ void noisy_input_kernel(const float* __restrict__ v, const double* __restrict__ noise, float* __restrict__ vplus,
+                                   long n) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float o = (float)((double)v[i] + noise[i]);      // float32(meas + noise), utils_image.py:188-192
+    vplus[i] = v[i] + o;                                    // test_fastdvdnet.py:359
+}
+
+// ---- measurement loss -------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) meas_loss_kernel(const float* __restrict__ xhat, const float* __restrict__ phi,
+                                                         const float* __restrict__ y, float* __restrict__ dxhat,
+                                                         double* __restrict__ loss, int H, int W, int B, float norm) {
+    __shared__ double red[32];
+    const long plane = (long)H * W;
+    const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    double err = 0.0;
+    if (p < plane) {
+        const int row = (int)(p / W), col = (int)(p % W);
+        const int c = (row & 1) + (col & 1);
+        float up = 0.f;
+        for (int t = 0; t < B; ++t) up += xhat[((long)t * 3 + c) * plane + p] * phi[t * plane + p];
+        const float diff = up - y[p];
+        err = (double)(diff * diff);
+        if (dxhat) {
+            const float g = norm * diff;                      // mse_loss backward: (2/N) * (input - target)
+            for (int t = 0; t < B; ++t) {
+                const float gv = g * phi[t * plane + p];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) dxhat[((long)t * 3 + k) * plane + p] = (k == c) ? gv : 0.f;
+            }
+        }
+    }
+    const double s = block_sum(err, red);
+    if (threadIdx.x == 0) atomicAdd(loss, s / (double)plane);
+}
+
+__global__ void adam_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
+                            float* __restrict__ v, long n, float one_m_beta1, float beta2, float one_m_beta2, float eps,
+                            float step_size, float bc2_sqrt) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float g = grad[i];
+    float mi = m[i], vi = v[i];
+    mi = mi + one_m_beta1 * (g - mi);                       // exp_avg.lerp_(grad, 1-beta1)
+    vi = vi * beta2 + one_m_beta2 * (g * g);                // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    param[i] = param[i] - step_size * (mi / denom);         // param.addcdiv_(exp_avg, denom, value=-step_size)
+    m[i] = mi; v[i] = vi;
+}
+
+inline int grid1d(long n, int block = 256) { return (int)((n + block - 1) / block); }
+
+}  // namespace
+
+extern "C" int sci_conv_pack_weights(const float* w, float* packed, int Co, int Ci, int groups, int Co_pad, int Ci_pad,
+                                     int ps, const float* oscale, int transpose_flip, int round_tf32, void* stream) {
+    SCI_REQUIRE(w && packed && Co > 0 && Ci > 0 && groups > 0 && Co % groups == 0 && Ci % groups == 0, "pack_weights");
+    SCI_REQUIRE(Co_pad >= Co && Ci_pad >= Ci && (!ps || Co % 4 == 0), "pack_weights: padding / pixel-shuffle");
+    SCI_REQUIRE(!ps || Co_pad == Co, "pack_weights: pixel-shuffle columns cannot be padded");
+    const long total = (long)9 * Co_pad * Ci_pad;
+    pack_weights_kernel<<<grid1d(total), 256, 0, sci_stream(stream)>>>(w, packed, Co, Ci, groups, Co_pad, Ci_pad, ps, oscale,
+                                                                       transpose_flip, round_tf32);
+    SCI_CHECK_LAUNCH("pack_weights");
+    return SCI_OK;
+}
+
+extern "C" int sci_conv_unpack_wgrad(const float* packed_dw, float* dw, int Co, int Ci, int groups, int Co_pad, int Ci_pad,
+                                     int ps, void* stream) {
+    SCI_REQUIRE(packed_dw && dw && Co > 0 && Ci > 0 && groups > 0 && Co_pad >= Co && Ci_pad >= Ci, "unpack_wgrad");
+    const long total = (long)Co * (Ci / groups) * 9;
+    unpack_wgrad_kernel<<<grid1d(total), 256, 0, sci_stream(stream)>>>(packed_dw, dw, Co, Ci, groups, Co_pad, Ci_pad, ps);
+    SCI_CHECK_LAUNCH("unpack_wgrad");
+    return SCI_OK;
+}
+
+extern "C" int sci_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                           float* scale, float* shift, int C, int C_pad, void* stream) {
+    SCI_REQUIRE(gamma && beta && mean && var && scale && shift && C > 0 && C_pad >= C, "bn_fold");
+    bn_fold_kernel<<<grid1d(C_pad, 128), 128, 0, sci_stream(stream)>>>(gamma, beta, mean, var, eps, scale, shift, C, C_pad);
+    SCI_CHECK_LAUNCH("bn_fold");
+    return SCI_OK;
+}
+
+extern "C" int sci_act_bwd(const float* dy, const float* y, float* dz, long n_pix, int C, int relu, float* s1, float* s2,
+                           void* stream) {
+    SCI_REQUIRE(dy && dz && n_pix > 0 && C > 0 && C <= 1024, "act_bwd");
+    SCI_REQUIRE(!(relu || s2) || y, "act_bwd: y needed for relu / s2");
+    const int rows = max(1, 256 / C);
+    const dim3 block(C, rows);
+    const int grid = (int)min((long)SCI_NUM_SMS * 8, (n_pix + rows - 1) / rows);
+    const size_t smem = (size_t)rows * C * 2 * sizeof(float);
+    act_bwd_kernel<<<grid, block, smem, sci_stream(stream)>>>(dy, y, dz, n_pix, C, relu, s1, s2);
+    SCI_CHECK_LAUNCH("act_bwd");
+    return SCI_OK;
+}
+
+extern "C" int sci_bn_param_grad(const float* s1, const float* s2, const float* gamma, const float* beta, float* dgamma,
+                                 float* dbeta, int C, void* stream) {
+    SCI_REQUIRE(s1 && s2 && gamma && beta && dgamma && dbeta && C > 0, "bn_param_grad");
+    bn_param_grad_kernel<<<grid1d(C, 128), 128, 0, sci_stream(stream)>>>(s1, s2, gamma, beta, dgamma, dbeta, C);
+    SCI_CHECK_LAUNCH("bn_param_grad");
+    return SCI_OK;
+}
+
+extern "C" int sci_nhwc_pixel_unshuffle(const float* in, float* out, int N, int H, int W, int C, void* stream) {
+    SCI_REQUIRE(in && out && N > 0 && H > 0 && W > 0 && C > 0, "pixel_unshuffle");
+    pixel_unshuffle_kernel<<<grid1d((long)N * H * W * 4 * C), 256, 0, sci_stream(stream)>>>(in, out, N, H, W, C);
+    SCI_CHECK_LAUNCH("pixel_unshuffle");
+    return SCI_OK;
+}
+
+extern "C" int sci_nhwc_dilate2(const float* in, float* out, int N, int H, int W, int C, void* stream) {
+    SCI_REQUIRE(in && out && N > 0 && H > 0 && W > 0 && C > 0, "dilate2");
+    dilate2_kernel<<<grid1d((long)N * 4 * H * W * C), 256, 0, sci_stream(stream)>>>(in, out, N, H, W, C);
+    SCI_CHECK_LAUNCH("dilate2");
+    return SCI_OK;
+}
+
+extern "C" int sci_ffdnet_pack_input(const float* u, float sigma, float* out, int B, int H, int W, int Cpad, int round_tf32,
+                                     void* stream) {
+    SCI_REQUIRE(u && out && B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && Cpad >= 13, "ffdnet_pack_input");
+    ffdnet_pack_kernel<<<grid1d((long)B * (H / 2) * (W / 2) * Cpad), 256, 0, sci_stream(stream)>>>(u, sigma, out, B, H, W, Cpad,
+                                                                                                 round_tf32);
+    SCI_CHECK_LAUNCH("ffdnet_pack_input");
+    return SCI_OK;
+}
+
+extern "C" int sci_ffdnet_unpack_output(const float* y, float* xhat, int B, int H, int W, int Cpad, void* stream) {
+    SCI_REQUIRE(y && xhat && B > 0 && H % 2 == 0 && W % 2 == 0 && Cpad >= 12, "ffdnet_unpack_output");
+    ffdnet_unpack_kernel<<<grid1d((long)B * 3 * H * W), 256, 0, sci_stream(stream)>>>(y, xhat, B, H, W, Cpad);
+    SCI_CHECK_LAUNCH("ffdnet_unpack_output");
+    return SCI_OK;
+}
+
+extern "C" int sci_ffdnet_unpack_output_grad(const float* dxhat, float* dy, int B, int H, int W, int Cpad, void* stream) {
+    SCI_REQUIRE(dy && dxhat && B > 0 && H % 2 == 0 && W % 2 == 0 && Cpad >= 12, "ffdnet_unpack_output_grad");
+    ffdnet_unpack_grad_kernel<<<grid1d((long)B * (H / 2) * (W / 2) * Cpad), 256, 0, sci_stream(stream)>>>(dxhat, dy, B, H, W,
+                                                                                                          Cpad);
+    SCI_CHECK_LAUNCH("ffdnet_unpack_output_grad");
+    return SCI_OK;
+}
+
+extern "C" int sci_fastdvd_pack_input(const float* frames, float sigma, float* out, int B, int H, int W, int Cpad,
+                                      int round_tf32, void* stream) {
+    SCI_REQUIRE(frames && out && B > 0 && H > 0 && W > 0 && Cpad >= 12, "fastdvd_pack_input");
+    fastdvd_pack_kernel<<<grid1d((long)B * H * W * Cpad), 256, 0, sci_stream(stream)>>>(frames, sigma, out, B, H, W, Cpad,
+                                                                                      round_tf32);
+    SCI_CHECK_LAUNCH("fastdvd_pack_input");
+    return SCI_OK;
+}
+
+extern "C" int sci_fastdvd_pack_input_grad(const float* din, float* dframes, int B, int H, int W, int Cpad, int accumulate,
+                                           void* stream) {
+    SCI_REQUIRE(din && dframes && B > 0 && H > 0 && W > 0 && Cpad >= 12, "fastdvd_pack_input_grad");
+    fastdvd_pack_grad_kernel<<<grid1d((long)B * 3 * H * W), 256, 0, sci_stream(stream)>>>(din, dframes, B, H, W, Cpad,
+                                                                                        accumulate);
+    SCI_CHECK_LAUNCH("fastdvd_pack_input_grad");
+    return SCI_OK;
+}
+
+extern "C" int sci_fastdvd_output(const float* frames, const float* y, float* out, int B, int H, int W, int Cpad,
+                                  void* stream) {
+    SCI_REQUIRE(frames && y && out && B > 0 && H > 0 && W > 0 && Cpad >= 3, "fastdvd_output");
+    fastdvd_output_kernel<<<grid1d((long)B * 3 * H * W), 256, 0, sci_stream(stream)>>>(frames, y, out, B, H, W, Cpad, 0);
+    SCI_CHECK_LAUNCH("fastdvd_output");
+    return SCI_OK;
+}
+
+extern "C" int sci_fastdvd_output_grad(const float* dout, float* dy, int B, int H, int W, int Cpad, void* stream) {
+    SCI_REQUIRE(dout && dy && B > 0 && H > 0 && W > 0 && Cpad >= 3, "fastdvd_output_grad");
+    fastdvd_output_kernel<<<grid1d((long)B * H * W * Cpad), 256, 0, sci_stream(stream)>>>(dout, nullptr, dy, B, H, W, Cpad, 1);
+    SCI_CHECK_LAUNCH("fastdvd_output_grad");
+    return SCI_OK;
+}
+
+extern "C" int sci_fastdvd_noisy_input(const float* v, const double* noise, float* vplus, long n, void* stream) {
+    SCI_REQUIRE(v && noise && vplus && n > 0, "fastdvd_noisy_input");
+    noisy_input_kernel<<<grid1d(n), 256, 0, sci_stream(stream)>>>(v, noise, vplus, n);
+    SCI_CHECK_LAUNCH("fastdvd_noisy_input");
+    return SCI_OK;
+}
+
+extern "C" int sci_meas_loss_fwd_bwd(const float* xhat, const float* phi, const float* y, float* dxhat, double* loss, int H,
+                                     int W, int B, void* stream) {
+    SCI_REQUIRE(xhat && phi && y && loss && H > 0 && W > 0 && B > 0, "meas_loss");
+    meas_loss_kernel<<<grid1d((long)H * W), 256, 0, sci_stream(stream)>>>(xhat, phi, y, dxhat, loss, H, W, B,
+                                                                          (float)(2.0 / ((double)H * (double)W)));
+    SCI_CHECK_LAUNCH("meas_loss");
+    return SCI_OK;
+}
+
+extern "C" int sci_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long n, double lr,
+                             double beta1, double beta2, double eps, int step, void* stream) {
+    SCI_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "adam_step");
+    // python-double scalars as in torch.optim.adam._single_tensor_adam
+    const double bc1 = 1.0 - pow(beta1, step), bc2 = 1.0 - pow(beta2, step);
+    const float step_size = (float)(lr / bc1);
+    const float bc2_sqrt = (float)sqrt(bc2);
+    adam_kernel<<<grid1d(n), 256, 0, sci_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, (float)(1.0 - beta1),
+                                                          (float)beta2, (float)(1.0 - beta2), (float)eps, step_size, bc2_sqrt);
+    SCI_CHECK_LAUNCH("adam_step");
+    return SCI_OK;
+}

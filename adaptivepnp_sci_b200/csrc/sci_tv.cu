@@ -164,29 +164,46 @@ __global__ void __launch_bounds__(TV_THREADS) tv_chambolle_kernel(
     }
 }
 
-// One thread per channel: fixed-order reduction of the block partials, then the reference's
-// stopping rule  |E_prev - E_i| < eps * E_init  (i >= 1).
-__global__ void tv_decide_kernel(const double* __restrict__ epart, int nblk, int nch, double weight, double eps,
-                                 double n_pix, int last_iter, int* __restrict__ nstop, int* __restrict__ nstop_out) {
-    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ch >= nch) return;
-    const int t = ch >> 2, phase = ch & 3;
-    double E_init = 0.0, E_prev = 0.0;
-    int stop = last_iter;
-    for (int k = 0; k < TV_MAX_UPD && k < last_iter; ++k) {
-        double sd = 0.0, sn = 0.0;
-        const double* pd = epart + ((((size_t)t * 4 + k) * 2 + 0) * 4 + phase) * nblk;
-        const double* pn = epart + ((((size_t)t * 4 + k) * 2 + 1) * 4 + phase) * nblk;
-        for (int j = 0; j < nblk; ++j) { sd += pd[j]; sn += pn[j]; }
-        double E = sd;
-        E += weight * sn;
-        E /= n_pix;
-        if (k == 0) { E_init = E; E_prev = E; }
-        else if (fabs(E_prev - E) < eps * E_init) { stop = k; break; }
-        else E_prev = E;
+// One block per channel: fixed-order (deterministic) reduction of the per-block partials, then the
+// reference's stopping rule  |E_prev - E_i| < eps * E_init  (i >= 1).
+constexpr int TV_DEC_THREADS = 128;
+__global__ void __launch_bounds__(TV_DEC_THREADS) tv_decide_kernel(const double* __restrict__ epart, int nblk, double weight,
+                                                                   double eps, double n_pix, int last_iter,
+                                                                   int* __restrict__ nstop, int* __restrict__ nstop_out) {
+    __shared__ double sm[TV_DEC_THREADS][8];
+    const int ch = blockIdx.x, t = ch >> 2, phase = ch & 3;
+    double acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {        // q = k*2 + kind
+        const double* p = epart + ((((size_t)t * 4 + (q >> 1)) * 2 + (q & 1)) * 4 + phase) * nblk;
+        double s = 0.0;
+        for (int j = threadIdx.x; j < nblk; j += TV_DEC_THREADS) s += p[j];
+        acc[q] = s;
     }
-    nstop[ch] = stop;
-    if (nstop_out) nstop_out[ch] = stop;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) sm[threadIdx.x][q] = acc[q];
+    __syncthreads();
+    for (int off = TV_DEC_THREADS / 2; off > 0; off >>= 1) {
+        if (threadIdx.x < off) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) sm[threadIdx.x][q] += sm[threadIdx.x + off][q];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double E_init = 0.0, E_prev = 0.0;
+        int stop = last_iter;
+        for (int k = 0; k < TV_MAX_UPD && k < last_iter; ++k) {
+            double E = sm[0][k * 2 + 0];
+            E += weight * sm[0][k * 2 + 1];
+            E /= n_pix;
+            if (k == 0) { E_init = E; E_prev = E; }
+            else if (fabs(E_prev - E) < eps * E_init) { stop = k; break; }
+            else E_prev = E;
+        }
+        nstop[ch] = stop;
+        if (nstop_out) nstop_out[ch] = stop;
+    }
 }
 
 }  // namespace
@@ -232,9 +249,8 @@ extern "C" int sci_tv_chambolle2d(const float* x, const float* b, float c_b, flo
                                                         epart, nullptr, 0);
     SCI_CHECK_LAUNCH("tv main pass");
     const int nch = B * 4;
-    tv_decide_kernel<<<sci_ceil_div(nch, 128), 128, 0, st>>>(epart, nblk, nch, (double)weight, (double)eps,
-                                                             (double)(H / 2) * (double)(W / 2), last_iter, nstop,
-                                                             nstop_out);
+    tv_decide_kernel<<<nch, TV_DEC_THREADS, 0, st>>>(epart, nblk, (double)weight, (double)eps,
+                                                     (double)(H / 2) * (double)(W / 2), last_iter, nstop, nstop_out);
     SCI_CHECK_LAUNCH("tv decide");
     tv_chambolle_kernel<<<grid, TV_THREADS, smem, st>>>(x, b, c_b, theta, b_out, s_b, clip, H, W, tau, tw, last_iter,
                                                         epart, nstop, 1);

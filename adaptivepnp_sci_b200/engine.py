@@ -1,0 +1,475 @@
+"""Native execution engine of the two denoisers (forward, backward, Adam) on the sm_100a kernels.
+
+The networks of the reference are short, fixed chains of 3x3 convolutions; this module is
+the host-side schedule that strings the C-ABI kernels together:
+
+* activations: NHWC fp32, channels padded to a multiple of 32 (16 for terminal outputs);
+* weights: PyTorch parameters (fp32 master copies, one flat bucket per model so that Adam
+  and the NCCL gradient all-reduce are single launches) re-packed into the implicit-GEMM
+  layout ``[9][Cout][Cin]`` whenever they change; BatchNorm (always in eval mode on this
+  path, test_fastdvdnet.py:376-379) is folded into the per-column scale/shift epilogue;
+* forward  = ``sci_conv3x3_fwd`` per layer (bias/BN + ReLU + skip-add + PixelShuffle fused);
+* backward = ``sci_act_bwd`` -> ``sci_conv3x3_wgrad`` -> ``sci_conv3x3_dgrad`` per layer, the
+  measurement loss and its gradient in one kernel (``sci_meas_loss_fwd_bwd``), one fused
+  ``sci_adam_step`` over the flat bucket.
+
+``SCI_CONV_IMPL`` selects the convolution kernels: ``tc`` (default; tcgen05/TMEM/TMA, TF32
+operands, fp32 accumulation) or ``ref`` (fp32 FFMA on-device reference).  Both are CUDA;
+there is no PyTorch/CPU path.
+"""
+import ctypes
+import os
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import call, ptr, stream
+
+_f32p = ctypes.c_void_p
+
+
+class ConvDesc(ctypes.Structure):
+    _fields_ = [("x", _f32p), ("w", _f32p), ("scale", _f32p), ("shift", _f32p), ("residual", _f32p), ("y", _f32p),
+                ("N", ctypes.c_int), ("H", ctypes.c_int), ("W", ctypes.c_int), ("Cin", ctypes.c_int),
+                ("Cout", ctypes.c_int), ("stride", ctypes.c_int), ("relu", ctypes.c_int),
+                ("pixel_shuffle", ctypes.c_int), ("round_tf32", ctypes.c_int)]
+
+
+class WgradDesc(ctypes.Structure):
+    _fields_ = [("x", _f32p), ("dz", _f32p), ("oscale", _f32p), ("dw", _f32p),
+                ("N", ctypes.c_int), ("H", ctypes.c_int), ("W", ctypes.c_int), ("Cin", ctypes.c_int),
+                ("Cout", ctypes.c_int), ("stride", ctypes.c_int)]
+
+
+IMPL_TC, IMPL_REF = 0, 1
+
+
+def default_impl():
+    v = os.environ.get("SCI_CONV_IMPL", "tc").lower()
+    if v not in ("tc", "ref"):
+        raise ValueError("SCI_CONV_IMPL must be 'tc' or 'ref'")
+    return IMPL_TC if v == "tc" else IMPL_REF
+
+
+def _pad(c, m):
+    return (c + m - 1) // m * m
+
+
+def _dp(t):
+    return None if t is None else t.data_ptr()
+
+
+class ParamBucket:
+    """All trainable parameters of a model as views of ONE flat fp32 CUDA buffer (+ flat grad, Adam moments)."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise _lib.SciError("model has no trainable parameters")
+        dev = self.params[0].device
+        if dev.type != "cuda":
+            raise _lib.SciError("move the model to the GPU before using it (model.cuda())")
+        self.sizes = [p.numel() for p in self.params]
+        self.offsets = [0]
+        for n in self.sizes:
+            self.offsets.append(self.offsets[-1] + _pad(n, 4))          # 16-byte aligned slots
+        self.total = self.offsets[-1]
+        self.flat = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        self.exp_avg = None
+        self.exp_avg_sq = None
+        self.step = 0
+        for p, off, n in zip(self.params, self.offsets, self.sizes):
+            view = self.flat[off:off + n].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+
+    def intact(self):
+        base = self.flat.data_ptr()
+        return all(p.data_ptr() == base + 4 * off for p, off in zip(self.params, self.offsets))
+
+    def grad_view(self, p):
+        i = next(k for k, q in enumerate(self.params) if q is p)
+        return self.grad[self.offsets[i]:self.offsets[i] + self.sizes[i]].view(p.shape)
+
+    def new_optimizer(self):
+        """Fresh Adam state, as the reference re-creates the optimizer on every adapter call."""
+        if self.exp_avg is None:
+            self.exp_avg = torch.zeros_like(self.flat)
+            self.exp_avg_sq = torch.zeros_like(self.flat)
+        else:
+            self.exp_avg.zero_()
+            self.exp_avg_sq.zero_()
+        self.step = 0
+
+    def adam_step(self, lr, betas=(0.9, 0.999), eps=1e-8):
+        self.step += 1
+        call("sci_adam_step", ptr(self.flat), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq), self.total,
+             float(lr), float(betas[0]), float(betas[1]), float(eps), self.step, stream())
+
+
+class ConvLayer:
+    """One 3x3 convolution of a network with its epilogue and its packed device-side state."""
+
+    def __init__(self, conv, bn=None, relu=False, stride=1, ps=False, terminal=False, cin_pad=None):
+        self.conv, self.bn, self.relu, self.stride, self.ps = conv, bn, relu, stride, ps
+        self.Co, self.groups = conv.out_channels, conv.groups
+        self.Ci = conv.in_channels
+        self.Ci_pad = cin_pad or _pad(self.Ci, 32)
+        self.Co_pad = self.Co if ps else _pad(self.Co, 16 if terminal else 32)
+        self.out_ch = self.Co_pad // 4 if ps else self.Co_pad       # channels of the stored output tensor
+        dev = conv.weight.device
+        self.wpk = torch.empty(9 * self.Co_pad * self.Ci_pad, dtype=torch.float32, device=dev)
+        self.wpk_t = None
+        self.has_affine = bn is not None or conv.bias is not None
+        self.scale = torch.empty(self.Co_pad, dtype=torch.float32, device=dev) if bn is not None else None
+        self.shift = torch.zeros(self.Co_pad, dtype=torch.float32, device=dev) if self.has_affine else None
+        self.s1 = self.s2 = None
+        self.dwpk = None
+
+    def refresh_fwd(self, tf32):
+        c = self.conv
+        if self.bn is not None:
+            bn = self.bn
+            call("sci_bn_fold", ptr(bn.weight.data), ptr(bn.bias.data), ptr(bn.running_mean), ptr(bn.running_var),
+                 float(bn.eps), ptr(self.scale), ptr(self.shift), self.Co, self.Co_pad, stream())
+        elif c.bias is not None:
+            self.shift[:self.Co].copy_(c.bias.data)
+        call("sci_conv_pack_weights", ptr(c.weight.data), ptr(self.wpk), self.Co, self.Ci, self.groups, self.Co_pad,
+             self.Ci_pad, int(self.ps), None, 0, int(tf32), stream())
+
+    def refresh_bwd(self, tf32):
+        """Data-gradient form of the weights: transposed, taps flipped, rows scaled by the folded BN scale."""
+        if self.wpk_t is None:
+            self.wpk_t = torch.empty_like(self.wpk)
+            self.s1 = torch.zeros(self.Co_pad, dtype=torch.float32, device=self.wpk.device)
+            self.s2 = torch.zeros(self.Co_pad, dtype=torch.float32, device=self.wpk.device)
+        call("sci_conv_pack_weights", ptr(self.conv.weight.data), ptr(self.wpk_t), self.Co, self.Ci, self.groups,
+             self.Co_pad, self.Ci_pad, int(self.ps), ptr(self.scale), 1, int(tf32), stream())
+
+
+class _Workspace:
+    """Named, shape-keyed device buffers that live as long as the engine (no allocation in steady state)."""
+
+    def __init__(self):
+        self.bufs = {}
+
+    def get(self, name, shape, device, zero=False):
+        key = (name, tuple(shape))
+        t = self.bufs.get(key)
+        if t is None:
+            t = torch.empty(shape, dtype=torch.float32, device=device)
+            self.bufs[key] = t
+            if zero:
+                t.zero_()
+        elif zero:
+            t.zero_()
+        return t
+
+
+class _EngineBase:
+    def __init__(self, module, layers):
+        self.module = module
+        self.layers = layers
+        self.impl = default_impl()
+        self.tf32 = self.impl == IMPL_TC
+        self.ws = _Workspace()
+        self.bucket = None
+        self._seen_version = None
+        self._bwd_valid = False
+        self.dirty = True
+        self.n_launch = 0
+
+    # ---- parameter state ------------------------------------------------------------------------------
+    def _version(self):
+        v = 0
+        for t in list(self.module.parameters()) + list(self.module.buffers()):
+            v += t._version
+        return v
+
+    def prepare(self, training=False):
+        """Make the packed device-side state consistent with the module's parameters."""
+        if self.bucket is None or not self.bucket.intact():
+            self.bucket = ParamBucket(list(self.module.parameters()))
+            self.dirty = True
+        if self.dirty or self._version() != self._seen_version:
+            for L in self.layers:
+                L.refresh_fwd(self.tf32)
+            self._seen_version = self._version()
+            self._bwd_valid = False
+            self.dirty = False
+        if training and not self._bwd_valid:
+            for L in self.layers:
+                L.refresh_bwd(self.tf32)
+            self._bwd_valid = True
+        if training and self.layers[0].dwpk is None:
+            total = sum(L.wpk.numel() for L in self.layers)
+            self.dw_flat = torch.zeros(total, dtype=torch.float32, device=self.layers[0].wpk.device)
+            off = 0
+            for L in self.layers:
+                L.dwpk = self.dw_flat[off:off + L.wpk.numel()]
+                off += L.wpk.numel()
+
+    # ---- kernel wrappers ------------------------------------------------------------------------------
+    def conv(self, L, x, N, H, W, y, residual=None, round_out=True):
+        d = ConvDesc(_dp(x), _dp(L.wpk), _dp(L.scale), _dp(L.shift), _dp(residual), _dp(y), N, H, W, L.Ci_pad, L.Co_pad,
+                     L.stride, int(L.relu), int(L.ps), int(self.tf32 and round_out))
+        call("sci_conv3x3_fwd", ctypes.byref(d), self.impl, stream())
+        self.n_launch += 1
+
+    def dgrad(self, L, dz, N, Ho, Wo, dx, residual=None):
+        """dx[N,Ho,Wo,Ci_pad] = conv(dz, packed transposed+flipped (and BN-scaled) weights) [+ residual]."""
+        d = ConvDesc(_dp(dz), _dp(L.wpk_t), None, None, _dp(residual), _dp(dx), N, Ho, Wo, L.Co_pad, L.Ci_pad, 1, 0, 0,
+                     int(self.tf32))
+        call("sci_conv3x3_dgrad", ctypes.byref(d), self.impl, stream())
+        self.n_launch += 1
+
+    def wgrad(self, L, x, dz, N, H, W):
+        d = WgradDesc(_dp(x), _dp(dz), _dp(L.scale), _dp(L.dwpk), N, H, W, L.Ci_pad, L.Co_pad, L.stride)
+        call("sci_conv3x3_wgrad", ctypes.byref(d), self.impl, stream())
+        self.n_launch += 1
+
+    def act_bwd(self, L, dy, y, n_pix, C):
+        """dz (in place over dy) = dy * relu'(y); accumulates the per-column sums needed for bias / BN grads."""
+        need = L.has_affine
+        if not (L.relu or need):
+            return dy
+        if need:
+            L.s1.zero_()
+            L.s2.zero_()
+        call("sci_act_bwd", ptr(dy), ptr(y) if (L.relu or L.bn is not None) else None, ptr(dy), n_pix, C, int(L.relu),
+             ptr(L.s1) if need else None, ptr(L.s2) if (need and L.bn is not None) else None, stream())
+        self.n_launch += 1
+        return dy
+
+    def param_grads(self, L):
+        """packed dW -> torch-layout grad slot; bias / BatchNorm affine grads from the column sums."""
+        b = self.bucket
+        call("sci_conv_unpack_wgrad", ptr(L.dwpk), ptr(b.grad_view(L.conv.weight)), L.Co, L.Ci, L.groups, L.Co_pad,
+             L.Ci_pad, int(L.ps), stream())
+        if L.bn is not None:
+            call("sci_bn_param_grad", ptr(L.s1), ptr(L.s2), ptr(L.bn.weight.data), ptr(L.bn.bias.data),
+                 ptr(b.grad_view(L.bn.weight)), ptr(b.grad_view(L.bn.bias)), L.Co, stream())
+        elif L.conv.bias is not None:
+            b.grad_view(L.conv.bias).copy_(L.s1[:L.Co])
+
+    def after_step(self):
+        """Parameters were updated in place by sci_adam_step (raw pointers): re-pack on next use."""
+        self.dirty = True
+
+
+class FFDNetEngine(_EngineBase):
+    """models/network_ffdnet.py:54-69 on the native kernels, all frames of a cube as one batch."""
+
+    def __init__(self, module):
+        convs = module.conv_layers()
+        layers = []
+        for i, c in enumerate(convs):
+            last = i == len(convs) - 1
+            layers.append(ConvLayer(c, None, relu=not last, terminal=last))
+        super().__init__(module, layers)
+        self.in_nc, self.out_nc = module.in_nc, module.out_nc
+        if (self.in_nc, self.out_nc) != (3, 3):
+            raise NotImplementedError("native FFDNet engine: colour model (in_nc=out_nc=3); the gray model of "
+                                      "BASELINE config 2 is a next-round row")
+
+    def forward(self, u, sigma, train=False):
+        """u [B,3,H,W] planar fp32 -> xhat [B,3,H,W].  train=True keeps every activation for backward()."""
+        B, _, H, W = u.shape
+        if H % 2 or W % 2:
+            raise _lib.SciError("native FFDNet engine needs even H and W (Bayer frames always are)")
+        self.prepare(training=train)
+        dev = u.device
+        h2, w2 = H // 2, W // 2
+        L0 = self.layers[0]
+        a = self.ws.get("in", (B, h2, w2, L0.Ci_pad), dev)
+        call("sci_ffdnet_pack_input", ptr(u), float(sigma), ptr(a), B, H, W, L0.Ci_pad, int(self.tf32), stream())
+        acts = [a]
+        for i, L in enumerate(self.layers):
+            name = ("act%d" % i) if train else ("pp%d" % (i % 2) if i < len(self.layers) - 1 else "tail")
+            y = self.ws.get(name, (B, h2, w2, L.Co_pad), dev)
+            self.conv(L, acts[-1], B, h2, w2, y, round_out=i < len(self.layers) - 1)
+            acts.append(y)
+        xhat = self.ws.get("xhat_train" if train else "xhat", (B, 3, H, W), dev)
+        call("sci_ffdnet_unpack_output", ptr(acts[-1]), ptr(xhat), B, H, W, self.layers[-1].Co_pad, stream())
+        if train:
+            self._saved = (acts, B, H, W)
+        return xhat
+
+    def backward(self, dxhat):
+        """Gradients of all parameters into the flat grad bucket, given d(loss)/d(xhat) [B,3,H,W]."""
+        acts, B, H, W = self._saved
+        dev = dxhat.device
+        h2, w2 = H // 2, W // 2
+        n_pix = B * h2 * w2
+        self.dw_flat.zero_()
+        Lt = self.layers[-1]
+        dy = self.ws.get("g_tail", (B, h2, w2, Lt.Co_pad), dev)
+        call("sci_ffdnet_unpack_output_grad", ptr(dxhat), ptr(dy), B, H, W, Lt.Co_pad, stream())
+        for i in range(len(self.layers) - 1, -1, -1):
+            L = self.layers[i]
+            dz = self.act_bwd(L, dy, acts[i + 1], n_pix, L.Co_pad)
+            self.wgrad(L, acts[i], dz, B, h2, w2)
+            if i > 0:
+                dx = self.ws.get("g%d" % (i % 2), (B, h2, w2, L.Ci_pad), dev)
+                self.dgrad(L, dz, B, h2, w2, dx)
+                dy = dx
+            self.param_grads(L)
+
+    def forward_nchw(self, x, sigma):
+        """Reference call convention model(img[N,3,H,W], sigma[N,1,1,1]) (test_ffdnet_ipol.py:350-351)."""
+        s = float(sigma.flatten()[0])
+        if sigma.numel() > 1 and not bool((sigma == sigma.flatten()[0]).all()):
+            raise NotImplementedError("one noise level per call on the native path")
+        return self.forward(x.contiguous().float(), s, train=False).clone()
+
+
+class _DenBlockLayers:
+    """The 16 convolutions of one DenBlock (packages/fastdvdnet/models.py:146-198) as ConvLayers."""
+
+    def __init__(self, block):
+        specs = block.conv_specs()
+        self.L = []
+        for i, (conv, bn, relu, stride, ps) in enumerate(specs):
+            self.L.append(ConvLayer(conv, bn, relu=relu, stride=stride, ps=ps, terminal=(i == len(specs) - 1)))
+
+
+class FastDVDnetEngine(_EngineBase):
+    """packages/fastdvdnet/models.py:200-253 + the circular sequence driver fastdvdnet.py:82-146, with every
+    temp1 triple evaluated once (B distinct triples instead of 3B; identical values)."""
+
+    def __init__(self, module):
+        self.t1 = _DenBlockLayers(module.temp1)
+        self.t2 = _DenBlockLayers(module.temp2)
+        super().__init__(module, self.t1.L + self.t2.L)
+
+    # ---- one DenBlock ---------------------------------------------------------------------------------
+    def _block_forward(self, tag, blk, frames, sigma, out, train):
+        B, _, H, W = frames.shape
+        dev = frames.device
+        L = blk.L
+        g = self.ws.get
+        keep = (lambda n: "%s_%s" % (tag, n)) if train else (lambda n: "inf_" + n)
+        h2, w2, h4, w4 = H // 2, W // 2, H // 4, W // 4
+        a_in = g(keep("in"), (B, H, W, L[0].Ci_pad), dev)
+        call("sci_fastdvd_pack_input", ptr(frames), float(sigma), ptr(a_in), B, H, W, L[0].Ci_pad, int(self.tf32), stream())
+        a0 = g(keep("a0"), (B, H, W, L[0].Co_pad), dev);   self.conv(L[0], a_in, B, H, W, a0)
+        x0 = g(keep("x0"), (B, H, W, L[1].Co_pad), dev);   self.conv(L[1], a0, B, H, W, x0)
+        d0a = g(keep("d0a"), (B, h2, w2, 64), dev);        self.conv(L[2], x0, B, H, W, d0a)
+        d0b = g(keep("d0b"), (B, h2, w2, 64), dev);        self.conv(L[3], d0a, B, h2, w2, d0b)
+        x1 = g(keep("x1"), (B, h2, w2, 64), dev);          self.conv(L[4], d0b, B, h2, w2, x1)
+        d1a = g(keep("d1a"), (B, h4, w4, 128), dev);       self.conv(L[5], x1, B, h2, w2, d1a)
+        d1b = g(keep("d1b"), (B, h4, w4, 128), dev);       self.conv(L[6], d1a, B, h4, w4, d1b)
+        x2 = g(keep("x2"), (B, h4, w4, 128), dev);         self.conv(L[7], d1b, B, h4, w4, x2)
+        u2a = g(keep("u2a"), (B, h4, w4, 128), dev);       self.conv(L[8], x2, B, h4, w4, u2a)
+        u2b = g(keep("u2b"), (B, h4, w4, 128), dev);       self.conv(L[9], u2a, B, h4, w4, u2b)
+        s1 = g(keep("s1"), (B, h2, w2, 64), dev);          self.conv(L[10], u2b, B, h4, w4, s1, residual=x1)
+        u1a = g(keep("u1a"), (B, h2, w2, 64), dev);        self.conv(L[11], s1, B, h2, w2, u1a)
+        u1b = g(keep("u1b"), (B, h2, w2, 64), dev);        self.conv(L[12], u1a, B, h2, w2, u1b)
+        s0 = g(keep("s0"), (B, H, W, 32), dev);            self.conv(L[13], u1b, B, h2, w2, s0, residual=x0)
+        o0 = g(keep("o0"), (B, H, W, 32), dev);            self.conv(L[14], s0, B, H, W, o0)
+        xo = g(keep("xo"), (B, H, W, L[15].Co_pad), dev);  self.conv(L[15], o0, B, H, W, xo, round_out=False)
+        call("sci_fastdvd_output", ptr(frames), ptr(xo), ptr(out), B, H, W, L[15].Co_pad, stream())
+        if train:
+            return dict(a_in=a_in, a0=a0, x0=x0, d0a=d0a, d0b=d0b, x1=x1, d1a=d1a, d1b=d1b, x2=x2, u2a=u2a, u2b=u2b,
+                        s1=s1, u1a=u1a, u1b=u1b, s0=s0, o0=o0, xo=xo)
+        return None
+
+    def forward(self, frames, sigma, train=False):
+        """frames [B,3,H,W] planar -> denoised [B,3,H,W] (whole circular sequence)."""
+        B, _, H, W = frames.shape
+        if H % 4 or W % 4:
+            raise NotImplementedError("native FastDVDnet engine needs H, W multiples of 4 (the reference reflect-pads, "
+                                      "fastdvdnet.py:119-127; the hot-path sizes never need it)")
+        self.prepare(training=train)
+        dev = frames.device
+        t1_out = self.ws.get("t1_out_train" if train else "t1_out", (B, 3, H, W), dev)
+        out = self.ws.get("out_train" if train else "out", (B, 3, H, W), dev)
+        s1 = self._block_forward("t1", self.t1, frames, sigma, t1_out, train)
+        s2 = self._block_forward("t2", self.t2, t1_out, sigma, out, train)
+        if train:
+            self._saved = (s1, s2, B, H, W)
+        return out
+
+    # ---- backward of one DenBlock -----------------------------------------------------------------------
+    def _block_backward(self, blk, S, dout, B, H, W, need_input_grad):
+        """dout [B,3,H,W] = d loss / d block output.  Returns d loss / d (packed input) [B,H,W,32] or None."""
+        L = blk.L
+        dev = dout.device
+        g = self.ws.get
+        h2, w2, h4, w4 = H // 2, W // 2, H // 4, W // 4
+        nf, nh, nq = B * H * W, B * h2 * w2, B * h4 * w4
+
+        def layer_bwd(i, dy, y, x_in, N, Hin, Win, n_out_pix, dx_name, dx_shape, residual=None, want_dx=True):
+            """Backward of layer i given dy wrt its stored output y; returns dx (grad wrt its input)."""
+            Li = L[i]
+            dz = self.act_bwd(Li, dy, y, n_out_pix, Li.Co_pad)
+            self.wgrad(Li, x_in, dz, N, Hin, Win)
+            dx = None
+            if want_dx:
+                dx = g(dx_name, dx_shape, dev)
+                if Li.stride == 2:
+                    dil = g("g_dil", (N, Hin, Win, Li.Co_pad), dev)
+                    call("sci_nhwc_dilate2", ptr(dz), ptr(dil), N, Hin // 2, Win // 2, Li.Co_pad, stream())
+                    self.dgrad(Li, dil, N, Hin, Win, dx, residual)
+                else:
+                    Ho, Wo = Hin, Win
+                    self.dgrad(Li, dz, N, Ho, Wo, dx, residual)
+            self.param_grads(Li)
+            return dx
+
+        # out = in1 - xo  ->  d xo = -dout (padded columns 0)
+        d_xo = g("g_xo", (B, H, W, L[15].Co_pad), dev)
+        call("sci_fastdvd_output_grad", ptr(dout), ptr(d_xo), B, H, W, L[15].Co_pad, stream())
+        d_o0 = layer_bwd(15, d_xo, S["xo"], S["o0"], B, H, W, nf, "g_f32a", (B, H, W, 32))
+        d_s0 = layer_bwd(14, d_o0, S["o0"], S["s0"], B, H, W, nf, "g_f32b", (B, H, W, 32))
+        # s0 = x0 + PS(conv13(u1b)): gradient of the GEMM output is the pixel-unshuffle of d_s0
+        d_c13 = g("g_h128", (B, h2, w2, 128), dev)
+        call("sci_nhwc_pixel_unshuffle", ptr(d_s0), ptr(d_c13), B, h2, w2, 32, stream())
+        d_u1b = layer_bwd(13, d_c13, None, S["u1b"], B, h2, w2, nh, "g_h64a", (B, h2, w2, 64))
+        d_u1a = layer_bwd(12, d_u1b, S["u1b"], S["u1a"], B, h2, w2, nh, "g_h64b", (B, h2, w2, 64))
+        d_s1 = layer_bwd(11, d_u1a, S["u1a"], S["s1"], B, h2, w2, nh, "g_h64a", (B, h2, w2, 64))
+        d_c10 = g("g_q256", (B, h4, w4, 256), dev)
+        call("sci_nhwc_pixel_unshuffle", ptr(d_s1), ptr(d_c10), B, h4, w4, 64, stream())
+        d_u2b = layer_bwd(10, d_c10, None, S["u2b"], B, h4, w4, nq, "g_q128a", (B, h4, w4, 128))
+        d_u2a = layer_bwd(9, d_u2b, S["u2b"], S["u2a"], B, h4, w4, nq, "g_q128b", (B, h4, w4, 128))
+        d_x2 = layer_bwd(8, d_u2a, S["u2a"], S["x2"], B, h4, w4, nq, "g_q128a", (B, h4, w4, 128))
+        d_d1b = layer_bwd(7, d_x2, S["x2"], S["d1b"], B, h4, w4, nq, "g_q128b", (B, h4, w4, 128))
+        d_d1a = layer_bwd(6, d_d1b, S["d1b"], S["d1a"], B, h4, w4, nq, "g_q128a", (B, h4, w4, 128))
+        # x1 feeds conv5 (stride 2) and the skip into s1: total gradient = dgrad + d_s1
+        d_x1 = layer_bwd(5, d_d1a, S["d1a"], S["x1"], B, h2, w2, nq, "g_h64b", (B, h2, w2, 64), residual=d_s1)
+        d_d0b = layer_bwd(4, d_x1, S["x1"], S["d0b"], B, h2, w2, nh, "g_h64a", (B, h2, w2, 64))
+        d_d0a = layer_bwd(3, d_d0b, S["d0b"], S["d0a"], B, h2, w2, nh, "g_h64b", (B, h2, w2, 64))
+        d_x0 = layer_bwd(2, d_d0a, S["d0a"], S["x0"], B, H, W, nh, "g_f32a", (B, H, W, 32), residual=d_s0)
+        d_a0 = layer_bwd(1, d_x0, S["x0"], S["a0"], B, H, W, nf, "g_f96", (B, H, W, L[0].Co_pad))
+        return layer_bwd(0, d_a0, S["a0"], S["a_in"], B, H, W, nf, "g_fin", (B, H, W, L[0].Ci_pad),
+                         want_dx=need_input_grad)
+
+    def backward(self, dout):
+        """Parameter gradients of both DenBlocks given d loss / d output [B,3,H,W]."""
+        s1, s2, B, H, W = self._saved
+        dev = dout.device
+        self.dw_flat.zero_()
+        d_in2 = self._block_backward(self.t2, s2, dout, B, H, W, need_input_grad=True)
+        # temp1 output j feeds slot (j - f + 1) of temp2 block f = j-1, j, j+1, and is `in1` of block j
+        d_t1 = self.ws.get("g_t1", (B, 3, H, W), dev)
+        d_t1.copy_(dout)
+        call("sci_fastdvd_pack_input_grad", ptr(d_in2), ptr(d_t1), B, H, W, self.t2.L[0].Ci_pad, 1, stream())
+        self._block_backward(self.t1, s1, d_t1, B, H, W, need_input_grad=False)
+
+    def forward_window(self, x, noise_map):
+        """Reference call convention model(x[1,15,H,W], noise_map[1,1,H,W]) for ONE 5-frame window
+        (packages/fastdvdnet/models.py:227-251); API parity only — the solvers use forward()."""
+        if x.shape[0] != 1 or x.shape[1] != 15:
+            raise _lib.SciError("expected x of shape [1,15,H,W]")
+        sigma = float(noise_map.flatten()[0])
+        frames = x.view(5, 3, x.shape[2], x.shape[3]).contiguous().float()
+        B, _, H, W = frames.shape
+        self.prepare(False)
+        dev = frames.device
+        t1 = self.ws.get("win_t1", (5, 3, H, W), dev)
+        out = self.ws.get("win_out", (5, 3, H, W), dev)
+        self._block_forward("w1", self.t1, frames, sigma, t1, False)      # centres 1,2,3 are the window's triples
+        self._block_forward("w2", self.t2, t1, sigma, out, False)         # block 2 reads temp1 results 1,2,3
+        return out[2:3].clone()

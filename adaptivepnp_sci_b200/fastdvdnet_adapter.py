@@ -1,0 +1,130 @@
+"""FastDVDnet plug-in denoiser adapter with online fine-tuning.
+
+Mirror of packages/fastdvdnet/test_fastdvdnet.py:325-500 (``fastdvdnet_denoiser_full_tensor_v2``) and
+packages/fastdvdnet/fastdvdnet.py:82-146 (``fastdvdnet_seqdenoise``): same names, arguments, layouts,
+return convention, and the same requirement that ``model`` exposes ``.module`` (the script wraps it in
+``nn.DataParallel``, two_stage_ADMM_Online_FastDVD_Warm.py:240-241; ``DataParallelLike`` is the
+single-device stand-in).
+
+Fine-tune semantics reproduced from the reference:
+* training input  vplus = v + float32(float64(v) + N(0,(5/255)^2))  — the helper at
+  utils/utils_image.py:183-192 returns ``meas + noise`` and :359 adds ``vnoisy`` again — with the noise
+  drawn on the HOST from the global numpy RNG (same call, same shape, same order), uploaded as float64;
+* BatchNorm layers frozen in eval mode, but their affine parameters are trained (:376-385);
+* fresh Adam state per (lr, n_iter) pair (:385); loss = MSE(sum_t Bayer(out_t)*Phi_t, y) over H*W (:428-431);
+* final denoise of the CLEAN input with the updated weights (:453-458).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import SciError, call, ptr, stream
+from .fastdvdnet_models import FastDVDnet
+
+NUM_IN_FR_EXT = 5          # test_fastdvdnet.py:23
+last_losses = []
+
+
+class DataParallelLike(nn.Module):
+    """Single-device stand-in for the ``nn.DataParallel`` wrapper of the script: ``.module`` attribute and
+    ``module.``-prefixed state-dict keys (so a DataParallel checkpoint loads), no scatter/gather (every
+    forward on the path is batch 1 in the reference, so DataParallel never split anything)."""
+
+    def __init__(self, module, device_ids=None):
+        super().__init__()
+        self.module = module
+
+    def forward(self, *a, **k):
+        return self.module(*a, **k)
+
+
+def _unwrap(model):
+    m = model.module if hasattr(model, "module") else model
+    if not isinstance(m, FastDVDnet):
+        raise SciError("fastdvdnet adapter expects adaptivepnp_sci_b200.fastdvdnet_models.FastDVDnet, got %s"
+                       % type(m).__name__)
+    return m
+
+
+def draw_finetune_noise(shape):
+    """The reference's host-side draw (utils/utils_image.py:186): float64 N(0, 5/255) from the global numpy RNG."""
+    return np.random.normal(0, 5 / 255, tuple(shape))
+
+
+def finetune_and_denoise(v, phi, y, sigma, model, lr, update_per_iter, grad_sync=None, noise=None):
+    """v [B,3,H,W], phi [B,H,W], y [H,W] planar; returns the denoised CLEAN sequence [B,3,H,W]."""
+    eng = _unwrap(model).engine()
+    B, _, H, W = v.shape
+    dev = v.device
+    if isinstance(update_per_iter, int):
+        n_update_iter, lr_all = [update_per_iter], [lr]                                  # :344-349
+    else:
+        n_update_iter, lr_all = list(update_per_iter), list(lr)
+    if noise is None:
+        noise = draw_finetune_noise((B, 3, H, W))
+    noise_d = torch.from_numpy(np.ascontiguousarray(noise, dtype=np.float64)).to(dev, non_blocking=True)
+    vplus = eng.ws.get("vplus", (B, 3, H, W), dev)
+    call("sci_fastdvd_noisy_input", ptr(v), ptr(noise_d), ptr(vplus), v.numel(), stream())    # :359
+    eng.prepare(training=True)
+    n_steps = int(sum(n_update_iter))
+    loss = torch.zeros(n_steps + 1, dtype=torch.float64, device=dev)
+    dout = eng.ws.get("dout", (B, 3, H, W), dev)
+    k = 0
+    for lr_i, nit in zip(lr_all, n_update_iter):
+        eng.bucket.new_optimizer()                                                        # :385
+        for _ in range(nit):
+            out = eng.forward(vplus, sigma, train=True)                                   # :412-419
+            call("sci_meas_loss_fwd_bwd", ptr(out), ptr(phi), ptr(y), ptr(dout), ptr(loss[k:k + 1]), H, W, B,
+                 stream())                                                                # :428-431
+            eng.backward(dout)                                                            # :445
+            if grad_sync is not None:
+                grad_sync(eng.bucket.grad)
+            eng.bucket.adam_step(lr_i)                                                    # :446
+            eng.after_step()
+            k += 1
+    out = eng.forward(v, sigma, train=False)                                              # :453-458
+    call("sci_meas_loss_fwd_bwd", ptr(out), ptr(phi), ptr(y), None, ptr(loss[n_steps:]), H, W, B, stream())
+    last_losses[:] = [loss]
+    return out
+
+
+def denoise_planar(u, pb, sigma, model, lr, do_update, update_per_iter, grad_sync=None, noise=None):
+    """Solver-facing entry: planar in, planar out (engine buffer, consumed before the next call)."""
+    if model is None:
+        raise SciError("model_denoise is required")
+    if do_update:
+        return finetune_and_denoise(u, pb.phi, pb.y, sigma, model, lr, update_per_iter, grad_sync, noise)
+    return _unwrap(model).engine().forward(u, sigma, train=False)
+
+
+def fastdvdnet_seqdenoise(seq, noise_std, windsize, model, train=None):
+    """fastdvdnet.py:82-146 — seq [N,3,H,W] -> [N,3,H,W], circular 5-frame window."""
+    if windsize != NUM_IN_FR_EXT:
+        raise NotImplementedError("window size 5 only")
+    out = _unwrap(model).engine().forward(seq.contiguous().float(), float(noise_std.flatten()[0]), train=False).clone()
+    return (out, model) if train else out
+
+
+def fastdvdnet_denoiser_full_tensor_v2(vnoisy, sigma, y_bayer=None, Phi=None, model=None,
+                                       useGPU=True, lr_=0.000001, updata_=False, update_per_iter=1, gray=False,
+                                       update_times=-1):
+    """vnoisy [H,W,3,B] CUDA, y_bayer [h,w,4], Phi [h,w,B,4] -> outv [H,W,3,B] (or ``(outv, model)``)."""
+    from .utils_image import fourCh2OneCh
+    if gray:
+        raise NotImplementedError("gray FastDVDnet is SURVEY §8(f).3 (next)")
+    vnoisy = vnoisy.contiguous().float()
+    H, W, _, B = vnoisy.shape
+    v = ops.pixlast_to_planar(vnoisy, 3, B).view(B, 3, H, W)
+    if updata_:
+        _ = model.module                                                                   # :377 requires the wrapper
+        phi = ops.pixlast_to_planar(fourCh2OneCh(Phi.contiguous().float()), 1, B).view(B, H, W)
+        y = fourCh2OneCh(y_bayer.contiguous().float())
+        out = finetune_and_denoise(v, phi, y, sigma, model, lr_, update_per_iter)
+        for val in last_losses[0].cpu().numpy():
+            print('loss:', end=' ')
+            print('tensor(%.4e)' % val)
+    else:
+        out = _unwrap(model).engine().forward(v, sigma, train=False)
+    outv = ops.planar_to_pixlast(out, 3, B).view(H, W, 3, B)
+    return (outv, model) if updata_ else outv

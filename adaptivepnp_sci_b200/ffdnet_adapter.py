@@ -1,0 +1,78 @@
+"""FFDNet plug-in denoiser adapter with online fine-tuning (``ffdnet_rgb_denoise_full_tensor``).
+
+Mirror of packages/ffdnet/test_ffdnet_ipol.py:240-359: same name, arguments, layouts and return
+convention.  The reference loops over the B frames calling ``model(img[1,3,H,W], sigma[1,1,1,1])``;
+here the whole cube is one batch through the native conv engine, the Bayer sampling, the sensing
+operator and the MSE of the measurement-consistency loss are one fused kernel that also emits the
+gradient, backward runs on the native dgrad/wgrad kernels and Adam is one launch over the flat
+parameter bucket (fresh optimizer state per call, like the reference's ``torch.optim.Adam`` at :251).
+"""
+import torch
+
+from . import ops
+from ._lib import SciError, call, ptr, stream
+from .network_ffdnet import FFDNet
+
+last_losses = []      # loss values of the most recent fine-tune call (the reference prints them, :298-299,:333-334)
+
+
+def _unwrap(model):
+    m = model.module if hasattr(model, "module") and not isinstance(model, FFDNet) else model
+    if not isinstance(m, FFDNet):
+        raise SciError("ffdnet adapter expects adaptivepnp_sci_b200.network_ffdnet.FFDNet, got %s" % type(m).__name__)
+    return m
+
+
+def finetune_and_denoise(u, phi, y, sigma, model, lr, update_per_iter, grad_sync=None):
+    """u [B,3,H,W], phi [B,H,W], y [H,W] planar.  update_per_iter Adam steps, then the eval forward."""
+    eng = _unwrap(model).engine()
+    B, _, H, W = u.shape
+    dev = u.device
+    eng.prepare(training=True)
+    eng.bucket.new_optimizer()
+    loss = torch.zeros(update_per_iter + 1, dtype=torch.float64, device=dev)
+    dxhat = eng.ws.get("dxhat", (B, 3, H, W), dev)
+    for it in range(update_per_iter):
+        xhat = eng.forward(u, sigma, train=True)                                        # :266-273
+        call("sci_meas_loss_fwd_bwd", ptr(xhat), ptr(phi), ptr(y), ptr(dxhat), ptr(loss[it:it + 1]), H, W, B,
+             stream())                                                                  # :275-291
+        eng.backward(dxhat)                                                             # :293
+        if grad_sync is not None:
+            grad_sync(eng.bucket.grad)
+        eng.bucket.adam_step(lr)                                                        # :294
+        eng.after_step()
+    out = eng.forward(u, sigma, train=False)                                            # :303-315 (model.eval())
+    call("sci_meas_loss_fwd_bwd", ptr(out), ptr(phi), ptr(y), None, ptr(loss[update_per_iter:]), H, W, B, stream())
+    last_losses[:] = [loss]          # device tensor; read lazily by whoever wants to print it
+    return out
+
+
+def denoise_planar(u, pb, sigma, model, lr, do_update, update_per_iter, grad_sync=None):
+    """Solver-facing entry: planar in, planar out (a view of an engine buffer, consumed before the next call)."""
+    if model is None:
+        raise SciError("model_denoise is required")
+    if do_update:
+        return finetune_and_denoise(u, pb.phi, pb.y, sigma, model, lr, update_per_iter, grad_sync)
+    return _unwrap(model).engine().forward(u, sigma, train=False)
+
+
+def ffdnet_rgb_denoise_full_tensor(x, yall, Phiall, sigma, model, useGPU=True, lr_=0.000001, updata_=False,
+                                   update_per_iter=4, device=0):
+    """x [H,W,3,B] CUDA, yall [h,w,4], Phiall [h,w,B,4], sigma float -> outv [H,W,3,B]
+    (or ``(outv, model)`` when ``updata_``), exactly the reference's convention (:356-359)."""
+    from .utils_image import fourCh2OneCh
+    x = x.contiguous().float()
+    H, W, _, B = x.shape
+    u = ops.pixlast_to_planar(x, 3, B).view(B, 3, H, W)
+    if updata_:
+        phi = ops.pixlast_to_planar(fourCh2OneCh(Phiall.contiguous().float()), 1, B).view(B, H, W)
+        y = fourCh2OneCh(yall.contiguous().float())
+        out = finetune_and_denoise(u, phi, y, sigma, model, lr_, update_per_iter)
+        vals = last_losses[0].cpu().numpy()
+        for v in vals:
+            print('loss:', end=' ')
+            print('tensor(%.4e)' % v)
+    else:
+        out = _unwrap(model).engine().forward(u, sigma, train=False)
+    outv = ops.planar_to_pixlast(out, 3, B).view(H, W, 3, B)
+    return (outv, model) if updata_ else outv

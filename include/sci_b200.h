@@ -143,6 +143,118 @@ int sci_mosaic_to_bayer4(const float* mosaic, float* stack, int h, int w, int B,
 int sci_psnr_accum(const float* a, const float* orig, long npix, int B, double* sse_per_frame,
                    void* stream);
 
+
+/* =========================================================================
+ * Denoiser networks: 3x3 convolutions as implicit GEMM (K7-K10)
+ * Replaces the cuDNN/ATen conv stacks of models/network_ffdnet.py:54-69 and
+ * packages/fastdvdnet/models.py:16-253 (forward) and the autograd graph built by
+ * the online fine-tune adapters (test_ffdnet_ipol.py:248-299, test_fastdvdnet.py:343-451).
+ *
+ * Activations are NHWC fp32 with the channel count padded to a multiple of 32
+ * (16 for pure outputs); padded channels hold zeros.  Weights are pre-packed by
+ * sci_conv_pack_weights into [9 taps][Cout][Cin] (Cin contiguous = K-major).
+ * impl: SCI_CONV_TC  = tcgen05/TMEM tensor-core kernel fed by TMA (TF32 operands, fp32 accumulate)
+ *       SCI_CONV_REF = fp32 FFMA implicit-GEMM (on-device numerics reference)
+ * ========================================================================= */
+#define SCI_CONV_TC  0
+#define SCI_CONV_REF 1
+
+typedef struct sci_conv_desc {
+    const float* x;         /* input  [N][H][W][Cin]                                              */
+    const float* w;         /* packed weights [9][Cout][Cin]                                      */
+    const float* scale;     /* per output column, NULL = 1   (folded BatchNorm gamma/sqrt(var+eps)) */
+    const float* shift;     /* per output column, NULL = 0   (bias, or folded BatchNorm shift)      */
+    const float* residual;  /* added after activation, same layout as y, NULL = none (skip add)    */
+    float* y;               /* output [N][Ho][Wo][Cout], or [N][2Ho][2Wo][Cout/4] if pixel_shuffle  */
+    int N, H, W;            /* input batch and spatial size                                        */
+    int Cin, Cout;          /* padded channel counts (Cin % 8 == 0; TC: Cin % 32 == 0, Cout % 16 == 0) */
+    int stride;             /* 1 or 2 (pad 1): Ho = (H-1)/stride+1                                  */
+    int relu;               /* ReLU after scale/shift                                             */
+    int pixel_shuffle;      /* 1: GEMM column q*(Cout/4)+c goes to sub-pixel q=(dy*2+dx), channel c */
+    int round_tf32;         /* 1: round stored outputs to TF32 (they feed the next tensor-core conv) */
+} sci_conv_desc;
+
+/* y = act(scale * conv3x3(x, w) + shift) [+ residual].  Forward pass of every layer; the data-gradient
+ * of a stride-1 layer is the same call with weights packed in transposed+flipped form. */
+int sci_conv3x3_fwd(const sci_conv_desc* d, int impl, void* stream);
+int sci_conv3x3_dgrad(const sci_conv_desc* d, int impl, void* stream);
+
+typedef struct sci_wgrad_desc {
+    const float* x;         /* layer input  [N][H][W][Cin]                          */
+    const float* dz;        /* grad wrt GEMM output [N][Ho][Wo][Cout]               */
+    const float* oscale;    /* per output column scale (folded BN), NULL = 1        */
+    float* dw;              /* packed weight gradient [9][Cout][Cin], ACCUMULATED   */
+    int N, H, W, Cin, Cout, stride;
+} sci_wgrad_desc;
+/* dw[tap][co][ci] += oscale[co] * sum_{n,ho,wo} dz[n,ho,wo,co] * x[n, ho*s+r-1, wo*s+q-1, ci] */
+int sci_conv3x3_wgrad(const sci_wgrad_desc* d, int impl, void* stream);
+
+/* PyTorch weight [Co][Ci/groups][3][3] -> packed [9][Co_pad][Ci_pad] (zero padded; grouped convs become
+ * block-diagonal; ps != 0 permutes output columns for PixelShuffle(2): column q*(Co/4)+c <- channel c*4+q).
+ * transpose_flip != 0 packs the data-gradient form [9][Ci_pad][Co_pad] with taps flipped and rows scaled by
+ * oscale (may be NULL).  round_tf32 != 0 rounds to TF32 (RNA). */
+int sci_conv_pack_weights(const float* w, float* packed, int Co, int Ci, int groups, int Co_pad, int Ci_pad,
+                          int ps, const float* oscale, int transpose_flip, int round_tf32, void* stream);
+/* inverse of the forward packing for gradients: dw_torch[Co][Ci/groups][3][3] = packed_dw (assign) */
+int sci_conv_unpack_wgrad(const float* packed_dw, float* dw, int Co, int Ci, int groups, int Co_pad, int Ci_pad,
+                          int ps, void* stream);
+
+/* BatchNorm (eval mode, packages/fastdvdnet/models.py:21-26) folded to per-column scale/shift:
+ * scale = gamma*rsqrt(var+eps), shift = beta - mean*scale; columns >= C are zeroed up to C_pad. */
+int sci_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                float* scale, float* shift, int C, int C_pad, void* stream);
+/* Backward of y = relu(scale*conv+shift):  dz = dy * (y > 0) (relu != 0) else dy, written to dz (may alias dy);
+ * s1[c] += sum dz, s2[c] += sum dz*y  (either may be NULL).  n_pix pixels of C channels (NHWC). */
+int sci_act_bwd(const float* dy, const float* y, float* dz, long n_pix, int C, int relu, float* s1, float* s2,
+                void* stream);
+/* BatchNorm affine gradients from the two sums: dbeta = s1, dgamma = (s2 - beta*s1)/gamma (0 where gamma == 0). */
+int sci_bn_param_grad(const float* s1, const float* s2, const float* gamma, const float* beta, float* dgamma,
+                      float* dbeta, int C, void* stream);
+
+/* NHWC helpers for the backward pass: pixel-unshuffle of a gradient ([N][2H][2W][C] -> [N][H][W][4C], column
+ * q*C+c) and zero-dilation by 2 ([N][H][W][C] -> [N][2H][2W][C]) for the data-gradient of stride-2 layers. */
+int sci_nhwc_pixel_unshuffle(const float* in, float* out, int N, int H, int W, int C, void* stream);
+int sci_nhwc_dilate2(const float* in, float* out, int N, int H, int W, int C, void* stream);
+
+/* FFDNet boundary (models/network_ffdnet.py:56-68, models/basicblock.py:104-126):
+ * pack:   u [B][3][H][W] planar -> head input [B][H/2][W/2][Cpad]: channel c*4+dy*2+dx = u[c][2h+dy][2w+dx],
+ *         channel 12 = sigma, rest 0 (TF32-rounded if round_tf32).
+ * unpack: tail output [B][H/2][W/2][Cpad] (column c*4+dy*2+dx) -> xhat [B][3][H][W] planar (PixelShuffle(2)).
+ * unpack_grad: d xhat planar -> d tail output (adjoint of unpack). */
+int sci_ffdnet_pack_input(const float* u, float sigma, float* out, int B, int H, int W, int Cpad, int round_tf32,
+                          void* stream);
+int sci_ffdnet_unpack_output(const float* y, float* xhat, int B, int H, int W, int Cpad, void* stream);
+int sci_ffdnet_unpack_output_grad(const float* dxhat, float* dy, int B, int H, int W, int Cpad, void* stream);
+
+/* FastDVDnet boundary (packages/fastdvdnet/models.py:185,196,234; fastdvdnet.py:115 circular window):
+ * pack:   frames [B][3][H][W] planar -> DenBlock input [B][H][W][Cpad], for block f the channels
+ *         [F(f-1) rgb, sigma, F(f) rgb, sigma, F(f+1) rgb, sigma] with circular frame indices, rest 0.
+ *         (temp1 is evaluated once per centre frame: the B distinct triples of the circular 5-window; temp2 of
+ *         output frame f then reads the temp1 results f-1, f, f+1 through the same packer.)
+ * output: out[f][c] = frames_center[f][c] - y[f][h][w][c]  (models.py:196), y = last conv [B][H][W][Cpad].
+ * The two *_grad entry points are the adjoints used by the fine-tune backward pass. */
+int sci_fastdvd_pack_input(const float* frames, float sigma, float* out, int B, int H, int W, int Cpad,
+                           int round_tf32, void* stream);
+int sci_fastdvd_output(const float* frames, const float* y, float* out, int B, int H, int W, int Cpad, void* stream);
+int sci_fastdvd_output_grad(const float* dout, float* dy, int B, int H, int W, int Cpad, void* stream);
+int sci_fastdvd_pack_input_grad(const float* din, float* dframes, int B, int H, int W, int Cpad, int accumulate,
+                                void* stream);
+/* training input of the FastDVDnet fine-tune (test_fastdvdnet.py:359 with utils_image.py:183-192):
+ * vplus = v + float32(float64(v) + noise), noise float64 from the host RNG. */
+int sci_fastdvd_noisy_input(const float* v, const double* noise, float* vplus, long n, void* stream);
+
+/* Measurement-consistency loss of the online fine-tune (test_ffdnet_ipol.py:275-291,
+ * test_fastdvdnet.py:428-431):  m = RGGB samples of xhat; up = sum_t m_t*phi_t;
+ * loss += mean((up - y)^2) over H*W (fp64 accumulate);  dxhat[t][c][p] = phi_t * 2(up-y)/(H*W) at the
+ * Bayer colour of p, 0 elsewhere.  dxhat may be NULL (loss only). */
+int sci_meas_loss_fwd_bwd(const float* xhat, const float* phi, const float* y, float* dxhat, double* loss,
+                          int H, int W, int B, void* stream);
+
+/* Adam step over a flat parameter bucket (torch.optim.Adam defaults: betas (0.9,0.999), eps 1e-8, no weight
+ * decay; test_ffdnet_ipol.py:251, test_fastdvdnet.py:385).  step is 1-based. */
+int sci_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long n, double lr,
+                  double beta1, double beta2, double eps, int step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -128,7 +128,9 @@ def test_tv_chambolle(cuda, shape):
     stack = np.empty((H // 2, W // 2, B, 4), np.float32)
     for t in range(B):
         for ib in range(4):
-            noise = (0.002 if (t + ib) % 3 == 0 else 0.08) * rng.standard_normal((H // 2, W // 2))   # smooth channels stop early
+            # large-amplitude channels make the energy converge fast: the reference loop stops at i=3 (sigma 8)
+            # or i=1 (sigma 50); ordinary channels run all 5 iterations
+            noise = (0.08, 8.0, 50.0)[(t + ib) % 3] * rng.standard_normal((H // 2, W // 2))
             stack[:, :, t, ib] = 0.5 + 0.3 * np.sin((xx + 3 * t) / 9.0) * np.cos((yy + ib) / 7.0) + noise
     ref, stops = tv_chambolle.denoise_tv_chambolle(stack.reshape(H // 2, W // 2, 4 * B), 0.1, n_iter_max=5,
                                                    multichannel=True, return_stops=True)
@@ -141,8 +143,7 @@ def test_tv_chambolle(cuda, shape):
     want_stops = np.minimum(np.array(stops).reshape(B, 4), 4)
     assert np.array_equal(got_stops, want_stops), (got_stops, want_stops)
     assert _rel(_planar_to_stack4(theta, H, W, B), ref.reshape(H // 2, W // 2, B, 4)) < REL
-    if shape == (256, 256, 8):
-        assert (want_stops < 4).any() and (want_stops == 4).any()        # both branches exercised
+    assert (want_stops == 1).any() and (want_stops == 3).any() and (want_stops == 4).any()   # all exits exercised
     # fused form: theta = clip(TV(x + c*b)), b' = b + s*(x - theta)
     b = 0.05 * torch.randn_like(x)
     b2 = torch.empty_like(b)

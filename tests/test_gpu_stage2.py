@@ -1,0 +1,64 @@
+"""GPU parity of the stage-2 loops (plug-in deep denoisers with online adaptation) against the golden vectors
+produced by the reference, for both convolution kernel families."""
+import io
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+
+from test_gpu_conv import _fastdvd, _ffdnet, impl  # noqa: E402,F401
+
+
+def _psnr(a, b):
+    return 10 * np.log10(1.0 / np.mean((np.asarray(a, np.float64) - np.asarray(b, np.float64)) ** 2))
+
+
+def test_stage2_ffdnet_color(cuda, impl):
+    from adaptivepnp_sci_b200.dvp_linear_inv_2_stage_ADMM_tensor_online import np2tch_cuda, twoStageAdmm_denoise_bayer
+    from oracle import synthetic
+    d = np.load(os.path.join(G, "loops.npz"))
+    meas, mask, orig = synthetic.make_case(64, 64, 8, 3000, bayer=True)
+    kw = dict(show_iqa=True, demosaic_method='malvar2004', lr_=2e-6, interval_iter=3, logf=io.StringIO())
+    # inference-only loop
+    r = twoStageAdmm_denoise_bayer(meas, mask, 1, 0.01, 'ffdnet_color', [3], False, [25 / 255],
+                                   x0_bayer=np2tch_cuda(d["s2_warm"]), X_orig=orig, model_denoise=_ffdnet(cuda),
+                                   model_demosaic=None, update_=False, **kw)
+    tol = {"ref": 2e-4, "tc": 1e-3}[impl]                       # north_star: <= 1e-3 max-abs on the reconstruction
+    assert len(r) == 7 and r[0].shape == (64, 64, 3, 8) and r[1].shape == (64, 64, 8)
+    assert np.max(np.abs(r[0] - d["s2ffd0_rgb"])) < tol and np.max(np.abs(r[1] - d["s2ffd0_x"])) < tol
+    assert np.max(np.abs(np.array(r[4]) - d["s2ffd0_psnr_all"])) < 0.05
+    # online-adaptive loop (two sigma levels, fine-tune at k=3 and k=6)
+    m = _ffdnet(cuda)
+    r = twoStageAdmm_denoise_bayer(meas, mask, 1, 0.01, 'ffdnet_color', [4, 3], False, [25 / 255, 12 / 255],
+                                   x0_bayer=np2tch_cuda(d["s2_warm"]), X_orig=orig, model_denoise=m,
+                                   model_demosaic=None, update_=True, update_per_iter=2, **kw)
+    assert r[5] is m
+    assert np.max(np.abs(r[0] - d["s2ffd_rgb"])) < tol and np.max(np.abs(r[1] - d["s2ffd_x"])) < tol
+    assert abs(_psnr(r[1], orig) - _psnr(d["s2ffd_x"], orig)) < 0.05                 # dB, north_star bound
+    assert np.max(np.abs(np.array(r[4]) - d["s2ffd_psnr_all"])) < 0.05
+    assert np.max(np.abs(np.array(r[2]) - d["s2ffd_psnr"])) < 0.05 and np.max(np.abs(np.array(r[3]) - d["s2ffd_ssim"])) < 1e-3
+
+
+def test_stage2_fastdvd_color(cuda, impl):
+    from adaptivepnp_sci_b200.dvp_linear_inv_2_stage_ADMM_tensor_online import np2tch_cuda, twoStageAdmm_denoise_bayer
+    from adaptivepnp_sci_b200.utilspy import worker_init_fn
+    from oracle import synthetic
+    d = np.load(os.path.join(G, "loops.npz"))
+    meas, mask, orig = synthetic.make_case(64, 64, 8, 3000, bayer=True)
+    m = _fastdvd(cuda)
+    worker_init_fn(0)                                          # the fine-tune noise comes from the global numpy RNG
+    r = twoStageAdmm_denoise_bayer(meas, mask, 1, 0.01, 'fastdvd_color', [5, 2], False, [12 / 255, 6 / 255],
+                                   x0_bayer=np2tch_cuda(d["s2_warm"]), X_orig=orig, model_denoise=m,
+                                   model_demosaic=None, show_iqa=True, demosaic_method='malvar2004', lr_=2e-6,
+                                   interval_iter=3, logf=io.StringIO(), update_=True, update_per_iter=2,
+                                   update_times=-1)
+    tol = {"ref": 2e-4, "tc": 1e-3}[impl]
+    assert r[5] is m and hasattr(r[5], "module")
+    assert np.max(np.abs(r[0] - d["s2fdvd_rgb"])) < tol and np.max(np.abs(r[1] - d["s2fdvd_x"])) < tol
+    assert abs(_psnr(r[1], orig) - _psnr(d["s2fdvd_x"], orig)) < 0.05
+    assert np.max(np.abs(np.array(r[4]) - d["s2fdvd_psnr_all"])) < 0.05
