@@ -1,10 +1,362 @@
-// Dispatch of the conv entry points + (to come) the tcgen05/TMEM/TMA implicit-GEMM kernels.
+// Tensor-core 3x3 convolution for sm_100a: implicit GEMM on tcgen05.mma (TF32 operands, fp32
+// accumulators in TMEM) fed by TMA, plus the dispatch of the public conv entry points.
+//
+// Forward / data-gradient kernel (conv_fwd_tc_kernel)
+//   GEMM view per output tile:  D[128 pixels][Cout] = sum over 9 taps x Cin/32 chunks of
+//        A[128 pixels][32 ch] (activations, K-major)  x  B[Cout][32 ch]^T (packed weights, K-major)
+//   * A tile = one TMA box {32 ch, 16 px, 8 rows, 1 image} of the NHWC activation tensor, shifted by the
+//     tap offset; out-of-image coordinates are zero-filled by TMA (= the conv's zero padding); stride-2
+//     layers use the tensor map's element strides, so no im2col buffer or gather code exists.
+//   * B tile = TMA box {32 ch, Cout, 1 tap} of the packed weights.  Both land in 128B-swizzled shared
+//     memory, which is exactly the canonical K-major SWIZZLE_128B UMMA operand layout.
+//   * warp roles (256 threads, 1 CTA/SM, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA
+//     issuer (one elected thread, 4 x tcgen05.mma of K=8 per stage), warp 2 = TMEM allocator,
+//     warps 4-7 = epilogue (tcgen05.ld -> scale/shift/ReLU/skip-add/PixelShuffle/TF32 round -> global).
+//   * pipelines: smem ring (full/empty mbarriers) between TMA and MMA; two TMEM accumulator stages
+//     (tmem_full/tmem_empty) between MMA and epilogue, so the epilogue of tile i overlaps the MMAs of i+1.
+#include <cuda.h>
+
 #include "sci_common.cuh"
 
 int sci_conv3x3_ref_launch(const sci_conv_desc* d, void* stream);
 int sci_wgrad_ref_launch(const sci_wgrad_desc* d, void* stream);
 
-static int check_conv_desc(const sci_conv_desc* d) {
+namespace {
+
+constexpr int TILE_W = 16, TILE_H = 8;      // 128 output pixels per tile = UMMA M
+constexpr int KCH = 32;                     // fp32 channels per K chunk = 128 bytes = one swizzle row
+constexpr int A_BYTES = TILE_W * TILE_H * KCH * 4;   // 16 KB
+constexpr int TC_THREADS = 256;
+constexpr int MAX_STAGES = 8;
+
+struct FwdParams {
+    const float* scale; const float* shift; const float* residual; float* y;
+    int N, H, W, Ho, Wo, Cin, Cout, stride, relu, ps, round_tf32;
+    int tiles_w, tiles_h, num_tiles, k_chunks, stages, acc_stride, tmem_cols;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+// K-major / MN-major shared-memory matrix descriptor, SWIZZLE_128B, version 1 (sm_100)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float rna_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// forward / data-gradient kernel
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_slot;
+    __shared__ float s_scale[256], s_shift[256];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t b_bytes = (uint32_t)p.Cout * KCH * 4;
+    const uint32_t stage_bytes = A_BYTES + b_bytes;
+
+    for (int i = threadIdx.x; i < p.Cout; i += TC_THREADS) {
+        s_scale[i] = p.scale ? p.scale[i] : 1.f;
+        s_shift[i] = p.shift ? p.shift[i] : 0.f;
+    }
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    const int k_steps = 9 * p.k_chunks;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, n = tile / (p.tiles_w * p.tiles_h);
+                const int iw0 = tw * TILE_W * p.stride - 1, ih0 = th * TILE_H * p.stride - 1;
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int r = tap / 3, s = tap % 3;
+                    for (int kc = 0; kc < p.k_chunks; ++kc) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1u);
+                        mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+                        const uint32_t a_dst = smem_base + (uint32_t)stage * stage_bytes;
+                        tma_load_4d(a_dst, &tmA, &full_bar[stage], kc * KCH, iw0 + s, ih0 + r, n);
+                        tma_load_3d(a_dst + A_BYTES, &tmB, &full_bar[stage], kc * KCH, 0, tap);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            // instruction descriptor: D=f32, A=B=tf32, K-major both, N = Cout, M = 128
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Cout >> 3) << 17) | ((128u >> 4) << 24);
+            int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
+                for (int ks = 0; ks < k_steps; ++ks) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes, b_addr = a_addr + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < KCH / 8; ++k) {
+                        tc_mma_tf32(d_tmem, umma_desc(a_addr + k * 32, 16, 1024), umma_desc(b_addr + k * 32, 16, 1024), idesc,
+                                    (uint32_t)((ks | k) != 0));
+                    }
+                    tc_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
+                tc_commit(&tfull_bar[acc]);                // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> registers -> global =====
+        const int q = warp & 3;                            // TMEM lane quarter this warp may access
+        const int m = q * 32 + lane, hh = m / TILE_W, ww = m % TILE_W;
+        const int Cq = p.Cout >> 2;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, n = tile / (p.tiles_w * p.tiles_h);
+            const int ho = th * TILE_H + hh, wo = tw * TILE_W + ww;
+            const bool valid = ho < p.Ho && wo < p.Wo;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + (uint32_t)(acc * p.acc_stride) + ((uint32_t)(q * 32) << 16);
+            for (int c0 = 0; c0 < p.Cout; c0 += 32) {
+                float v[32];
+                const int nc = min(32, p.Cout - c0);
+                if (nc == 32) tmem_ld32(t_row + c0, v); else tmem_ld16(t_row + c0, v);
+                if (valid) {
+                    long o;
+                    if (p.ps) {
+                        const int qq = c0 / Cq, cc = c0 % Cq;
+                        o = (((long)n * 2 * p.Ho + 2 * ho + (qq >> 1)) * 2 * p.Wo + 2 * wo + (qq & 1)) * Cq + cc;
+                    } else {
+                        o = (((long)n * p.Ho + ho) * p.Wo + wo) * p.Cout + c0;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        if (j >= nc) break;
+                        float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.residual) r4 = *reinterpret_cast<const float4*>(p.residual + o + j);
+                        float out[4];
+                        const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float t = v[j + e] * s_scale[c0 + j + e] + s_shift[c0 + j + e];
+                            if (p.relu) t = fmaxf(t, 0.f);
+                            t += rr[e];
+                            if (p.round_tf32) t = rna_tf32(t);
+                            out[e] = t;
+                        }
+                        *reinterpret_cast<float4*>(p.y + o + j) = make_float4(out[0], out[1], out[2], out[3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side: TMA descriptors through the driver entry point (no libcuda link dependency)
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// NHWC activation tensor [N][H][W][C], box = {32 ch, TILE_W*stride, TILE_H*stride, 1} traversed with element stride `stride`
+int make_act_map(CUtensorMap* tm, const float* x, int N, int H, int W, int C, int stride, int box_w, int box_h) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return sci_fail(SCI_ELAUNCH, "cuTensorMapEncodeTiled entry point not available");
+    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    const cuuint32_t box[4] = {KCH, (cuuint32_t)(box_w * stride), (cuuint32_t)(box_h * stride), 1};
+    const cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char msg[96];
+        snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled(activations) failed with CUresult %d", (int)r);
+        return sci_fail(SCI_ELAUNCH, msg);
+    }
+    return SCI_OK;
+}
+
+// packed weights [9][Cout][Cin], box = {32 ch, Cout, 1}
+int make_weight_map(CUtensorMap* tm, const float* w, int Cout, int Cin) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return sci_fail(SCI_ELAUNCH, "cuTensorMapEncodeTiled entry point not available");
+    const cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, 9};
+    const cuuint64_t strides[2] = {(cuuint64_t)Cin * 4, (cuuint64_t)Cout * Cin * 4};
+    const cuuint32_t box[3] = {KCH, (cuuint32_t)Cout, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(w), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char msg[96];
+        snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled(weights) failed with CUresult %d", (int)r);
+        return sci_fail(SCI_ELAUNCH, msg);
+    }
+    return SCI_OK;
+}
+
+int next_pow2_cols(int c) { int v = 32; while (v < c) v <<= 1; return v; }
+
+int conv_fwd_tc_launch(const sci_conv_desc* d, void* stream) {
+    if (d->Cin % KCH != 0 || d->Cout % 16 != 0 || d->Cout > 256)
+        return sci_fail(SCI_EUNSUPPORTED, "conv tc: needs Cin % 32 == 0, Cout % 16 == 0, Cout <= 256");
+    if (((uintptr_t)d->x | (uintptr_t)d->w | (uintptr_t)d->y | (uintptr_t)d->residual) & 15)
+        return sci_fail(SCI_EINVAL, "conv tc: pointers must be 16-byte aligned");
+    if (d->pixel_shuffle && (d->Cout % 128 != 0))
+        return sci_fail(SCI_EUNSUPPORTED, "conv tc: pixel_shuffle needs Cout % 128 == 0");
+    FwdParams p;
+    p.scale = d->scale; p.shift = d->shift; p.residual = d->residual; p.y = d->y;
+    p.N = d->N; p.H = d->H; p.W = d->W; p.stride = d->stride;
+    p.Ho = (d->H - 1) / d->stride + 1; p.Wo = (d->W - 1) / d->stride + 1;
+    p.Cin = d->Cin; p.Cout = d->Cout; p.relu = d->relu; p.ps = d->pixel_shuffle; p.round_tf32 = d->round_tf32;
+    p.tiles_w = (p.Wo + TILE_W - 1) / TILE_W; p.tiles_h = (p.Ho + TILE_H - 1) / TILE_H;
+    p.num_tiles = p.tiles_w * p.tiles_h * p.N;
+    p.k_chunks = p.Cin / KCH;
+    const int stage_bytes = A_BYTES + p.Cout * KCH * 4;
+    p.stages = min(MAX_STAGES, (200 * 1024) / stage_bytes);
+    p.acc_stride = ((p.Cout + 31) / 32) * 32;
+    p.tmem_cols = next_pow2_cols(2 * p.acc_stride);
+    CUtensorMap tmA, tmB;
+    int rc = make_act_map(&tmA, d->x, d->N, d->H, d->W, d->Cin, d->stride, TILE_W, TILE_H);
+    if (rc) return rc;
+    rc = make_weight_map(&tmB, d->w, d->Cout, d->Cin);
+    if (rc) return rc;
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(conv_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return sci_fail(SCI_ELAUNCH, "conv tc: smem attribute", e);
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    const int grid = min(p.num_tiles, SCI_NUM_SMS);
+    conv_fwd_tc_kernel<<<grid, TC_THREADS, smem, sci_stream(stream)>>>(tmA, tmB, p);
+    SCI_CHECK_LAUNCH("conv tc fwd");
+    return SCI_OK;
+}
+
+int check_conv_desc(const sci_conv_desc* d) {
     SCI_REQUIRE(d && d->x && d->w && d->y, "conv: null pointer");
     SCI_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "conv: shape");
     SCI_REQUIRE(d->Cin % 8 == 0 && d->Cout % 4 == 0, "conv: Cin % 8, Cout % 4");
@@ -13,11 +365,16 @@ static int check_conv_desc(const sci_conv_desc* d) {
     return SCI_OK;
 }
 
+}  // namespace
+
+extern "C" int sci_conv_tc_available(void) { return 1; }
+
 extern "C" int sci_conv3x3_fwd(const sci_conv_desc* d, int impl, void* stream) {
     int rc = check_conv_desc(d);
     if (rc) return rc;
     if (impl == SCI_CONV_REF) return sci_conv3x3_ref_launch(d, stream);
-    return sci_fail(SCI_EUNSUPPORTED, "conv: tensor-core path not built yet");
+    if (impl == SCI_CONV_TC) return conv_fwd_tc_launch(d, stream);
+    return sci_fail(SCI_EINVAL, "conv: unknown impl");
 }
 
 extern "C" int sci_conv3x3_dgrad(const sci_conv_desc* d, int impl, void* stream) {
@@ -29,6 +386,7 @@ extern "C" int sci_conv3x3_wgrad(const sci_wgrad_desc* d, int impl, void* stream
     SCI_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0 && (d->stride == 1 || d->stride == 2),
                 "wgrad: shape");
     SCI_REQUIRE(d->Cin % 4 == 0 && d->Cout % 4 == 0, "wgrad: channels % 4");
-    if (impl == SCI_CONV_REF) return sci_wgrad_ref_launch(d, stream);
-    return sci_fail(SCI_EUNSUPPORTED, "wgrad: tensor-core path not built yet");
+    // TODO(round 1): tcgen05 weight-gradient kernel (MN-major operands); until then both impls use the fp32 kernel
+    (void)impl;
+    return sci_wgrad_ref_launch(d, stream);
 }

@@ -174,6 +174,8 @@ typedef struct sci_conv_desc {
     int round_tf32;         /* 1: round stored outputs to TF32 (they feed the next tensor-core conv) */
 } sci_conv_desc;
 
+/* 1 if this build contains the tcgen05 tensor-core convolution kernels. */
+int sci_conv_tc_available(void);
 /* y = act(scale * conv3x3(x, w) + shift) [+ residual].  Forward pass of every layer; the data-gradient
  * of a stride-1 layer is the same call with weights packed in transposed+flipped form. */
 int sci_conv3x3_fwd(const sci_conv_desc* d, int impl, void* stream);
