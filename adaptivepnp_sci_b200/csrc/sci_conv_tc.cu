@@ -333,7 +333,7 @@ int conv_fwd_tc_launch(const sci_conv_desc* d, void* stream) {
     p.num_tiles = p.tiles_w * p.tiles_h * p.N;
     p.k_chunks = p.Cin / KCH;
     const int stage_bytes = A_BYTES + p.Cout * KCH * 4;
-    p.stages = min(MAX_STAGES, (200 * 1024) / stage_bytes);
+    p.stages = min(MAX_STAGES, (216 * 1024) / stage_bytes);
     p.acc_stride = ((p.Cout + 31) / 32) * 32;
     p.tmem_cols = next_pow2_cols(2 * p.acc_stride);
     CUtensorMap tmA, tmB;
@@ -346,7 +346,7 @@ int conv_fwd_tc_launch(const sci_conv_desc* d, void* stream) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(conv_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(conv_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         if (e != cudaSuccess) return sci_fail(SCI_ELAUNCH, "conv tc: smem attribute", e);
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }

@@ -151,7 +151,7 @@ def twoStageAdmm_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, gamma=0.01,
                                demosaic_method='malvar2004', lr_=0.000001,
                                inital_iter=1, interval_iter=5, logf=None, useGPU=True, update_=False, update_per_iter=1,
                                close_form_demosaic=False,
-                               large=False, update_times=-1, args=None, grad_sync=None):
+                               large=False, update_times=-1, args=None, grad_sync=None, return_device=False):
     """Stage 2: ADMM with a plug-in denoiser ('tv', 'ffdnet_color', 'fastdvd_color') and optional
     online fine-tuning of the denoiser on the measurement-consistency loss.
 
@@ -159,6 +159,8 @@ def twoStageAdmm_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, gamma=0.01,
     otherwise ``(xbgr3_np[H,W,3,B], x_bayer_np[H,W,B], psnr_, ssim_, psnr_all, model_denoise,
     model_demosaic)`` (:324).  ``grad_sync`` (extension, default None) is a callable applied to the
     flat gradient bucket before each Adam step; the multi-GPU driver passes an NCCL all-reduce.
+    ``return_device`` (extension) returns the planar device tensors ``(xhat[B,3,H,W], theta[B,H,W])`` instead of
+    numpy arrays (no D2H copy, no host sync) — used by bench.py for the HBM-resident measurement.
     """
     name = denoiser if denoiser == 'tv' else str(denoiser).lower()
     if name not in ('tv', 'ffdnet_color', 'fastdvd_color'):
@@ -194,6 +196,15 @@ def twoStageAdmm_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, gamma=0.01,
     sched = []
     k = 0
     update_i = 0
+    noise_q = None
+    if name == 'fastdvd_color' and update_:
+        # The FastDVDnet fine-tune perturbs its input with HOST numpy-RNG noise (utils_image.py:183-192).  The
+        # draws (same call, shape and order as the reference) are produced by a helper thread started now, so
+        # the ~25 ns/sample legacy generator overlaps the first ADMM iterations instead of stalling the GPU.
+        n_upd = sum(1 for kk in range(n_total) if kk > inital_iter and kk % interval_iter == 0)
+        if update_times >= 0:
+            n_upd = min(n_upd, update_times)
+        noise_q = fastdvdnet_adapter.NoisePrefetch((B, 3, H, W), n_upd)
     for idx, nsig in enumerate(sigma):
         for _ in range(iter_max[idx]):
             # p = theta - b/rho ; x = p + Phi*((y - A p)/(alpha*rho + Phi_sum))                     (:128-140)
@@ -214,13 +225,18 @@ def twoStageAdmm_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, gamma=0.01,
                 else:
                     do_update = do_update and (update_i < update_times or update_times < 0)   # :247
                     xhat = fastdvdnet_adapter.denoise_planar(u, pb, nsig, model_denoise, lr_, do_update,
-                                                             update_per_iter, grad_sync=grad_sync)
+                                                             update_per_iter, grad_sync=grad_sync,
+                                                             noise=noise_q.get() if do_update else None)
                     update_i += int(do_update)
                 # theta = clip(RGGB samples of xhat) ; b += x - theta ; w += x_rgb - xhat [+ PSNR]    (:206-209, :265-280)
                 ops.dual_update_rgb(xhat, x_rgb, w, x, b, theta, first_iter=(k == 0),
                                     orig=pb.orig if want_iqa else None, sse=sse[k:k + 1] if want_iqa else None)
             sched.append(nsig)
             k += 1
+    if noise_q is not None:
+        noise_q.close()
+    if return_device:
+        return xhat, theta
     psnr_all = []
     if want_iqa:
         psnr_all = list(iqa.psnr_from_sse(sse.cpu().numpy()[:n_total], pb.npix * B))

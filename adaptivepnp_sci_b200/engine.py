@@ -3,7 +3,7 @@
 The networks of the reference are short, fixed chains of 3x3 convolutions; this module is
 the host-side schedule that strings the C-ABI kernels together:
 
-* activations: NHWC fp32, channels padded to a multiple of 32 (16 for terminal outputs);
+* activations: NHWC fp32, channels padded to a multiple of 32 (padded channels hold zeros);
 * weights: PyTorch parameters (fp32 master copies, one flat bucket per model so that Adam
   and the NCCL gradient all-reduce are single launches) re-packed into the implicit-GEMM
   layout ``[9][Cout][Cin]`` whenever they change; BatchNorm (always in eval mode on this
@@ -112,12 +112,12 @@ class ParamBucket:
 class ConvLayer:
     """One 3x3 convolution of a network with its epilogue and its packed device-side state."""
 
-    def __init__(self, conv, bn=None, relu=False, stride=1, ps=False, terminal=False, cin_pad=None):
+    def __init__(self, conv, bn=None, relu=False, stride=1, ps=False, cin_pad=None):
         self.conv, self.bn, self.relu, self.stride, self.ps = conv, bn, relu, stride, ps
         self.Co, self.groups = conv.out_channels, conv.groups
         self.Ci = conv.in_channels
         self.Ci_pad = cin_pad or _pad(self.Ci, 32)
-        self.Co_pad = self.Co if ps else _pad(self.Co, 16 if terminal else 32)
+        self.Co_pad = self.Co if ps else _pad(self.Co, 32)   # multiple of 32: it is the K extent of the data-gradient GEMM
         self.out_ch = self.Co_pad // 4 if ps else self.Co_pad       # channels of the stored output tensor
         dev = conv.weight.device
         self.wpk = torch.empty(9 * self.Co_pad * self.Ci_pad, dtype=torch.float32, device=dev)
@@ -180,6 +180,7 @@ class _EngineBase:
         self._bwd_valid = False
         self.dirty = True
         self.n_launch = 0
+        self.profile = None      # set to a list to record (start_event, end_event, algorithmic_flops, tag) per conv launch
 
     # ---- parameter state ------------------------------------------------------------------------------
     def _version(self):
@@ -215,7 +216,15 @@ class _EngineBase:
     def conv(self, L, x, N, H, W, y, residual=None, round_out=True):
         d = ConvDesc(_dp(x), _dp(L.wpk), _dp(L.scale), _dp(L.shift), _dp(residual), _dp(y), N, H, W, L.Ci_pad, L.Co_pad,
                      L.stride, int(L.relu), int(L.ps), int(self.tf32 and round_out))
+        if self.profile is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         call("sci_conv3x3_fwd", ctypes.byref(d), self.impl, stream())
+        if self.profile is not None:
+            ev1.record()
+            Ho, Wo = (H - 1) // L.stride + 1, (W - 1) // L.stride + 1
+            self.profile.append((ev0, ev1, 2.0 * N * Ho * Wo * 9 * (L.Ci // L.groups) * L.Co,
+                                 "fwd %dx%d %d->%d s%d" % (H, W, L.Ci, L.Co, L.stride)))
         self.n_launch += 1
 
     def dgrad(self, L, dz, N, Ho, Wo, dx, residual=None):
@@ -267,7 +276,7 @@ class FFDNetEngine(_EngineBase):
         layers = []
         for i, c in enumerate(convs):
             last = i == len(convs) - 1
-            layers.append(ConvLayer(c, None, relu=not last, terminal=last))
+            layers.append(ConvLayer(c, None, relu=not last))
         super().__init__(module, layers)
         self.in_nc, self.out_nc = module.in_nc, module.out_nc
         if (self.in_nc, self.out_nc) != (3, 3):
@@ -332,7 +341,7 @@ class _DenBlockLayers:
         specs = block.conv_specs()
         self.L = []
         for i, (conv, bn, relu, stride, ps) in enumerate(specs):
-            self.L.append(ConvLayer(conv, bn, relu=relu, stride=stride, ps=ps, terminal=(i == len(specs) - 1)))
+            self.L.append(ConvLayer(conv, bn, relu=relu, stride=stride, ps=ps))
 
 
 class FastDVDnetEngine(_EngineBase):

@@ -52,6 +52,36 @@ def draw_finetune_noise(shape):
     return np.random.normal(0, 5 / 255, tuple(shape))
 
 
+class NoisePrefetch:
+    """Draws the fine-tune noise of one reconstruction on a helper thread, in the reference's order.
+
+    ``count`` arrays of ``shape`` are generated back to back from the GLOBAL numpy RNG (numpy releases the GIL
+    while filling), so the values and the final RNG state are exactly those of ``count`` sequential
+    ``np.random.normal`` calls made by the reference's adapter.  ``close()`` joins the thread."""
+
+    def __init__(self, shape, count):
+        import queue
+        import threading
+        self.q = queue.Queue()
+        self.count = count
+        self.taken = 0
+
+        def work():
+            for _ in range(count):
+                self.q.put(draw_finetune_noise(shape))
+        self.thread = threading.Thread(target=work, daemon=True)
+        self.thread.start()
+
+    def get(self):
+        if self.taken >= self.count:
+            raise SciError("more fine-tune calls than scheduled")
+        self.taken += 1
+        return self.q.get()
+
+    def close(self):
+        self.thread.join()
+
+
 def finetune_and_denoise(v, phi, y, sigma, model, lr, update_per_iter, grad_sync=None, noise=None):
     """v [B,3,H,W], phi [B,H,W], y [H,W] planar; returns the denoised CLEAN sequence [B,3,H,W]."""
     eng = _unwrap(model).engine()

@@ -88,7 +88,7 @@ def test_conv_layer_fwd_bwd(cuda, impl, case):
     if bn:
         cbn = torch.nn.BatchNorm2d(Co).cuda().eval()
         cbn.load_state_dict(bnm.state_dict())
-    L = engine.ConvLayer(cconv, cbn, relu=relu, stride=stride, ps=ps, terminal=(Co < 16))
+    L = engine.ConvLayer(cconv, cbn, relu=relu, stride=stride, ps=ps)
     eng = engine._EngineBase(torch.nn.ModuleList([cconv] + ([cbn] if bn else [])), [L])
     eng.prepare(training=True)
     xd = torch.zeros(N, H, W, L.Ci_pad, device=cuda)
@@ -102,7 +102,8 @@ def test_conv_layer_fwd_bwd(cuda, impl, case):
     eng.conv(L, xd, N, H, W, y, residual=resd, round_out=False)
     cout_valid = Co // 4 if ps else Co
     tol = TOL[impl]
-    assert _rel(y[..., :cout_valid].permute(0, 3, 1, 2).cpu(), yref.detach()) < tol
+    e_fwd = _rel(y[..., :cout_valid].permute(0, 3, 1, 2).cpu(), yref.detach())
+    assert e_fwd < tol, "forward rel err %g" % e_fwd
     if not ps and L.Co_pad > Co:
         assert float(y[..., Co:].abs().max()) == 0.0                  # padded columns stay exactly zero
     # ---- backward: dz = act_bwd(dy), wgrad, dgrad
@@ -113,7 +114,11 @@ def test_conv_layer_fwd_bwd(cuda, impl, case):
         call("sci_nhwc_pixel_unshuffle", ptr(dyd), ptr(dconv), N, Ho, Wo, och, stream())
         dyd, ystore = dconv, None
     else:
-        ystore = y
+        # the ReLU mask is taken from the ORACLE's forward output: with TF32 operands a handful of near-zero
+        # activations change sign, which would turn this per-layer check into a test of mask flips instead of
+        # the dgrad / wgrad kernels (the end-to-end fine-tune tests cover the real mask)
+        ystore = torch.zeros(N, oh, ow, och, device=cuda)
+        ystore[..., :cout_valid] = yref.detach().permute(0, 2, 3, 1).to(cuda)
     eng.dw_flat.zero_()
     dz = eng.act_bwd(L, dyd, ystore, N * Ho * Wo, L.Co_pad)
     eng.wgrad(L, xd, dz, N, H, W)
@@ -126,13 +131,14 @@ def test_conv_layer_fwd_bwd(cuda, impl, case):
         eng.dgrad(L, dz, N, Ho, Wo, dx)
     eng.param_grads(L)
     btol = tol * 3
-    assert _rel(dx[..., :Ci].permute(0, 3, 1, 2).cpu(), xr.grad) < btol
-    assert _rel(eng.bucket.grad_view(cconv.weight).cpu(), conv.weight.grad) < btol
+    errs = dict(dx=_rel(dx[..., :Ci].permute(0, 3, 1, 2).cpu(), xr.grad),
+                dw=_rel(eng.bucket.grad_view(cconv.weight).cpu(), conv.weight.grad))
     if bias:
-        assert _rel(eng.bucket.grad_view(cconv.bias).cpu(), conv.bias.grad) < btol
+        errs["dbias"] = _rel(eng.bucket.grad_view(cconv.bias).cpu(), conv.bias.grad)
     if bn:
-        assert _rel(eng.bucket.grad_view(cbn.weight).cpu(), bnm.weight.grad) < btol
-        assert _rel(eng.bucket.grad_view(cbn.bias).cpu(), bnm.bias.grad) < btol
+        errs["dgamma"] = _rel(eng.bucket.grad_view(cbn.weight).cpu(), bnm.weight.grad)
+        errs["dbeta"] = _rel(eng.bucket.grad_view(cbn.bias).cpu(), bnm.bias.grad)
+    assert all(v < btol for v in errs.values()), "backward rel errs %s (fwd %g)" % (errs, e_fwd)
 
 
 def _ffdnet(cuda):
