@@ -14,6 +14,7 @@
 //     warps 4-7 = epilogue (tcgen05.ld -> scale/shift/ReLU/skip-add/PixelShuffle/TF32 round -> global).
 //   * pipelines: smem ring (full/empty mbarriers) between TMA and MMA; two TMEM accumulator stages
 //     (tmem_full/tmem_empty) between MMA and epilogue, so the epilogue of tile i overlaps the MMAs of i+1.
+// Weight-gradient kernel (conv_wgrad_tc_kernel): see the comment above its definition.
 #include <cuda.h>
 
 #include "sci_common.cuh"
@@ -356,6 +357,172 @@ int conv_fwd_tc_launch(const sci_conv_desc* d, void* stream) {
     return SCI_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// weight-gradient kernel (conv_wgrad_tc_kernel)
+//   dW[tap][co][ci] += oscale[co] * sum_pixels dz[p][co] * x[p (+) tap][ci]
+//   GEMM view: D[128 co][Cin] += A^T B over K = pixels, both operands MN-major (channels contiguous):
+//     A = dz tile  [64 pixels][Cout_tile]  = Cout_tile/32 TMA boxes {32 ch, 8 px, 8 rows, 1 image}
+//     B = x  tile  [64 pixels][Cin]        = Cin/32 TMA boxes at the tap-shifted (and, for stride-2 layers,
+//                                            element-strided) coordinates; out-of-image pixels are zero-filled
+//   One CTA owns a filter row (3 taps -> 3 TMEM accumulators of Cin columns), one 128-wide block of output
+//   channels and a strided subset of the 8x8 pixel tiles; it accumulates over all its tiles in TMEM and
+//   finishes with vectorised red.global.add into the packed gradient.
+// ---------------------------------------------------------------------------------------------------
+constexpr int WG_TILE = 8;                       // 8x8 pixels = 64 = K block
+constexpr int WG_CHUNK_BYTES = WG_TILE * WG_TILE * KCH * 4;   // 8 KB per 32-channel chunk
+constexpr int WG_STAGES = 3;
+
+struct WgradParams {
+    const float* oscale; float* dw;
+    int N, Ho, Wo, Cin, Cout, stride;
+    int tiles_w, tiles_h, num_tiles, a_chunks, b_chunks, m_tiles, tmem_cols;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmX, const WgradParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[WG_STAGES], empty_bar[WG_STAGES], done_bar;
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int frow = blockIdx.y / p.m_tiles;          // filter row r (taps r*3 .. r*3+2)
+    const int mt = blockIdx.y % p.m_tiles;            // 128-wide block of output channels
+    const int a_chunks = min(p.a_chunks - mt * 4, 4);
+    const uint32_t a_bytes = (uint32_t)a_chunks * WG_CHUNK_BYTES, b_bytes = (uint32_t)p.b_chunks * WG_CHUNK_BYTES;
+    const uint32_t a_region = 4 * WG_CHUNK_BYTES, stage_bytes = a_region + (uint32_t)p.b_chunks * WG_CHUNK_BYTES;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmZ) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&done_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, n = tile / (p.tiles_w * p.tiles_h);
+                const int ow0 = tw * WG_TILE, oh0 = th * WG_TILE;
+                for (int s = 0; s < 3; ++s) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+                    const uint32_t base = smem_base + (uint32_t)stage * stage_bytes;
+                    for (int c = 0; c < a_chunks; ++c)
+                        tma_load_4d(base + c * WG_CHUNK_BYTES, &tmZ, &full_bar[stage], (mt * 4 + c) * KCH, ow0, oh0, n);
+                    for (int c = 0; c < p.b_chunks; ++c)
+                        tma_load_4d(base + a_region + c * WG_CHUNK_BYTES, &tmX, &full_bar[stage], c * KCH,
+                                    ow0 * p.stride + s - 1, oh0 * p.stride + frow - 1, n);
+                    if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // D=f32, A=B=tf32, both MN-major (bits 15/16), N = Cin, M = 128
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                                   ((uint32_t)(p.Cin >> 3) << 17) | ((128u >> 4) << 24);
+            int stage = 0; uint32_t phase = 0; bool first = true;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                for (int s = 0; s < 3; ++s) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes, b_addr = a_addr + a_region;
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(s * p.Cin);
+#pragma unroll
+                    for (int k8 = 0; k8 < WG_TILE * WG_TILE / 8; ++k8) {
+                        // MN-major SWIZZLE_128B: LBO = stride between 32-channel chunks, SBO = stride between 8-pixel groups
+                        tc_mma_tf32(d_tmem, umma_desc(a_addr + k8 * 1024, WG_CHUNK_BYTES, 1024),
+                                    umma_desc(b_addr + k8 * 1024, WG_CHUNK_BYTES, 1024), idesc, (uint32_t)(!first || k8 != 0));
+                    }
+                    tc_commit(&empty_bar[stage]);
+                    if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
+                }
+                first = false;
+            }
+            tc_commit(&done_bar);
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        const int co = mt * 128 + q * 32 + lane;
+        const bool has_work = blockIdx.x < p.num_tiles;
+        if (has_work) {
+            mbar_wait(&done_bar, 0);
+            tc_fence_after();
+            const float sc = (co < p.Cout && p.oscale) ? p.oscale[co] : 1.f;
+            for (int s = 0; s < 3; ++s) {
+                const int tap = frow * 3 + s;
+                const uint32_t t_row = tmem_base + (uint32_t)(s * p.Cin) + ((uint32_t)(q * 32) << 16);
+                for (int c0 = 0; c0 < p.Cin; c0 += 32) {
+                    float v[32];
+                    tmem_ld32(t_row + c0, v);
+                    if (co < p.Cout) {
+                        float* dst = p.dw + ((long)tap * p.Cout + co) * p.Cin + c0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v[j] * sc),
+                                         "f"(v[j + 1] * sc), "f"(v[j + 2] * sc), "f"(v[j + 3] * sc) : "memory");
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
+}
+
+int conv_wgrad_tc_launch(const sci_wgrad_desc* d, void* stream) {
+    if (d->Cin % KCH != 0 || d->Cout % KCH != 0 || d->Cin > 128 || d->Cout > 256)
+        return sci_fail(SCI_EUNSUPPORTED, "wgrad tc: needs Cin % 32 == 0 (<= 128), Cout % 32 == 0 (<= 256)");
+    WgradParams p;
+    p.oscale = d->oscale; p.dw = d->dw;
+    p.N = d->N; p.stride = d->stride; p.Cin = d->Cin; p.Cout = d->Cout;
+    p.Ho = (d->H - 1) / d->stride + 1; p.Wo = (d->W - 1) / d->stride + 1;
+    p.tiles_w = (p.Wo + WG_TILE - 1) / WG_TILE; p.tiles_h = (p.Ho + WG_TILE - 1) / WG_TILE;
+    p.num_tiles = p.tiles_w * p.tiles_h * p.N;
+    p.a_chunks = p.Cout / KCH; p.b_chunks = p.Cin / KCH;
+    p.m_tiles = (p.Cout + 127) / 128;
+    p.tmem_cols = next_pow2_cols(3 * p.Cin);
+    CUtensorMap tmZ, tmX;
+    int rc = make_act_map(&tmZ, d->dz, d->N, p.Ho, p.Wo, d->Cout, 1, WG_TILE, WG_TILE);
+    if (rc) return rc;
+    rc = make_act_map(&tmX, d->x, d->N, d->H, d->W, d->Cin, d->stride, WG_TILE, WG_TILE);
+    if (rc) return rc;
+    const size_t stage_bytes = (size_t)4 * WG_CHUNK_BYTES + (size_t)p.b_chunks * WG_CHUNK_BYTES;
+    const size_t smem = WG_STAGES * stage_bytes + 1024;
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        if (e != cudaSuccess) return sci_fail(SCI_ELAUNCH, "wgrad tc: smem attribute", e);
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    const int groups = 3 * p.m_tiles;
+    const int gx = max(1, min(p.num_tiles, (2 * SCI_NUM_SMS) / groups));
+    conv_wgrad_tc_kernel<<<dim3(gx, groups), TC_THREADS, smem, sci_stream(stream)>>>(tmZ, tmX, p);
+    SCI_CHECK_LAUNCH("conv tc wgrad");
+    return SCI_OK;
+}
+
 int check_conv_desc(const sci_conv_desc* d) {
     SCI_REQUIRE(d && d->x && d->w && d->y, "conv: null pointer");
     SCI_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "conv: shape");
@@ -386,7 +553,7 @@ extern "C" int sci_conv3x3_wgrad(const sci_wgrad_desc* d, int impl, void* stream
     SCI_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0 && (d->stride == 1 || d->stride == 2),
                 "wgrad: shape");
     SCI_REQUIRE(d->Cin % 4 == 0 && d->Cout % 4 == 0, "wgrad: channels % 4");
-    // TODO(round 1): tcgen05 weight-gradient kernel (MN-major operands); until then both impls use the fp32 kernel
-    (void)impl;
-    return sci_wgrad_ref_launch(d, stream);
+    if (impl == SCI_CONV_REF) return sci_wgrad_ref_launch(d, stream);
+    if (impl == SCI_CONV_TC) return conv_wgrad_tc_launch(d, stream);
+    return sci_fail(SCI_EINVAL, "wgrad: unknown impl");
 }

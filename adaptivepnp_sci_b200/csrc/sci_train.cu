@@ -19,7 +19,7 @@ __device__ __forceinline__ int out_column(int co, int Co, int ps) {
 
 __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restrict__ packed, int Co, int Ci, int groups,
                                     int Co_pad, int Ci_pad, int ps, const float* __restrict__ oscale, int tflip,
-                                    int round_tf32) {
+                                    int round_tf32, int ci_dup) {
     const long total = (long)9 * Co_pad * Ci_pad;
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
@@ -27,6 +27,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restri
     if (!tflip) { ci = (int)(idx % Ci_pad); col = (int)((idx / Ci_pad) % Co_pad); tap = (int)(idx / ((long)Ci_pad * Co_pad)); }
     else        { col = (int)(idx % Co_pad); ci = (int)((idx / Co_pad) % Ci_pad); tap = (int)(idx / ((long)Ci_pad * Co_pad)); }
     float v = 0.f;
+    if (ci_dup > 0 && ci >= ci_dup && ci < ci_dup + Ci) ci -= ci_dup;     // remainder copy of the input: same weights
     if (col < Co && ci < Ci) {
         // invert the column permutation: which torch channel lives in this column?
         const int co = ps ? (col % (Co >> 2)) * 4 + col / (Co >> 2) : col;
@@ -42,7 +43,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restri
 }
 
 __global__ void unpack_wgrad_kernel(const float* __restrict__ packed, float* __restrict__ dw, int Co, int Ci, int groups,
-                                    int Co_pad, int Ci_pad, int ps) {
+                                    int Co_pad, int Ci_pad, int ps, int ci_dup) {
     const int cig = Ci / groups, cog = Co / groups;
     const long total = (long)Co * cig * 9;
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -50,7 +51,9 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ packed, float* __r
     const int tap = (int)(idx % 9), cil = (int)((idx / 9) % cig), co = (int)(idx / (9L * cig));
     const int ci = (co / cog) * cig + cil;
     const int col = out_column(co, Co, ps);
-    dw[idx] = packed[((long)tap * Co_pad + col) * Ci_pad + ci];
+    float g = packed[((long)tap * Co_pad + col) * Ci_pad + ci];
+    if (ci_dup > 0) g += packed[((long)tap * Co_pad + col) * Ci_pad + ci + ci_dup];
+    dw[idx] = g;
 }
 
 __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -136,14 +139,19 @@ __global__ void ffdnet_pack_kernel(const float* __restrict__ u, float sigma, flo
     const int k = (int)(idx % Cpad);
     const long p = idx / Cpad;
     const int w = (int)(p % w2), h = (int)((p / w2) % h2), n = (int)(p / ((long)w2 * h2));
+    // round_tf32: channel k holds tf32(v), channel k+16 the remainder tf32(v - tf32(v)) (weights duplicated)
+    const int kk = (round_tf32 && k >= 16) ? k - 16 : k;
     float v = 0.f;
-    if (k < 12) {
-        const int c = k >> 2, dy = (k >> 1) & 1, dx = k & 1;
+    if (kk < 12) {
+        const int c = kk >> 2, dy = (kk >> 1) & 1, dx = kk & 1;
         v = u[(((long)n * 3 + c) * H + 2 * h + dy) * W + 2 * w + dx];
-    } else if (k == 12) {
+    } else if (kk == 12) {
         v = sigma;
     }
-    if (round_tf32) v = rna_tf32(v);
+    if (round_tf32) {
+        const float hi = rna_tf32(v);
+        v = (k >= 16) ? rna_tf32(v - hi) : hi;
+    }
     out[idx] = v;
 }
 
@@ -186,16 +194,20 @@ __global__ void fastdvd_pack_kernel(const float* __restrict__ frames, float sigm
     const int k = (int)(idx % Cpad);
     const long p = (idx / Cpad) % plane;
     const int f = (int)(idx / (Cpad * plane));
+    const int kk = (round_tf32 && k >= 16) ? k - 16 : k;      // k+16: remainder copy (see ffdnet_pack_kernel)
     float v = 0.f;
-    if (k < 12) {
-        const int slot = k >> 2, c = k & 3;
+    if (kk < 12) {
+        const int slot = kk >> 2, c = kk & 3;
         if (c == 3) v = sigma;
         else {
             const int src = (f + slot - 1 + B) % B;      // circular window (fastdvdnet.py:115)
             v = frames[((long)src * 3 + c) * plane + p];
         }
     }
-    if (round_tf32) v = rna_tf32(v);
+    if (round_tf32) {
+        const float hi = rna_tf32(v);
+        v = (k >= 16) ? rna_tf32(v - hi) : hi;
+    }
     out[idx] = v;
 }
 
@@ -294,22 +306,26 @@ inline int grid1d(long n, int block = 256) { return (int)((n + block - 1) / bloc
 }  // namespace
 
 extern "C" int sci_conv_pack_weights(const float* w, float* packed, int Co, int Ci, int groups, int Co_pad, int Ci_pad,
-                                     int ps, const float* oscale, int transpose_flip, int round_tf32, void* stream) {
+                                     int ps, const float* oscale, int transpose_flip, int round_tf32, int ci_dup,
+                                     void* stream) {
     SCI_REQUIRE(w && packed && Co > 0 && Ci > 0 && groups > 0 && Co % groups == 0 && Ci % groups == 0, "pack_weights");
     SCI_REQUIRE(Co_pad >= Co && Ci_pad >= Ci && (!ps || Co % 4 == 0), "pack_weights: padding / pixel-shuffle");
     SCI_REQUIRE(!ps || Co_pad == Co, "pack_weights: pixel-shuffle columns cannot be padded");
+    SCI_REQUIRE(ci_dup == 0 || (ci_dup >= Ci && ci_dup + Ci <= Ci_pad), "pack_weights: ci_dup block does not fit");
     const long total = (long)9 * Co_pad * Ci_pad;
     pack_weights_kernel<<<grid1d(total), 256, 0, sci_stream(stream)>>>(w, packed, Co, Ci, groups, Co_pad, Ci_pad, ps, oscale,
-                                                                       transpose_flip, round_tf32);
+                                                                       transpose_flip, round_tf32, ci_dup);
     SCI_CHECK_LAUNCH("pack_weights");
     return SCI_OK;
 }
 
 extern "C" int sci_conv_unpack_wgrad(const float* packed_dw, float* dw, int Co, int Ci, int groups, int Co_pad, int Ci_pad,
-                                     int ps, void* stream) {
+                                     int ps, int ci_dup, void* stream) {
     SCI_REQUIRE(packed_dw && dw && Co > 0 && Ci > 0 && groups > 0 && Co_pad >= Co && Ci_pad >= Ci, "unpack_wgrad");
+    SCI_REQUIRE(ci_dup == 0 || (ci_dup >= Ci && ci_dup + Ci <= Ci_pad), "unpack_wgrad: ci_dup block does not fit");
     const long total = (long)Co * (Ci / groups) * 9;
-    unpack_wgrad_kernel<<<grid1d(total), 256, 0, sci_stream(stream)>>>(packed_dw, dw, Co, Ci, groups, Co_pad, Ci_pad, ps);
+    unpack_wgrad_kernel<<<grid1d(total), 256, 0, sci_stream(stream)>>>(packed_dw, dw, Co, Ci, groups, Co_pad, Ci_pad, ps,
+                                                                       ci_dup);
     SCI_CHECK_LAUNCH("unpack_wgrad");
     return SCI_OK;
 }
@@ -359,7 +375,8 @@ extern "C" int sci_nhwc_dilate2(const float* in, float* out, int N, int H, int W
 
 extern "C" int sci_ffdnet_pack_input(const float* u, float sigma, float* out, int B, int H, int W, int Cpad, int round_tf32,
                                      void* stream) {
-    SCI_REQUIRE(u && out && B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && Cpad >= 13, "ffdnet_pack_input");
+    SCI_REQUIRE(u && out && B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && Cpad >= (round_tf32 ? 32 : 13),
+                "ffdnet_pack_input");
     ffdnet_pack_kernel<<<grid1d((long)B * (H / 2) * (W / 2) * Cpad), 256, 0, sci_stream(stream)>>>(u, sigma, out, B, H, W, Cpad,
                                                                                                  round_tf32);
     SCI_CHECK_LAUNCH("ffdnet_pack_input");
@@ -383,7 +400,7 @@ extern "C" int sci_ffdnet_unpack_output_grad(const float* dxhat, float* dy, int 
 
 extern "C" int sci_fastdvd_pack_input(const float* frames, float sigma, float* out, int B, int H, int W, int Cpad,
                                       int round_tf32, void* stream) {
-    SCI_REQUIRE(frames && out && B > 0 && H > 0 && W > 0 && Cpad >= 12, "fastdvd_pack_input");
+    SCI_REQUIRE(frames && out && B > 0 && H > 0 && W > 0 && Cpad >= (round_tf32 ? 32 : 12), "fastdvd_pack_input");
     fastdvd_pack_kernel<<<grid1d((long)B * H * W * Cpad), 256, 0, sci_stream(stream)>>>(frames, sigma, out, B, H, W, Cpad,
                                                                                       round_tf32);
     SCI_CHECK_LAUNCH("fastdvd_pack_input");

@@ -112,7 +112,7 @@ class ParamBucket:
 class ConvLayer:
     """One 3x3 convolution of a network with its epilogue and its packed device-side state."""
 
-    def __init__(self, conv, bn=None, relu=False, stride=1, ps=False, cin_pad=None):
+    def __init__(self, conv, bn=None, relu=False, stride=1, ps=False, cin_pad=None, first=False):
         self.conv, self.bn, self.relu, self.stride, self.ps = conv, bn, relu, stride, ps
         self.Co, self.groups = conv.out_channels, conv.groups
         self.Ci = conv.in_channels
@@ -127,6 +127,7 @@ class ConvLayer:
         self.shift = torch.zeros(self.Co_pad, dtype=torch.float32, device=dev) if self.has_affine else None
         self.s1 = self.s2 = None
         self.dwpk = None
+        self.first = first       # network input layer: on the TF32 path its input arrives as hi + remainder copies
 
     def refresh_fwd(self, tf32):
         c = self.conv
@@ -136,8 +137,9 @@ class ConvLayer:
                  float(bn.eps), ptr(self.scale), ptr(self.shift), self.Co, self.Co_pad, stream())
         elif c.bias is not None:
             self.shift[:self.Co].copy_(c.bias.data)
+        self.ci_dup = 16 if (self.first and tf32) else 0
         call("sci_conv_pack_weights", ptr(c.weight.data), ptr(self.wpk), self.Co, self.Ci, self.groups, self.Co_pad,
-             self.Ci_pad, int(self.ps), None, 0, int(tf32), stream())
+             self.Ci_pad, int(self.ps), None, 0, int(tf32), self.ci_dup, stream())
 
     def refresh_bwd(self, tf32):
         """Data-gradient form of the weights: transposed, taps flipped, rows scaled by the folded BN scale."""
@@ -146,7 +148,7 @@ class ConvLayer:
             self.s1 = torch.zeros(self.Co_pad, dtype=torch.float32, device=self.wpk.device)
             self.s2 = torch.zeros(self.Co_pad, dtype=torch.float32, device=self.wpk.device)
         call("sci_conv_pack_weights", ptr(self.conv.weight.data), ptr(self.wpk_t), self.Co, self.Ci, self.groups,
-             self.Co_pad, self.Ci_pad, int(self.ps), ptr(self.scale), 1, int(tf32), stream())
+             self.Co_pad, self.Ci_pad, int(self.ps), ptr(self.scale), 1, int(tf32), self.ci_dup, stream())
 
 
 class _Workspace:
@@ -256,7 +258,7 @@ class _EngineBase:
         """packed dW -> torch-layout grad slot; bias / BatchNorm affine grads from the column sums."""
         b = self.bucket
         call("sci_conv_unpack_wgrad", ptr(L.dwpk), ptr(b.grad_view(L.conv.weight)), L.Co, L.Ci, L.groups, L.Co_pad,
-             L.Ci_pad, int(L.ps), stream())
+             L.Ci_pad, int(L.ps), L.ci_dup, stream())
         if L.bn is not None:
             call("sci_bn_param_grad", ptr(L.s1), ptr(L.s2), ptr(L.bn.weight.data), ptr(L.bn.bias.data),
                  ptr(b.grad_view(L.bn.weight)), ptr(b.grad_view(L.bn.bias)), L.Co, stream())
@@ -276,7 +278,7 @@ class FFDNetEngine(_EngineBase):
         layers = []
         for i, c in enumerate(convs):
             last = i == len(convs) - 1
-            layers.append(ConvLayer(c, None, relu=not last))
+            layers.append(ConvLayer(c, None, relu=not last, first=(i == 0)))
         super().__init__(module, layers)
         self.in_nc, self.out_nc = module.in_nc, module.out_nc
         if (self.in_nc, self.out_nc) != (3, 3):
@@ -341,7 +343,7 @@ class _DenBlockLayers:
         specs = block.conv_specs()
         self.L = []
         for i, (conv, bn, relu, stride, ps) in enumerate(specs):
-            self.L.append(ConvLayer(conv, bn, relu=relu, stride=stride, ps=ps))
+            self.L.append(ConvLayer(conv, bn, relu=relu, stride=stride, ps=ps, first=(i == 0)))
 
 
 class FastDVDnetEngine(_EngineBase):

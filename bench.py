@@ -245,6 +245,10 @@ def main():
     eng.forward(u, SIGMA[0])
     torch.cuda.synchronize()
     prof, eng.profile = eng.profile, None
+    if os.environ.get("SCI_BENCH_VERBOSE"):
+        for ev0, ev1, fl, tag in prof:
+            t_ms = ev0.elapsed_time(ev1)
+            sys.stderr.write("  %-28s %8.3f ms %8.1f TFLOP/s\n" % (tag, t_ms, fl / t_ms / 1e9))
     flops = sum(p[2] for p in prof)
     conv_s = sum(p[0].elapsed_time(p[1]) for p in prof) * 1e-3
     achieved = flops / conv_s / 1e12

@@ -194,12 +194,16 @@ int sci_conv3x3_wgrad(const sci_wgrad_desc* d, int impl, void* stream);
 /* PyTorch weight [Co][Ci/groups][3][3] -> packed [9][Co_pad][Ci_pad] (zero padded; grouped convs become
  * block-diagonal; ps != 0 permutes output columns for PixelShuffle(2): column q*(Co/4)+c <- channel c*4+q).
  * transpose_flip != 0 packs the data-gradient form [9][Ci_pad][Co_pad] with taps flipped and rows scaled by
- * oscale (may be NULL).  round_tf32 != 0 rounds to TF32 (RNA). */
+ * oscale (may be NULL).  round_tf32 != 0 rounds to TF32 (RNA).
+ * ci_dup > 0 (first layers on the tensor-core path): input channels [ci_dup, ci_dup+Ci) get the SAME weights as
+ * [0, Ci).  The network-boundary packers put tf32(v) in channel k and the remainder tf32(v - tf32(v)) in channel
+ * k + ci_dup, so the first layer sees its input at ~2^-22 relative precision at no extra cost (K is padded to 32
+ * anyway); sci_conv_unpack_wgrad then sums the two gradient blocks. */
 int sci_conv_pack_weights(const float* w, float* packed, int Co, int Ci, int groups, int Co_pad, int Ci_pad,
-                          int ps, const float* oscale, int transpose_flip, int round_tf32, void* stream);
+                          int ps, const float* oscale, int transpose_flip, int round_tf32, int ci_dup, void* stream);
 /* inverse of the forward packing for gradients: dw_torch[Co][Ci/groups][3][3] = packed_dw (assign) */
 int sci_conv_unpack_wgrad(const float* packed_dw, float* dw, int Co, int Ci, int groups, int Co_pad, int Ci_pad,
-                          int ps, void* stream);
+                          int ps, int ci_dup, void* stream);
 
 /* BatchNorm (eval mode, packages/fastdvdnet/models.py:21-26) folded to per-column scale/shift:
  * scale = gamma*rsqrt(var+eps), shift = beta - mean*scale; columns >= C are zeroed up to C_pad. */
