@@ -80,10 +80,11 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uin
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
-// K-major / MN-major shared-memory matrix descriptor, SWIZZLE_128B, version 1 (sm_100)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// Shared-memory matrix descriptor, version 1 (sm_100).  layout: 2 = SWIZZLE_128B (K-major operands),
+// 1 = SWIZZLE_128B_BASE32B (the only layout tcgen05 accepts for MN-major TF32 operands).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint64_t layout = 2) {
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (layout << 61);
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
@@ -279,7 +280,8 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // NHWC activation tensor [N][H][W][C], box = {32 ch, TILE_W*stride, TILE_H*stride, 1} traversed with element stride `stride`
-int make_act_map(CUtensorMap* tm, const float* x, int N, int H, int W, int C, int stride, int box_w, int box_h) {
+int make_act_map(CUtensorMap* tm, const float* x, int N, int H, int W, int C, int stride, int box_w, int box_h,
+                 CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return sci_fail(SCI_ELAUNCH, "cuTensorMapEncodeTiled entry point not available");
     const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
@@ -287,8 +289,7 @@ int make_act_map(CUtensorMap* tm, const float* x, int N, int H, int W, int C, in
     const cuuint32_t box[4] = {KCH, (cuuint32_t)(box_w * stride), (cuuint32_t)(box_h * stride), 1};
     const cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         char msg[96];
         snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled(activations) failed with CUresult %d", (int)r);
@@ -361,7 +362,8 @@ int conv_fwd_tc_launch(const sci_conv_desc* d, void* stream) {
 // ---------------------------------------------------------------------------------------------------
 // weight-gradient kernel (conv_wgrad_tc_kernel)
 //   dW[tap][co][ci] += oscale[co] * sum_pixels dz[p][co] * x[p (+) tap][ci]
-//   GEMM view: D[128 co][Cin] += A^T B over K = pixels, both operands MN-major (channels contiguous):
+//   GEMM view: D[128 co][Cin] += A^T B over K = pixels, both operands MN-major (channels contiguous; TMA swizzle
+//   128B_ATOM_32B <-> UMMA SWIZZLE_128B_BASE32B, the only MN-major layout tcgen05 accepts for TF32):
 //     A = dz tile  [64 pixels][Cout_tile]  = Cout_tile/32 TMA boxes {32 ch, 8 px, 8 rows, 1 image}
 //     B = x  tile  [64 pixels][Cin]        = Cin/32 TMA boxes at the tap-shifted (and, for stride-2 layers,
 //                                            element-strided) coordinates; out-of-image pixels are zero-filled
@@ -445,9 +447,10 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
                     const uint32_t d_tmem = tmem_base + (uint32_t)(s * p.Cin);
 #pragma unroll
                     for (int k8 = 0; k8 < WG_TILE * WG_TILE / 8; ++k8) {
-                        // MN-major SWIZZLE_128B: LBO = stride between 32-channel chunks, SBO = stride between 8-pixel groups
-                        tc_mma_tf32(d_tmem, umma_desc(a_addr + k8 * 1024, WG_CHUNK_BYTES, 1024),
-                                    umma_desc(b_addr + k8 * 1024, WG_CHUNK_BYTES, 1024), idesc, (uint32_t)(!first || k8 != 0));
+                        // MN-major SWIZZLE_128B_BASE32B (atom = 32 channels x 4 pixels): LBO = stride between
+                        // 32-channel chunks, SBO = stride between 4-pixel groups; one K=8 MMA spans two atoms
+                        tc_mma_tf32(d_tmem, umma_desc(a_addr + k8 * 1024, WG_CHUNK_BYTES, 512, 1),
+                                    umma_desc(b_addr + k8 * 1024, WG_CHUNK_BYTES, 512, 1), idesc, (uint32_t)(!first || k8 != 0));
                     }
                     tc_commit(&empty_bar[stage]);
                     if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
@@ -502,9 +505,9 @@ int conv_wgrad_tc_launch(const sci_wgrad_desc* d, void* stream) {
     p.m_tiles = (p.Cout + 127) / 128;
     p.tmem_cols = next_pow2_cols(3 * p.Cin);
     CUtensorMap tmZ, tmX;
-    int rc = make_act_map(&tmZ, d->dz, d->N, p.Ho, p.Wo, d->Cout, 1, WG_TILE, WG_TILE);
+    int rc = make_act_map(&tmZ, d->dz, d->N, p.Ho, p.Wo, d->Cout, 1, WG_TILE, WG_TILE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
-    rc = make_act_map(&tmX, d->x, d->N, d->H, d->W, d->Cin, d->stride, WG_TILE, WG_TILE);
+    rc = make_act_map(&tmX, d->x, d->N, d->H, d->W, d->Cin, d->stride, WG_TILE, WG_TILE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
     const size_t stage_bytes = (size_t)4 * WG_CHUNK_BYTES + (size_t)p.b_chunks * WG_CHUNK_BYTES;
     const size_t smem = WG_STAGES * stage_bytes + 1024;
