@@ -32,7 +32,7 @@ constexpr int MAX_STAGES = 8;
 
 struct FwdParams {
     const float* scale; const float* shift; const float* residual; float* y;
-    int N, H, W, Ho, Wo, Cin, Cout, stride, relu, ps, round_tf32;
+    int N, H, W, Ho, Wo, Cin, Cout, stride, relu, ps, round_tf32, wsplit;
     int tiles_w, tiles_h, num_tiles, k_chunks, stages, acc_stride, tmem_cols;
 };
 
@@ -130,7 +130,7 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t b_bytes = (uint32_t)p.Cout * KCH * 4;
-    const uint32_t stage_bytes = A_BYTES + b_bytes;
+    const uint32_t stage_bytes = A_BYTES + b_bytes * (1u + (uint32_t)p.wsplit);   // wsplit: tf32 hi + remainder weights
 
     for (int i = threadIdx.x; i < p.Cout; i += TC_THREADS) {
         s_scale[i] = p.scale ? p.scale[i] : 1.f;
@@ -171,6 +171,7 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         const uint32_t a_dst = smem_base + (uint32_t)stage * stage_bytes;
                         tma_load_4d(a_dst, &tmA, &full_bar[stage], kc * KCH, iw0 + s, ih0 + r, n);
                         tma_load_3d(a_dst + A_BYTES, &tmB, &full_bar[stage], kc * KCH, 0, tap);
+                        if (p.wsplit) tma_load_3d(a_dst + A_BYTES + b_bytes, &tmB, &full_bar[stage], kc * KCH, 0, tap + 9);
                         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                     }
                 }
@@ -194,6 +195,12 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     for (int k = 0; k < KCH / 8; ++k) {
                         tc_mma_tf32(d_tmem, umma_desc(a_addr + k * 32, 16, 1024), umma_desc(b_addr + k * 32, 16, 1024), idesc,
                                     (uint32_t)((ks | k) != 0));
+                    }
+                    if (p.wsplit) {
+#pragma unroll
+                        for (int k = 0; k < KCH / 8; ++k)
+                            tc_mma_tf32(d_tmem, umma_desc(a_addr + k * 32, 16, 1024), umma_desc(b_addr + b_bytes + k * 32, 16, 1024),
+                                        idesc, 1u);
                     }
                     tc_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -298,11 +305,11 @@ int make_act_map(CUtensorMap* tm, const float* x, int N, int H, int W, int C, in
     return SCI_OK;
 }
 
-// packed weights [9][Cout][Cin], box = {32 ch, Cout, 1}
-int make_weight_map(CUtensorMap* tm, const float* w, int Cout, int Cin) {
+// packed weights [taps][Cout][Cin] (taps = 9, or 18 with the hi/remainder split), box = {32 ch, Cout, 1}
+int make_weight_map(CUtensorMap* tm, const float* w, int Cout, int Cin, int taps) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return sci_fail(SCI_ELAUNCH, "cuTensorMapEncodeTiled entry point not available");
-    const cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, 9};
+    const cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)taps};
     const cuuint64_t strides[2] = {(cuuint64_t)Cin * 4, (cuuint64_t)Cout * Cin * 4};
     const cuuint32_t box[3] = {KCH, (cuuint32_t)Cout, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
@@ -331,17 +338,18 @@ int conv_fwd_tc_launch(const sci_conv_desc* d, void* stream) {
     p.N = d->N; p.H = d->H; p.W = d->W; p.stride = d->stride;
     p.Ho = (d->H - 1) / d->stride + 1; p.Wo = (d->W - 1) / d->stride + 1;
     p.Cin = d->Cin; p.Cout = d->Cout; p.relu = d->relu; p.ps = d->pixel_shuffle; p.round_tf32 = d->round_tf32;
+    p.wsplit = d->w_split ? 1 : 0;
     p.tiles_w = (p.Wo + TILE_W - 1) / TILE_W; p.tiles_h = (p.Ho + TILE_H - 1) / TILE_H;
     p.num_tiles = p.tiles_w * p.tiles_h * p.N;
     p.k_chunks = p.Cin / KCH;
-    const int stage_bytes = A_BYTES + p.Cout * KCH * 4;
+    const int stage_bytes = A_BYTES + p.Cout * KCH * 4 * (1 + p.wsplit);
     p.stages = min(MAX_STAGES, (216 * 1024) / stage_bytes);
     p.acc_stride = ((p.Cout + 31) / 32) * 32;
     p.tmem_cols = next_pow2_cols(2 * p.acc_stride);
     CUtensorMap tmA, tmB;
     int rc = make_act_map(&tmA, d->x, d->N, d->H, d->W, d->Cin, d->stride, TILE_W, TILE_H);
     if (rc) return rc;
-    rc = make_weight_map(&tmB, d->w, d->Cout, d->Cin);
+    rc = make_weight_map(&tmB, d->w, d->Cout, d->Cin, 9 * (1 + p.wsplit));
     if (rc) return rc;
     const size_t smem = (size_t)p.stages * stage_bytes + 1024;
     static bool attr_set[64] = {};
@@ -542,7 +550,10 @@ extern "C" int sci_conv_tc_available(void) { return 1; }
 extern "C" int sci_conv3x3_fwd(const sci_conv_desc* d, int impl, void* stream) {
     int rc = check_conv_desc(d);
     if (rc) return rc;
-    if (impl == SCI_CONV_REF) return sci_conv3x3_ref_launch(d, stream);
+    if (impl == SCI_CONV_REF) {
+        SCI_REQUIRE(!d->w_split, "conv ref: w_split is a tensor-core (TF32) option");
+        return sci_conv3x3_ref_launch(d, stream);
+    }
     if (impl == SCI_CONV_TC) return conv_fwd_tc_launch(d, stream);
     return sci_fail(SCI_EINVAL, "conv: unknown impl");
 }

@@ -38,6 +38,12 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restri
             if (tflip && oscale) v = v * oscale[col];
         }
     }
+    if (round_tf32 == 2) {              // split form: hi in taps 0..8, remainder in taps 9..17
+        const float hi = rna_tf32(v);
+        packed[idx] = hi;
+        packed[idx + total] = rna_tf32(v - hi);
+        return;
+    }
     if (round_tf32) v = rna_tf32(v);
     packed[idx] = v;
 }
@@ -312,6 +318,7 @@ extern "C" int sci_conv_pack_weights(const float* w, float* packed, int Co, int 
     SCI_REQUIRE(Co_pad >= Co && Ci_pad >= Ci && (!ps || Co % 4 == 0), "pack_weights: padding / pixel-shuffle");
     SCI_REQUIRE(!ps || Co_pad == Co, "pack_weights: pixel-shuffle columns cannot be padded");
     SCI_REQUIRE(ci_dup == 0 || (ci_dup >= Ci && ci_dup + Ci <= Ci_pad), "pack_weights: ci_dup block does not fit");
+    SCI_REQUIRE(round_tf32 != 2 || !transpose_flip, "pack_weights: split form is for forward weights only");
     const long total = (long)9 * Co_pad * Ci_pad;
     pack_weights_kernel<<<grid1d(total), 256, 0, sci_stream(stream)>>>(w, packed, Co, Ci, groups, Co_pad, Ci_pad, ps, oscale,
                                                                        transpose_flip, round_tf32, ci_dup);

@@ -172,6 +172,9 @@ typedef struct sci_conv_desc {
     int relu;               /* ReLU after scale/shift                                             */
     int pixel_shuffle;      /* 1: GEMM column q*(Cout/4)+c goes to sub-pixel q=(dy*2+dx), channel c */
     int round_tf32;         /* 1: round stored outputs to TF32 (they feed the next tensor-core conv) */
+    int w_split;            /* TC only. 1: w is [18][Cout][Cin] = tf32(w) in taps 0..8 and the remainder
+                               tf32(w - tf32(w)) in taps 9..17 (sci_conv_pack_weights round_tf32 = 2); both are
+                               multiplied, which removes the weight-rounding error of the TF32 path */
 } sci_conv_desc;
 
 /* 1 if this build contains the tcgen05 tensor-core convolution kernels. */
@@ -194,7 +197,8 @@ int sci_conv3x3_wgrad(const sci_wgrad_desc* d, int impl, void* stream);
 /* PyTorch weight [Co][Ci/groups][3][3] -> packed [9][Co_pad][Ci_pad] (zero padded; grouped convs become
  * block-diagonal; ps != 0 permutes output columns for PixelShuffle(2): column q*(Co/4)+c <- channel c*4+q).
  * transpose_flip != 0 packs the data-gradient form [9][Ci_pad][Co_pad] with taps flipped and rows scaled by
- * oscale (may be NULL).  round_tf32 != 0 rounds to TF32 (RNA).
+ * oscale (may be NULL).  round_tf32 = 1 rounds to TF32 (RNA); round_tf32 = 2 (forward form only) writes the split
+ * form [18][Co_pad][Ci_pad]: tf32(w) in taps 0..8 and tf32(w - tf32(w)) in taps 9..17 (see sci_conv_desc.w_split).
  * ci_dup > 0 (first layers on the tensor-core path): input channels [ci_dup, ci_dup+Ci) get the SAME weights as
  * [0, Ci).  The network-boundary packers put tf32(v) in channel k and the remainder tf32(v - tf32(v)) in channel
  * k + ci_dup, so the first layer sees its input at ~2^-22 relative precision at no extra cost (K is padded to 32

@@ -218,7 +218,8 @@ def test_adam_and_loss_kernels(cuda):
     for step, gr in enumerate(grads, 1):
         pr.grad = gr.clone()
         opt.step()
-        call("sci_adam_step", ptr(pd), ptr(gr.cuda()), ptr(m), ptr(v), 1000, 2e-6, 0.9, 0.999, 1e-8, step, stream())
+        gd = gr.cuda()
+        call("sci_adam_step", ptr(pd), ptr(gd), ptr(m), ptr(v), 1000, 2e-6, 0.9, 0.999, 1e-8, step, stream())
         assert float((pd.cpu() - pr.detach()).abs().max()) <= 2.5e-7          # <= 2 ulp of a unit-scale fp32 weight
     # loss + gradient vs autograd
     from oracle import sci_ops
@@ -231,6 +232,7 @@ def test_adam_and_loss_kernels(cuda):
     loss.backward()
     dx = torch.empty(B, 3, H, W, device=cuda)
     lo = torch.zeros(1, dtype=torch.float64, device=cuda)
-    call("sci_meas_loss_fwd_bwd", ptr(xhat.detach().cuda()), ptr(phi.cuda()), ptr(y.cuda()), ptr(dx), ptr(lo), H, W, B, stream())
+    xd, pd_, yd = xhat.detach().cuda(), phi.cuda(), y.cuda()       # keep the device tensors alive across the launch
+    call("sci_meas_loss_fwd_bwd", ptr(xd), ptr(pd_), ptr(yd), ptr(dx), ptr(lo), H, W, B, stream())
     assert abs(float(lo) - float(loss.detach())) < 1e-5 * float(loss.detach())
     assert _rel(dx.cpu(), xhat.grad) < 1e-5
