@@ -32,7 +32,7 @@ constexpr int MAX_STAGES = 8;
 
 struct FwdParams {
     const float* scale; const float* shift; const float* residual; float* y;
-    int N, H, W, Ho, Wo, Cin, Cout, stride, relu, ps, round_tf32, wsplit;
+    int N, H, W, Ho, Wo, Cin, Cout, stride, relu, ps, round_tf32, wsplit, emit_lo;
     int tiles_w, tiles_h, num_tiles, k_chunks, stages, acc_stride, tmem_cols;
 };
 
@@ -232,24 +232,27 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         const int qq = c0 / Cq, cc = c0 % Cq;
                         o = (((long)n * 2 * p.Ho + 2 * ho + (qq >> 1)) * 2 * p.Wo + 2 * wo + (qq & 1)) * Cq + cc;
                     } else {
-                        o = (((long)n * p.Ho + ho) * p.Wo + wo) * p.Cout + c0;
+                        o = (((long)n * p.Ho + ho) * p.Wo + wo) * (p.Cout << p.emit_lo) + c0;
                     }
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         if (j >= nc) break;
                         float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (p.residual) r4 = *reinterpret_cast<const float4*>(p.residual + o + j);
-                        float out[4];
+                        float out[4], lo[4];
                         const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             float t = v[j + e] * s_scale[c0 + j + e] + s_shift[c0 + j + e];
                             if (p.relu) t = fmaxf(t, 0.f);
                             t += rr[e];
-                            if (p.round_tf32) t = rna_tf32(t);
-                            out[e] = t;
+                            const float hi = p.round_tf32 ? rna_tf32(t) : t;
+                            lo[e] = rna_tf32(t - hi);
+                            out[e] = hi;
                         }
                         *reinterpret_cast<float4*>(p.y + o + j) = make_float4(out[0], out[1], out[2], out[3]);
+                        if (p.emit_lo)      // TF32 remainder of the activation, consumed by the next layer's duplicated weights
+                            *reinterpret_cast<float4*>(p.y + o + p.Cout + j) = make_float4(lo[0], lo[1], lo[2], lo[3]);
                     }
                 }
             }
@@ -339,6 +342,9 @@ int conv_fwd_tc_launch(const sci_conv_desc* d, void* stream) {
     p.Ho = (d->H - 1) / d->stride + 1; p.Wo = (d->W - 1) / d->stride + 1;
     p.Cin = d->Cin; p.Cout = d->Cout; p.relu = d->relu; p.ps = d->pixel_shuffle; p.round_tf32 = d->round_tf32;
     p.wsplit = d->w_split ? 1 : 0;
+    p.emit_lo = d->emit_lo ? 1 : 0;
+    if (p.emit_lo && (d->pixel_shuffle || d->residual || !d->round_tf32))
+        return sci_fail(SCI_EUNSUPPORTED, "conv tc: emit_lo needs round_tf32 and no pixel_shuffle / residual");
     p.tiles_w = (p.Wo + TILE_W - 1) / TILE_W; p.tiles_h = (p.Ho + TILE_H - 1) / TILE_H;
     p.num_tiles = p.tiles_w * p.tiles_h * p.N;
     p.k_chunks = p.Cin / KCH;
@@ -551,7 +557,7 @@ extern "C" int sci_conv3x3_fwd(const sci_conv_desc* d, int impl, void* stream) {
     int rc = check_conv_desc(d);
     if (rc) return rc;
     if (impl == SCI_CONV_REF) {
-        SCI_REQUIRE(!d->w_split, "conv ref: w_split is a tensor-core (TF32) option");
+        SCI_REQUIRE(!d->w_split && !d->emit_lo, "conv ref: w_split / emit_lo are tensor-core (TF32) options");
         return sci_conv3x3_ref_launch(d, stream);
     }
     if (impl == SCI_CONV_TC) return conv_fwd_tc_launch(d, stream);

@@ -33,7 +33,7 @@ class ConvDesc(ctypes.Structure):
     _fields_ = [("x", _f32p), ("w", _f32p), ("scale", _f32p), ("shift", _f32p), ("residual", _f32p), ("y", _f32p),
                 ("N", ctypes.c_int), ("H", ctypes.c_int), ("W", ctypes.c_int), ("Cin", ctypes.c_int),
                 ("Cout", ctypes.c_int), ("stride", ctypes.c_int), ("relu", ctypes.c_int),
-                ("pixel_shuffle", ctypes.c_int), ("round_tf32", ctypes.c_int), ("w_split", ctypes.c_int)]
+                ("pixel_shuffle", ctypes.c_int), ("round_tf32", ctypes.c_int), ("w_split", ctypes.c_int), ("emit_lo", ctypes.c_int)]
 
 
 class WgradDesc(ctypes.Structure):
@@ -112,11 +112,16 @@ class ParamBucket:
 class ConvLayer:
     """One 3x3 convolution of a network with its epilogue and its packed device-side state."""
 
-    def __init__(self, conv, bn=None, relu=False, stride=1, ps=False, cin_pad=None, first=False, wsplit=False):
+    def __init__(self, conv, bn=None, relu=False, stride=1, ps=False, cin_pad=None, first=False, wsplit=False,
+                 dup_in=False):
         self.conv, self.bn, self.relu, self.stride, self.ps = conv, bn, relu, stride, ps
         self.Co, self.groups = conv.out_channels, conv.groups
         self.Ci = conv.in_channels
         self.Ci_pad = cin_pad or _pad(self.Ci, 32)
+        self.dup_in = dup_in     # input tensor carries [hi | remainder] halves of Ci_pad channels each (emit_lo producer)
+        if dup_in:
+            self.ci_half = self.Ci_pad
+            self.Ci_pad *= 2
         self.Co_pad = self.Co if ps else _pad(self.Co, 32)   # multiple of 32: it is the K extent of the data-gradient GEMM
         self.out_ch = self.Co_pad // 4 if ps else self.Co_pad       # channels of the stored output tensor
         dev = conv.weight.device
@@ -138,7 +143,7 @@ class ConvLayer:
                  float(bn.eps), ptr(self.scale), ptr(self.shift), self.Co, self.Co_pad, stream())
         elif c.bias is not None:
             self.shift[:self.Co].copy_(c.bias.data)
-        self.ci_dup = 16 if (self.first and tf32) else 0
+        self.ci_dup = self.ci_half if self.dup_in else (16 if (self.first and tf32) else 0)
         call("sci_conv_pack_weights", ptr(c.weight.data), ptr(self.wpk), self.Co, self.Ci, self.groups, self.Co_pad,
              self.Ci_pad, int(self.ps), None, 0, (2 if (tf32 and self.wsplit) else int(tf32)), self.ci_dup, stream())
 
@@ -198,7 +203,7 @@ class _EngineBase:
             self.bucket = ParamBucket(list(self.module.parameters()))
             self.dirty = True
         if self.dirty or self._version() != self._seen_version:
-            for L in self.layers:
+            for L in self.layers + (getattr(self, "layers_inf", None) or []):
                 L.refresh_fwd(self.tf32)
             self._seen_version = self._version()
             self._bwd_valid = False
@@ -216,9 +221,10 @@ class _EngineBase:
                 off += n
 
     # ---- kernel wrappers ------------------------------------------------------------------------------
-    def conv(self, L, x, N, H, W, y, residual=None, round_out=True):
+    def conv(self, L, x, N, H, W, y, residual=None, round_out=True, emit_lo=False):
         d = ConvDesc(_dp(x), _dp(L.wpk), _dp(L.scale), _dp(L.shift), _dp(residual), _dp(y), N, H, W, L.Ci_pad, L.Co_pad,
-                     L.stride, int(L.relu), int(L.ps), int(self.tf32 and round_out), int(self.tf32 and L.wsplit))
+                     L.stride, int(L.relu), int(L.ps), int(self.tf32 and round_out), int(self.tf32 and L.wsplit),
+                     int(emit_lo))
         if self.profile is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
@@ -233,7 +239,7 @@ class _EngineBase:
     def dgrad(self, L, dz, N, Ho, Wo, dx, residual=None):
         """dx[N,Ho,Wo,Ci_pad] = conv(dz, packed transposed+flipped (and BN-scaled) weights) [+ residual]."""
         d = ConvDesc(_dp(dz), _dp(L.wpk_t), None, None, _dp(residual), _dp(dx), N, Ho, Wo, L.Co_pad, L.Ci_pad, 1, 0, 0,
-                     int(self.tf32), 0)
+                     int(self.tf32), 0, 0)
         call("sci_conv3x3_dgrad", ctypes.byref(d), self.impl, stream())
         self.n_launch += 1
 
@@ -283,6 +289,13 @@ class FFDNetEngine(_EngineBase):
             # undamped: on the TF32 path its weights are kept as tf32 hi + remainder (north_star 1e-3 max-abs bound)
             layers.append(ConvLayer(c, None, relu=not last, first=(i == 0), wsplit=(default_impl() == IMPL_TC)))
         super().__init__(module, layers)
+        # inference on the TF32 path uses "3xTF32": every activation is stored as tf32 hi + remainder and every weight
+        # as tf32 hi + remainder, which brings the conv stack to ~fp32 accuracy (FFDNet has no residual connection, so
+        # plain TF32 rounding reaches the output undamped and is then integrated by the ADMM dual variables)
+        self.layers_inf = None
+        if self.tf32:
+            self.layers_inf = [ConvLayer(c, None, relu=(i < len(convs) - 1), first=(i == 0), wsplit=True, dup_in=(i > 0))
+                               for i, c in enumerate(convs)]
         self.in_nc, self.out_nc = module.in_nc, module.out_nc
         if (self.in_nc, self.out_nc) != (3, 3):
             raise NotImplementedError("native FFDNet engine: colour model (in_nc=out_nc=3); the gray model of "
@@ -296,6 +309,8 @@ class FFDNetEngine(_EngineBase):
         self.prepare(training=train)
         dev = u.device
         h2, w2 = H // 2, W // 2
+        if not train and self.layers_inf is not None:
+            return self._forward_precise(u, sigma, B, H, W)
         L0 = self.layers[0]
         a = self.ws.get("in", (B, h2, w2, L0.Ci_pad), dev)
         call("sci_ffdnet_pack_input", ptr(u), float(sigma), ptr(a), B, H, W, L0.Ci_pad, int(self.tf32), stream())
@@ -309,6 +324,21 @@ class FFDNetEngine(_EngineBase):
         call("sci_ffdnet_unpack_output", ptr(acts[-1]), ptr(xhat), B, H, W, self.layers[-1].Co_pad, stream())
         if train:
             self._saved = (acts, B, H, W)
+        return xhat
+
+    def _forward_precise(self, u, sigma, B, H, W):
+        dev = u.device
+        h2, w2 = H // 2, W // 2
+        Ls = self.layers_inf
+        a = self.ws.get("in", (B, h2, w2, Ls[0].Ci_pad), dev)
+        call("sci_ffdnet_pack_input", ptr(u), float(sigma), ptr(a), B, H, W, Ls[0].Ci_pad, 1, stream())
+        for i, L in enumerate(Ls):
+            last = i == len(Ls) - 1
+            y = self.ws.get("tail" if last else "ppx%d" % (i % 2), (B, h2, w2, L.Co_pad * (1 if last else 2)), dev)
+            self.conv(L, a, B, h2, w2, y, round_out=not last, emit_lo=not last)
+            a = y
+        xhat = self.ws.get("xhat", (B, 3, H, W), dev)
+        call("sci_ffdnet_unpack_output", ptr(a), ptr(xhat), B, H, W, Ls[-1].Co_pad, stream())
         return xhat
 
     def backward(self, dxhat):

@@ -1,0 +1,56 @@
+"""Minimal I/O for the scripts: the stage-1 -> stage-2 hand-off file and the dataset loader.
+
+The reference reads MATLAB v7.3 datasets with h5py (ADMM_TV_Warm_Start_save.py:69-74) and hands the warm start
+to stage 2 through ``results/savedmat/_Admm_tv_<name>8.mat`` (key ``v_Admm_tv_denoise``, [H,W,B*nmea] float32;
+:174-178 <-> two_stage_ADMM_Online_FFD_Warm.py:171-176).  The hand-off file is written/read with scipy.io exactly
+as in the reference.  Dataset files are read with h5py when it is installed; no dataset ships with the
+reference (readme.md:22-23), so the scripts fall back to the deterministic synthetic videos of ``synthetic.py``
+when ``dataset/cacti/mid_scale/<name>.mat`` is absent (``--synthetic`` forces it)."""
+import os
+
+import numpy as np
+import scipy.io as sio
+
+from .synthetic import make_case
+
+VIDEOS = ['Beauty_bayer', 'Bosphorus_bayer', 'Jockey_bayer', 'Runner_bayer', 'ShakeNDry_bayer', 'Traffic_bayer']
+
+
+def load_video(datasetdir, datname, nmea=4, synthetic_shape=(512, 512, 8), force_synthetic=False):
+    """Returns meas_bayer [H,W,nmea] (0..255 scale), mask_bayer [H,W,B], orig_bayer [H,W,B*nmea] (0..255 scale)."""
+    path = os.path.join(datasetdir, datname + '.mat')
+    if not force_synthetic and os.path.exists(path):
+        try:
+            import h5py
+        except ImportError as e:
+            raise ImportError("reading the MATLAB v7.3 dataset %s needs h5py, which is not installed" % path) from e
+        with h5py.File(path, 'r') as f:
+            meas = np.float32(np.array(f['meas_bayer']))
+            mask = np.float32(np.array(f['mask_bayer'])).transpose((2, 1, 0))
+            orig = np.float32(np.array(f['orig_bayer'])).transpose((2, 1, 0))
+        meas = meas.transpose((1, 0))[:, :, None] if meas.ndim < 3 else meas.transpose((2, 1, 0))
+        return meas, mask, orig
+    H, W, B = synthetic_shape
+    vid = VIDEOS.index(datname) if datname in VIDEOS else 0
+    meas_l, orig_l, mask = [], [], None
+    for g in range(nmea):
+        m, msk, o = make_case(H, W, B, 3000 + 10 * vid + g, bayer=True)
+        mask = msk if mask is None else mask
+        meas_l.append((o * mask).sum(2) * 255.0)
+        orig_l.append(o * 255.0)
+    return np.stack(meas_l, 2).astype(np.float32), mask, np.concatenate(orig_l, 2).astype(np.float32)
+
+
+def warm_start_path(savedmatdir, datname, nmask):
+    return '{}_Admm_{}_{}{:d}.mat'.format(savedmatdir, 'tv', datname, nmask)
+
+
+def save_warm_start(savedmatdir, datname, nmask, v, psnr, ssim):
+    os.makedirs(savedmatdir, exist_ok=True)
+    p = warm_start_path(savedmatdir, datname, nmask)
+    sio.savemat(p, {'v_Admm_tv_denoise': v, 'psnr_Admm_tv_denoise': psnr, 'ssim_Admm_tv_denoise': ssim})
+    return p
+
+
+def load_warm_start(savedmatdir, datname, nmask):
+    return np.array(sio.loadmat(warm_start_path(savedmatdir, datname, nmask))['v_Admm_tv_denoise'], dtype=np.float32)

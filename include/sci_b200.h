@@ -175,6 +175,8 @@ typedef struct sci_conv_desc {
     int w_split;            /* TC only. 1: w is [18][Cout][Cin] = tf32(w) in taps 0..8 and the remainder
                                tf32(w - tf32(w)) in taps 9..17 (sci_conv_pack_weights round_tf32 = 2); both are
                                multiplied, which removes the weight-rounding error of the TF32 path */
+    int emit_lo;            /* TC only. 1: y has 2*Cout channels per pixel: [tf32(v) | tf32(v - tf32(v))]; the next
+                               layer is packed with ci_dup = Cout so it multiplies both ("3xTF32": ~fp32 accuracy) */
 } sci_conv_desc;
 
 /* 1 if this build contains the tcgen05 tensor-core convolution kernels. */
