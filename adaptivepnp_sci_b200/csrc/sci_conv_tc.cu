@@ -16,6 +16,7 @@
 //     (tmem_full/tmem_empty) between MMA and epilogue, so the epilogue of tile i overlaps the MMAs of i+1.
 // Weight-gradient kernel (conv_wgrad_tc_kernel): see the comment above its definition.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "sci_common.cuh"
 
@@ -270,6 +271,194 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// forward / data-gradient kernel, version 2 (stride-1 layers, Cout <= 128): operand reuse
+//   Profile of version 1 (profiles/): tensor pipe 19-43 % active, bound by the L2 -> shared-memory fill rate
+//   (~42 B/cycle/SM): every activation element was fetched 9x (once per tap) and the weights once per tile.
+//   Version 2 cuts the fill traffic:
+//   * tile = 128 consecutive pixels of ONE output row.  For filter row r and channel chunk kc a single TMA box
+//     {32 ch, 130 px, 1 row} is loaded; the three horizontal taps s = 0,1,2 are the SAME shared-memory tile read
+//     through UMMA descriptors whose start address is advanced by s pixels (s * 128 B; the hardware derives the
+//     swizzle phase from the absolute shared-memory address, so shifted views need no re-layout).  Activation fill traffic: 3x per element instead of 9x
+//     (the 3 vertical neighbours come from L2).
+//   * when all 9 x Cin x Cout weights fit beside the pipeline (<= ~150 KB: every 32/64/96-channel layer of
+//     FastDVDnet) they are loaded ONCE per CTA and stay resident; otherwise the three B tiles of a stage are
+//     streamed with the row box.
+// ---------------------------------------------------------------------------------------------------
+constexpr int ROW_PX = 130;
+constexpr int ROW_BYTES = ROW_PX * KCH * 4;       // 16640
+constexpr int A2_STAGE = 17 * 1024;               // row box rounded up to the 1024-byte swizzle period
+
+struct Fwd2Params {
+    const float* scale; const float* shift; const float* residual; float* y;
+    int N, H, W, Cin, Cout, relu, ps, round_tf32;
+    int tiles_w, num_tiles, k_chunks, stages, acc_stride, tmem_cols, resident, desc_mode;
+};
+
+__device__ __forceinline__ uint64_t umma_desc_off(uint32_t saddr, int mode) {
+    // K-major SWIZZLE_128B descriptor whose start is advanced by whole 128-byte rows inside the 1024-byte swizzle
+    // period.  Measured on B200: the swizzle XOR is taken from the ABSOLUTE shared-memory address bits, so the plain
+    // descriptor (base-offset field 0) reads exactly what TMA wrote; setting the base-offset field to
+    // (start >> 7) & 7 (mode 1, kept for experiments) gives wrong results.
+    uint64_t d = umma_desc(saddr, 16, 1024);
+    if (mode == 1) d |= (uint64_t)((saddr >> 7) & 7u) << 49;
+    return d;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Fwd2Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2], w_bar;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float s_scale[128], s_shift[128];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t b_bytes = (uint32_t)p.Cout * KCH * 4;
+    const uint32_t w_bytes = p.resident ? 9u * (uint32_t)p.k_chunks * b_bytes : 0u;
+    const uint32_t stage_bytes = A2_STAGE + (p.resident ? 0u : 3u * b_bytes);
+    const uint32_t ring_base = smem_base + w_bytes;
+
+    for (int i = threadIdx.x; i < p.Cout; i += TC_THREADS) {
+        s_scale[i] = p.scale ? p.scale[i] : 1.f;
+        s_shift[i] = p.shift ? p.shift[i] : 0.f;
+    }
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+        mbar_init(&w_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            if (p.resident) {
+                mbar_arrive_expect_tx(&w_bar, w_bytes);
+                for (int tap = 0; tap < 9; ++tap)
+                    for (int kc = 0; kc < p.k_chunks; ++kc)
+                        tma_load_3d(smem_base + (uint32_t)(tap * p.k_chunks + kc) * b_bytes, &tmB, &w_bar, kc * KCH, 0, tap);
+            }
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int wt = tile % p.tiles_w, h = (tile / p.tiles_w) % p.H, n = tile / (p.tiles_w * p.H);
+                for (int r = 0; r < 3; ++r) {
+                    for (int kc = 0; kc < p.k_chunks; ++kc) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1u);
+                        mbar_arrive_expect_tx(&full_bar[stage], ROW_BYTES + (p.resident ? 0u : 3u * b_bytes));
+                        const uint32_t a_dst = ring_base + (uint32_t)stage * stage_bytes;
+                        tma_load_4d(a_dst, &tmA, &full_bar[stage], kc * KCH, wt * 128 - 1, h + r - 1, n);
+                        if (!p.resident) {
+                            for (int s = 0; s < 3; ++s)
+                                tma_load_3d(a_dst + A2_STAGE + (uint32_t)s * b_bytes, &tmB, &full_bar[stage], kc * KCH, 0, r * 3 + s);
+                        }
+                        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Cout >> 3) << 17) | ((128u >> 4) << 24);
+            if (p.resident) { mbar_wait(&w_bar, 0); tc_fence_after(); }
+            int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
+                for (int r = 0; r < 3; ++r) {
+                    for (int kc = 0; kc < p.k_chunks; ++kc) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a_addr = ring_base + (uint32_t)stage * stage_bytes;
+#pragma unroll
+                        for (int s = 0; s < 3; ++s) {
+                            const uint32_t b_addr = p.resident ? smem_base + (uint32_t)((r * 3 + s) * p.k_chunks + kc) * b_bytes
+                                                               : a_addr + A2_STAGE + (uint32_t)s * b_bytes;
+#pragma unroll
+                            for (int k = 0; k < KCH / 8; ++k) {
+                                tc_mma_tf32(d_tmem, umma_desc_off(a_addr + s * 128 + k * 32, p.desc_mode),
+                                            umma_desc(b_addr + k * 32, 16, 1024), idesc, (uint32_t)((r | kc | s | k) != 0));
+                            }
+                        }
+                        tc_commit(&empty_bar[stage]);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+                tc_commit(&tfull_bar[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue =====
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const int Cq = p.Cout >> 2;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int wt = tile % p.tiles_w, ho = (tile / p.tiles_w) % p.H, n = tile / (p.tiles_w * p.H);
+            const int wo = wt * 128 + m;
+            const bool valid = wo < p.W;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + (uint32_t)(acc * p.acc_stride) + ((uint32_t)(q * 32) << 16);
+            for (int c0 = 0; c0 < p.Cout; c0 += 32) {
+                float v[32];
+                tmem_ld32(t_row + c0, v);
+                if (valid) {
+                    long o;
+                    if (p.ps) {
+                        const int qq = c0 / Cq, cc = c0 % Cq;
+                        o = (((long)n * 2 * p.H + 2 * ho + (qq >> 1)) * 2 * p.W + 2 * wo + (qq & 1)) * Cq + cc;
+                    } else {
+                        o = (((long)n * p.H + ho) * p.W + wo) * p.Cout + c0;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.residual) r4 = *reinterpret_cast<const float4*>(p.residual + o + j);
+                        float out[4];
+                        const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float t = v[j + e] * s_scale[c0 + j + e] + s_shift[c0 + j + e];
+                            if (p.relu) t = fmaxf(t, 0.f);
+                            t += rr[e];
+                            out[e] = p.round_tf32 ? rna_tf32(t) : t;
+                        }
+                        *reinterpret_cast<float4*>(p.y + o + j) = make_float4(out[0], out[1], out[2], out[3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host side: TMA descriptors through the driver entry point (no libcuda link dependency)
 // ---------------------------------------------------------------------------------------------------
@@ -372,6 +561,70 @@ int conv_fwd_tc_launch(const sci_conv_desc* d, void* stream) {
     return SCI_OK;
 }
 
+
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+bool fwd2_eligible(const sci_conv_desc* d) {
+    return d->stride == 1 && d->Cout % 32 == 0 && d->Cout <= 128 && !d->w_split && !d->emit_lo &&
+           env_int("SCI_CONV_V2", 1) != 0;
+}
+
+int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream) {
+    if (d->Cin % KCH != 0) return sci_fail(SCI_EUNSUPPORTED, "conv tc v2: Cin % 32");
+    if (((uintptr_t)d->x | (uintptr_t)d->w | (uintptr_t)d->y | (uintptr_t)d->residual) & 15)
+        return sci_fail(SCI_EINVAL, "conv tc: pointers must be 16-byte aligned");
+    Fwd2Params p;
+    p.scale = d->scale; p.shift = d->shift; p.residual = d->residual; p.y = d->y;
+    p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;
+    p.relu = d->relu; p.ps = d->pixel_shuffle; p.round_tf32 = d->round_tf32;
+    p.tiles_w = (p.W + 127) / 128;
+    p.num_tiles = p.tiles_w * p.H * p.N;
+    p.k_chunks = p.Cin / KCH;
+    const int b_bytes = p.Cout * KCH * 4;
+    const int budget = 214 * 1024;
+    const int w_bytes = 9 * p.k_chunks * b_bytes;
+    p.resident = (w_bytes + 3 * A2_STAGE <= budget) ? 1 : 0;
+    if (env_int("SCI_CONV_RESIDENT", 1) == 0) p.resident = 0;
+    const int stage_bytes = A2_STAGE + (p.resident ? 0 : 3 * b_bytes);
+    p.stages = min(MAX_STAGES, (budget - (p.resident ? w_bytes : 0)) / stage_bytes);
+    if (p.stages < 2) return sci_fail(SCI_EUNSUPPORTED, "conv tc v2: pipeline does not fit");
+    p.acc_stride = p.Cout;
+    p.tmem_cols = next_pow2_cols(2 * p.acc_stride);
+    p.desc_mode = env_int("SCI_CONV_DESC_MODE", 0);
+    CUtensorMap tmA, tmB;
+    // activation map with a {32 ch, 130 px, 1 row, 1 image} box
+    {
+        EncodeTiledFn fn = get_encode_fn();
+        if (!fn) return sci_fail(SCI_ELAUNCH, "cuTensorMapEncodeTiled entry point not available");
+        const cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+        const cuuint64_t strides[3] = {(cuuint64_t)d->Cin * 4, (cuuint64_t)d->W * d->Cin * 4, (cuuint64_t)d->H * d->W * d->Cin * 4};
+        const cuuint32_t box[4] = {KCH, ROW_PX, 1, 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = fn(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(d->x), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return sci_fail(SCI_ELAUNCH, "cuTensorMapEncodeTiled(row box) failed");
+    }
+    int rc = make_weight_map(&tmB, d->w, d->Cout, d->Cin, 9);
+    if (rc) return rc;
+    const size_t smem = (size_t)(p.resident ? w_bytes : 0) + (size_t)p.stages * stage_bytes + 1024;
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(conv_fwd2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        if (e != cudaSuccess) return sci_fail(SCI_ELAUNCH, "conv tc v2: smem attribute", e);
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    const int grid = min(p.num_tiles, SCI_NUM_SMS);
+    conv_fwd2_tc_kernel<<<grid, TC_THREADS, smem, sci_stream(stream)>>>(tmA, tmB, p);
+    SCI_CHECK_LAUNCH("conv tc fwd v2");
+    return SCI_OK;
+}
 
 // ---------------------------------------------------------------------------------------------------
 // weight-gradient kernel (conv_wgrad_tc_kernel)
@@ -560,7 +813,7 @@ extern "C" int sci_conv3x3_fwd(const sci_conv_desc* d, int impl, void* stream) {
         SCI_REQUIRE(!d->w_split && !d->emit_lo, "conv ref: w_split / emit_lo are tensor-core (TF32) options");
         return sci_conv3x3_ref_launch(d, stream);
     }
-    if (impl == SCI_CONV_TC) return conv_fwd_tc_launch(d, stream);
+    if (impl == SCI_CONV_TC) return fwd2_eligible(d) ? conv_fwd2_tc_launch(d, stream) : conv_fwd_tc_launch(d, stream);
     return sci_fail(SCI_EINVAL, "conv: unknown impl");
 }
 

@@ -1,0 +1,62 @@
+"""CPU (gloo, world_size 2): the N>1 host logic — unit sharding, result gathering, shared-weight gradient sync."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    from adaptivepnp_sci_b200 import parallel
+    ctx = parallel.init(backend="gloo")
+    units = ctx.my_units(5)
+    # every rank "reconstructs" its own measurement groups
+    results = {u: (np.full((2, 2), u, np.float32), np.array([10.0 + u])) for u in units}
+    merged = ctx.gather_units(results)
+    # shared-weight fine-tune: identical averaged gradient on every rank
+    g = torch.full((7,), float(rank + 1))
+    ctx.grad_sync(g)
+    w = torch.zeros(3) + rank
+    ctx.broadcast_(w, 0)
+    ctx.barrier()
+    q.put((rank, units, sorted(merged.keys()), g.tolist(), w.tolist()))
+    ctx.finalize()
+
+
+def test_two_rank_sharding_and_grad_sync():
+    world, port = 2, _free_port()
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    procs = [ctxm.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, u0, m0, g0, w0), (r1, u1, m1, g1, w1) = out
+    assert u0 == [0, 2, 4] and u1 == [1, 3]                    # round-robin, disjoint, complete
+    assert m0 == [0, 1, 2, 3, 4] and m1 == []                  # gathered on rank 0 only
+    assert g0 == g1 == [1.5] * 7                               # mean of the two ranks' gradients
+    assert w0 == w1 == [0.0, 0.0, 0.0]
+
+
+def test_single_rank_is_identity():
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        os.environ.pop(k, None)
+    from adaptivepnp_sci_b200 import parallel
+    ctx = parallel.init(backend="gloo")
+    assert ctx.world == 1 and ctx.my_units(3) == [0, 1, 2]
+    g = torch.ones(4)
+    assert ctx.grad_sync(g) is g and ctx.gather_units({1: 2}) == {1: 2}
