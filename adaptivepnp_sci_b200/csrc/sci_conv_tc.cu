@@ -262,6 +262,7 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");    // TMA stores (if any) have landed
     }
     tc_fence_before();
     __syncthreads();
@@ -293,7 +294,7 @@ constexpr int A2_STAGE = 17 * 1024;               // row box rounded up to the 1
 struct Fwd2Params {
     const float* scale; const float* shift; const float* residual; float* y;
     int N, H, W, Cin, Cout, relu, ps, round_tf32;
-    int tiles_w, num_tiles, k_chunks, stages, acc_stride, tmem_cols, resident, desc_mode;
+    int tiles_w, num_tiles, k_chunks, stages, acc_stride, tmem_cols, resident, desc_mode, tma_store, out_bufs;
 };
 
 __device__ __forceinline__ uint64_t umma_desc_off(uint32_t saddr, int mode) {
@@ -307,7 +308,8 @@ __device__ __forceinline__ uint64_t umma_desc_off(uint32_t saddr, int mode) {
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Fwd2Params p) {
+conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmY, const Fwd2Params p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2], w_bar;
     __shared__ uint32_t tmem_slot;
@@ -319,6 +321,7 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t w_bytes = p.resident ? 9u * (uint32_t)p.k_chunks * b_bytes : 0u;
     const uint32_t stage_bytes = A2_STAGE + (p.resident ? 0u : 3u * b_bytes);
     const uint32_t ring_base = smem_base + w_bytes;
+    const uint32_t stage_out_base = ring_base + (uint32_t)p.stages * stage_bytes;   // 4 warps x 2 x 4 KB store staging
 
     for (int i = threadIdx.x; i < p.Cout; i += TC_THREADS) {
         s_scale[i] = p.scale ? p.scale[i] : 1.f;
@@ -410,6 +413,7 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int m = q * 32 + lane;
         const int Cq = p.Cout >> 2;
         int acc = 0; uint32_t acc_phase = 0;
+        uint32_t st_cnt = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             const int wt = tile % p.tiles_w, ho = (tile / p.tiles_w) % p.H, n = tile / (p.tiles_w * p.H);
             const int wo = wt * 128 + m;
@@ -420,6 +424,37 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int c0 = 0; c0 < p.Cout; c0 += 32) {
                 float v[32];
                 tmem_ld32(t_row + c0, v);
+                if (p.tma_store) {
+                    // coalesced path: the warp's 32 pixels x 32 channels go through a 128B-swizzled 4 KB staging tile
+                    // and leave as ONE TMA store (box {32 ch, 32 px}); out-of-image pixels are clipped by TMA
+                    const uint32_t sbuf = stage_out_base + (uint32_t)(q * p.out_bufs + (p.out_bufs == 2 ? (st_cnt & 1) : 0)) * 4096u;
+                    if (lane == 0) {
+                        if (p.out_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        else                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float out[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float t = v[j + e] * s_scale[c0 + j + e] + s_shift[c0 + j + e];
+                            if (p.relu) t = fmaxf(t, 0.f);
+                            out[e] = p.round_tf32 ? rna_tf32(t) : t;
+                        }
+                        const uint32_t a = sbuf + (uint32_t)lane * 128u + (uint32_t)(((j >> 2) ^ (lane & 7)) << 4);
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(out[0]), "f"(out[1]), "f"(out[2]), "f"(out[3]) : "memory");
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                                     ::"l"(&tmY), "r"(sbuf), "r"(c0), "r"(wt * 128 + q * 32), "r"(ho), "r"(n) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    ++st_cnt;
+                    continue;
+                }
                 if (valid) {
                     long o;
                     if (p.ps) {
@@ -450,6 +485,7 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");    // TMA stores (if any) have landed
     }
     tc_fence_before();
     __syncthreads();
@@ -585,9 +621,21 @@ int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream) {
     p.num_tiles = p.tiles_w * p.H * p.N;
     p.k_chunks = p.Cin / KCH;
     const int b_bytes = p.Cout * KCH * 4;
-    const int budget = 214 * 1024;
+    p.tma_store = (!d->pixel_shuffle && !d->residual && env_int("SCI_CONV_TMA_STORE", 1)) ? 1 : 0;
     const int w_bytes = 9 * p.k_chunks * b_bytes;
-    p.resident = (w_bytes + 3 * A2_STAGE <= budget) ? 1 : 0;
+    // shared-memory plan: [resident weights] [pipeline stages] [store staging: 4 warps x out_bufs x 4 KB]
+    const int total_budget = 214 * 1024;
+    int out_stage = 0, budget = 0;
+    for (p.out_bufs = 2; p.out_bufs >= 1; --p.out_bufs) {
+        out_stage = p.tma_store ? 4 * p.out_bufs * 4096 : 0;
+        budget = total_budget - out_stage;
+        p.resident = (w_bytes + 3 * A2_STAGE <= budget) ? 1 : 0;
+        const int sb = A2_STAGE + (p.resident ? 0 : 3 * b_bytes);
+        const int st = (budget - (p.resident ? w_bytes : 0)) / sb;
+        const bool would_be_resident = w_bytes + 3 * A2_STAGE <= total_budget - 4 * 4096;
+        if ((p.resident || !would_be_resident) && st >= 3) break;
+        if (p.out_bufs == 1) break;
+    }
     if (env_int("SCI_CONV_RESIDENT", 1) == 0) p.resident = 0;
     const int stage_bytes = A2_STAGE + (p.resident ? 0 : 3 * b_bytes);
     p.stages = min(MAX_STAGES, (budget - (p.resident ? w_bytes : 0)) / stage_bytes);
@@ -611,7 +659,19 @@ int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream) {
     }
     int rc = make_weight_map(&tmB, d->w, d->Cout, d->Cin, 9);
     if (rc) return rc;
-    const size_t smem = (size_t)(p.resident ? w_bytes : 0) + (size_t)p.stages * stage_bytes + 1024;
+    CUtensorMap tmY = tmA;
+    if (p.tma_store) {
+        EncodeTiledFn fn = get_encode_fn();
+        const cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+        const cuuint64_t strides[3] = {(cuuint64_t)d->Cout * 4, (cuuint64_t)d->W * d->Cout * 4, (cuuint64_t)d->H * d->W * d->Cout * 4};
+        const cuuint32_t box[4] = {KCH, 32, 1, 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = fn(&tmY, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d->y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return sci_fail(SCI_ELAUNCH, "cuTensorMapEncodeTiled(output) failed");
+    }
+    const size_t smem = (size_t)(p.resident ? w_bytes : 0) + (size_t)p.stages * stage_bytes + out_stage + 1024;
+    if (smem > 220 * 1024) return sci_fail(SCI_EUNSUPPORTED, "conv tc v2: shared memory budget exceeded");
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -621,7 +681,7 @@ int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream) {
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     const int grid = min(p.num_tiles, SCI_NUM_SMS);
-    conv_fwd2_tc_kernel<<<grid, TC_THREADS, smem, sci_stream(stream)>>>(tmA, tmB, p);
+    conv_fwd2_tc_kernel<<<grid, TC_THREADS, smem, sci_stream(stream)>>>(tmA, tmB, tmY, p);
     SCI_CHECK_LAUNCH("conv tc fwd v2");
     return SCI_OK;
 }

@@ -196,15 +196,10 @@ def twoStageAdmm_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, gamma=0.01,
     sched = []
     k = 0
     update_i = 0
-    noise_q = None
     if name == 'fastdvd_color' and update_:
-        # The FastDVDnet fine-tune perturbs its input with HOST numpy-RNG noise (utils_image.py:183-192).  The
-        # draws (same call, shape and order as the reference) are produced by a helper thread started now, so
-        # the ~25 ns/sample legacy generator overlaps the first ADMM iterations instead of stalling the GPU.
-        n_upd = sum(1 for kk in range(n_total) if kk > inital_iter and kk % interval_iter == 0)
-        if update_times >= 0:
-            n_upd = min(n_upd, update_times)
-        noise_q = fastdvdnet_adapter.NoisePrefetch((B, 3, H, W), n_upd)
+        # The FastDVDnet fine-tune perturbs its input with HOST numpy-RNG noise (utils_image.py:183-192); a helper
+        # thread keeps those draws ahead of the GPU with exact global-RNG semantics (fastdvdnet_adapter.NoiseStream).
+        fastdvdnet_adapter.noise_stream.prefetch((B, 3, H, W))
     for idx, nsig in enumerate(sigma):
         for _ in range(iter_max[idx]):
             # p = theta - b/rho ; x = p + Phi*((y - A p)/(alpha*rho + Phi_sum))                     (:128-140)
@@ -225,16 +220,13 @@ def twoStageAdmm_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, gamma=0.01,
                 else:
                     do_update = do_update and (update_i < update_times or update_times < 0)   # :247
                     xhat = fastdvdnet_adapter.denoise_planar(u, pb, nsig, model_denoise, lr_, do_update,
-                                                             update_per_iter, grad_sync=grad_sync,
-                                                             noise=noise_q.get() if do_update else None)
+                                                             update_per_iter, grad_sync=grad_sync)
                     update_i += int(do_update)
                 # theta = clip(RGGB samples of xhat) ; b += x - theta ; w += x_rgb - xhat [+ PSNR]    (:206-209, :265-280)
                 ops.dual_update_rgb(xhat, x_rgb, w, x, b, theta, first_iter=(k == 0),
                                     orig=pb.orig if want_iqa else None, sse=sse[k:k + 1] if want_iqa else None)
             sched.append(nsig)
             k += 1
-    if noise_q is not None:
-        noise_q.close()
     if return_device:
         return xhat, theta
     psnr_all = []

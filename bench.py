@@ -187,15 +187,15 @@ def main():
               update_=True, update_per_iter=UPDATE_PER_ITER, update_times=-1, grad_sync=grad_sync)
     d_meas, d_mask, d_warm = (torch.from_numpy(a).to(dev) for a in (meas, mask, warm))
 
+    worker_init_fn(0)      # seeds = 42 once, like the reference scripts (the fine-tune noise stream then continues)
+
     def step_device():
         reset_model()
-        worker_init_fn(0)
         return twoStageAdmm_denoise_bayer(d_meas, d_mask, 1, 0.01, 'fastdvd_color', ITERS, False, SIGMA, x0_bayer=d_warm,
                                           X_orig=None, show_iqa=False, return_device=True, **kw)
 
     def step_e2e():
         reset_model()
-        worker_init_fn(0)
         return twoStageAdmm_denoise_bayer(meas, mask, 1, 0.01, 'fastdvd_color', ITERS, False, SIGMA,
                                           x0_bayer=torch.from_numpy(warm).cuda(), X_orig=None, show_iqa=False, logf=None, **kw)
 
