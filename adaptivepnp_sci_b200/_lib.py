@@ -66,6 +66,7 @@ PROTOTYPES = {
     "sci_fastdvd_output_grad": [_p, _p, _i, _i, _i, _i, _p],
     "sci_fastdvd_pack_input_grad": [_p, _p, _i, _i, _i, _i, _i, _p],
     "sci_fastdvd_noisy_input": [_p, _p, _p, _l, _p],
+    "sci_host_legacy_normal": [_p, _p, _p, _p, _d, _d, _p, _l, _i],
     "sci_meas_loss_fwd_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _p],
     "sci_adam_step": [_p, _p, _p, _p, _l, _d, _d, _d, _d, _i, _p],
 }
@@ -103,7 +104,7 @@ def check(rc, what):
 
 
 # kernel launches issued through the C ABI since import (bench.py reports the count inside its timed region)
-KERNELS_PER_CALL = {"sci_tv_chambolle2d": 3, "sci_version": 0, "sci_conv_tc_available": 0}
+KERNELS_PER_CALL = {"sci_tv_chambolle2d": 3, "sci_version": 0, "sci_conv_tc_available": 0, "sci_host_legacy_normal": 0}
 launch_count = 0
 
 

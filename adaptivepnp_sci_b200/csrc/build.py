@@ -26,6 +26,7 @@ SOURCES = [
     ("sci_conv_ref.cu", []),
     ("sci_conv_tc.cu", []),
     ("sci_train.cu", ["--fmad=false"]),
+    ("sci_host_rng.cu", ["-Xcompiler", "-ffp-contract=off"]),
 ]
 
 
@@ -59,7 +60,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+    cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lpthread"]
     subprocess.check_call(cmd)
     with open(stamp, "w") as f:
         f.write(dig)

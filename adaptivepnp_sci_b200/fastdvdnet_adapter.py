@@ -54,6 +54,27 @@ def draw_finetune_noise(shape):
     return np.random.normal(0, 5 / 255, tuple(shape))
 
 
+def fast_legacy_normal(rs, loc, scale, shape, nthreads=None):
+    """``rs.normal(loc, scale, shape)`` for a legacy ``np.random.RandomState``, bit for bit (values and final state),
+    computed by the multi-threaded host routine ``sci_host_legacy_normal`` (~5x faster than numpy on 16 cores)."""
+    import ctypes
+    from ._lib import lib
+    name, key, pos, has_gauss, gauss = rs.get_state()
+    if name != 'MT19937':
+        return rs.normal(loc, scale, shape)
+    key = np.ascontiguousarray(key, dtype=np.uint32).copy()
+    n = int(np.prod(shape))
+    out = np.empty(n, dtype=np.float64)
+    c_pos, c_has, c_g = ctypes.c_int(int(pos)), ctypes.c_int(int(has_gauss)), ctypes.c_double(float(gauss))
+    rc = lib.sci_host_legacy_normal(key.ctypes.data_as(ctypes.c_void_p), ctypes.byref(c_pos), ctypes.byref(c_has),
+                                    ctypes.byref(c_g), float(loc), float(scale), out.ctypes.data_as(ctypes.c_void_p), n,
+                                    int(nthreads or min(16, os.cpu_count() or 1)))
+    if rc != 0:
+        raise SciError("sci_host_legacy_normal failed (%d)" % rc)
+    rs.set_state((name, key, c_pos.value, c_has.value, c_g.value))
+    return out.reshape(shape)
+
+
 def _state_key(st):
     """Comparable fingerprint of a numpy legacy RNG state tuple (MT19937 key, position, cached gaussian)."""
     return (st[0], st[1].tobytes(), st[2], st[3], st[4])
@@ -92,7 +113,7 @@ class NoiseStream:
                     return
                 shape, rs = self.shape, self.rs
             before = _state_key(rs.get_state())
-            arr = rs.normal(0, 5 / 255, shape)              # same call as utils/utils_image.py:186, private state
+            arr = fast_legacy_normal(rs, 0, 5 / 255, shape)   # == rs.normal(0, 5/255, shape) (utils_image.py:186), bit for bit
             after = rs.get_state()
             with self.lock:
                 if self.epoch != epoch:

@@ -255,6 +255,13 @@ int sci_fastdvd_pack_input_grad(const float* din, float* dframes, int B, int H, 
  * vplus = v + float32(float64(v) + noise), noise float64 from the host RNG. */
 int sci_fastdvd_noisy_input(const float* v, const double* noise, float* vplus, long n, void* stream);
 
+/* HOST function (no GPU work): numpy's LEGACY normal generator, bit for bit, multi-threaded.
+ * out_host[n] = loc + scale * legacy_gauss() exactly as np.random.RandomState.normal(loc, scale, n) would produce from
+ * the MT19937 state (key[624], pos, has_gauss, gauss), which is advanced in place.  Replaces the single-threaded draw
+ * inside add_gaussian_noise_meas_cuda (utils/utils_image.py:183-192). */
+int sci_host_legacy_normal(uint32_t* key_host, int* pos_host, int* has_gauss_host, double* gauss_host, double loc,
+                           double scale, double* out_host, long n, int nthreads);
+
 /* Measurement-consistency loss of the online fine-tune (test_ffdnet_ipol.py:275-291,
  * test_fastdvdnet.py:428-431):  m = RGGB samples of xhat; up = sum_t m_t*phi_t;
  * loss += mean((up - y)^2) over H*W (fp64 accumulate);  dxhat[t][c][p] = phi_t * 2(up-y)/(H*W) at the
