@@ -70,6 +70,13 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(dst), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// one lane of a fully converged warp (the role loops below are warp-uniform; only the issuing instruction is
+// predicated, so addresses and descriptors stay in uniform registers instead of per-MMA ELECT/BRA.U loops)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -86,6 +93,21 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uin
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint64_t layout = 2) {
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (layout << 61);
+}
+// Same instructions issued by ONE elected lane of a converged warp, with the election folded into the predicate of
+// the instruction itself: the surrounding code stays straight-line and warp-uniform (descriptor arithmetic in uniform
+// registers, no per-instruction divergence handling), which matters because the single issuing thread is the
+// critical path for narrow layers (an N=32 TF32 MMA occupies the tensor pipe for only ~67 cycles).
+__device__ __forceinline__ void tc_mma_tf32_elect(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
@@ -345,23 +367,26 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_slot, 0);
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ===== TMA producer =====
-            if (p.resident) {
+        // ===== TMA producer (warp-uniform loop, one elected lane issues) =====
+        if (p.resident) {
+            if (elect_one()) {
                 mbar_arrive_expect_tx(&w_bar, w_bytes);
                 for (int tap = 0; tap < 9; ++tap)
                     for (int kc = 0; kc < p.k_chunks; ++kc)
                         tma_load_3d(smem_base + (uint32_t)(tap * p.k_chunks + kc) * b_bytes, &tmB, &w_bar, kc * KCH, 0, tap);
             }
-            int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const int wt = tile % p.tiles_w, h = (tile / p.tiles_w) % p.H, n = tile / (p.tiles_w * p.H);
-                for (int r = 0; r < 3; ++r) {
-                    for (int kc = 0; kc < p.k_chunks; ++kc) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1u);
+            __syncwarp();
+        }
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int wt = tile % p.tiles_w, h = (tile / p.tiles_w) % p.H, n = tile / (p.tiles_w * p.H);
+            for (int r = 0; r < 3; ++r) {
+                for (int kc = 0; kc < p.k_chunks; ++kc) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    if (elect_one()) {
                         mbar_arrive_expect_tx(&full_bar[stage], ROW_BYTES + (p.resident ? 0u : 3u * b_bytes));
                         const uint32_t a_dst = ring_base + (uint32_t)stage * stage_bytes;
                         tma_load_4d(a_dst, &tmA, &full_bar[stage], kc * KCH, wt * 128 - 1, h + r - 1, n);
@@ -369,43 +394,44 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             for (int s = 0; s < 3; ++s)
                                 tma_load_3d(a_dst + A2_STAGE + (uint32_t)s * b_bytes, &tmB, &full_bar[stage], kc * KCH, 0, r * 3 + s);
                         }
-                        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                     }
+                    __syncwarp();
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer =====
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Cout >> 3) << 17) | ((128u >> 4) << 24);
-            if (p.resident) { mbar_wait(&w_bar, 0); tc_fence_after(); }
-            int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
-                for (int r = 0; r < 3; ++r) {
-                    for (int kc = 0; kc < p.k_chunks; ++kc) {
-                        mbar_wait(&full_bar[stage], phase);
-                        tc_fence_after();
-                        const uint32_t a_addr = ring_base + (uint32_t)stage * stage_bytes;
+        // ===== MMA issuer (warp-uniform loop, one elected lane issues) =====
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Cout >> 3) << 17) | ((128u >> 4) << 24);
+        const uint64_t desc_hi = umma_desc(0, 16, 1024);          // everything but the start-address field
+        if (p.resident) { mbar_wait(&w_bar, 0); tc_fence_after(); }
+        int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
+            for (int r = 0; r < 3; ++r) {
+                for (int kc = 0; kc < p.k_chunks; ++kc) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = ring_base + (uint32_t)stage * stage_bytes;
+                    const uint32_t b_base = p.resident ? smem_base + (uint32_t)(r * 3 * p.k_chunks + kc) * b_bytes : a_addr + A2_STAGE;
+                    const uint32_t b_step = p.resident ? (uint32_t)p.k_chunks * b_bytes : b_bytes;
 #pragma unroll
-                        for (int s = 0; s < 3; ++s) {
-                            const uint32_t b_addr = p.resident ? smem_base + (uint32_t)((r * 3 + s) * p.k_chunks + kc) * b_bytes
-                                                               : a_addr + A2_STAGE + (uint32_t)s * b_bytes;
+                    for (int s = 0; s < 3; ++s) {
 #pragma unroll
-                            for (int k = 0; k < KCH / 8; ++k) {
-                                tc_mma_tf32(d_tmem, umma_desc_off(a_addr + s * 128 + k * 32, p.desc_mode),
-                                            umma_desc(b_addr + k * 32, 16, 1024), idesc, (uint32_t)((r | kc | s | k) != 0));
-                            }
+                        for (int k = 0; k < KCH / 8; ++k) {
+                            const uint64_t ad = desc_hi | (uint64_t)(((a_addr + s * 128 + k * 32) & 0x3FFFFu) >> 4);
+                            const uint64_t bd = desc_hi | (uint64_t)(((b_base + s * b_step + k * 32) & 0x3FFFFu) >> 4);
+                            tc_mma_tf32_elect(d_tmem, ad, bd, idesc, (uint32_t)((r | kc | s | k) != 0));
                         }
-                        tc_commit(&empty_bar[stage]);
-                        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                     }
+                    tc_commit_elect(&empty_bar[stage]);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
-                tc_commit(&tfull_bar[acc]);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
+            tc_commit_elect(&tfull_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
     } else if (warp >= 4) {
         // ===== epilogue =====

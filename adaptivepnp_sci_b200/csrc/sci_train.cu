@@ -191,30 +191,41 @@ __global__ void ffdnet_unpack_grad_kernel(const float* __restrict__ dxhat, float
 }
 
 // ---- FastDVDnet boundary --------------------------------------------------------------------------
-__global__ void fastdvd_pack_kernel(const float* __restrict__ frames, float sigma, float* __restrict__ out, int B, int H,
-                                    int W, int Cpad, int round_tf32) {
+// One thread builds the 32-channel row of one pixel (9 coalesced plane reads), the block transposes it through
+// shared memory so that the NHWC write is fully coalesced.
+constexpr int FPACK_PIX = 256;
+__global__ void __launch_bounds__(FPACK_PIX) fastdvd_pack_kernel(const float* __restrict__ frames, float sigma,
+                                                                   float* __restrict__ out, int B, int H, int W, int Cpad,
+                                                                   int round_tf32) {
+    extern __shared__ float srow[];                   // [FPACK_PIX][Cpad + 1]
     const long plane = (long)H * W;
-    const long total = (long)B * plane * Cpad;
-    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int k = (int)(idx % Cpad);
-    const long p = (idx / Cpad) % plane;
-    const int f = (int)(idx / (Cpad * plane));
-    const int kk = (round_tf32 && k >= 16) ? k - 16 : k;      // k+16: remainder copy (see ffdnet_pack_kernel)
-    float v = 0.f;
-    if (kk < 12) {
-        const int slot = kk >> 2, c = kk & 3;
-        if (c == 3) v = sigma;
-        else {
-            const int src = (f + slot - 1 + B) % B;      // circular window (fastdvdnet.py:115)
-            v = frames[((long)src * 3 + c) * plane + p];
+    const int f = blockIdx.y;
+    const long p0 = (long)blockIdx.x * FPACK_PIX;
+    const long p = p0 + threadIdx.x;
+    const int CS = Cpad + 1;
+    float* row = srow + threadIdx.x * CS;
+    for (int k = 0; k < Cpad; ++k) row[k] = 0.f;
+    if (p < plane) {
+#pragma unroll
+        for (int slot = 0; slot < 3; ++slot) {
+            const int src = (f + slot - 1 + B) % B;                              // circular window (fastdvdnet.py:115)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float v = (c == 3) ? sigma : frames[((long)src * 3 + c) * plane + p];
+                if (round_tf32) {        // channel k: tf32(v); channel k+16: remainder (weights duplicated)
+                    const float hi = rna_tf32(v);
+                    row[slot * 4 + c] = hi;
+                    row[16 + slot * 4 + c] = rna_tf32(v - hi);
+                } else {
+                    row[slot * 4 + c] = v;
+                }
+            }
         }
     }
-    if (round_tf32) {
-        const float hi = rna_tf32(v);
-        v = (k >= 16) ? rna_tf32(v - hi) : hi;
-    }
-    out[idx] = v;
+    __syncthreads();
+    const int npx = (int)min((long)FPACK_PIX, plane - p0);
+    float* dst = out + ((long)f * plane + p0) * Cpad;
+    for (int i = threadIdx.x; i < npx * Cpad; i += FPACK_PIX) dst[i] = srow[(i / Cpad) * CS + (i % Cpad)];
 }
 
 __global__ void fastdvd_pack_grad_kernel(const float* __restrict__ din, float* __restrict__ dframes, int B, int H, int W,
@@ -244,7 +255,7 @@ __global__ void fastdvd_output_kernel(const float* __restrict__ frames, const fl
         if (idx >= total) return;
         const long p = idx % plane;
         const int c = (int)((idx / plane) % 3), f = (int)(idx / (3 * plane));
-        out[idx] = frames[idx] - y[((long)f * plane + p) * Cpad + c];            // models.py:196
+        out[idx] = frames[idx] - __ldg(y + ((long)f * plane + p) * Cpad + c);    // models.py:196
     } else {
         // dy[f][p][c] = -dout[f][c][p] for c < 3, 0 for the padded columns   (frames = dout here)
         const long total = (long)B * plane * Cpad;
@@ -408,8 +419,12 @@ extern "C" int sci_ffdnet_unpack_output_grad(const float* dxhat, float* dy, int 
 extern "C" int sci_fastdvd_pack_input(const float* frames, float sigma, float* out, int B, int H, int W, int Cpad,
                                       int round_tf32, void* stream) {
     SCI_REQUIRE(frames && out && B > 0 && H > 0 && W > 0 && Cpad >= (round_tf32 ? 32 : 12), "fastdvd_pack_input");
-    fastdvd_pack_kernel<<<grid1d((long)B * H * W * Cpad), 256, 0, sci_stream(stream)>>>(frames, sigma, out, B, H, W, Cpad,
-                                                                                      round_tf32);
+    SCI_REQUIRE(Cpad <= 48 && B <= 65535, "fastdvd_pack_input: Cpad <= 48");
+    const size_t smem = (size_t)FPACK_PIX * (Cpad + 1) * sizeof(float);
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(fastdvd_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    fastdvd_pack_kernel<<<dim3(grid1d((long)H * W, FPACK_PIX), B), FPACK_PIX, smem, sci_stream(stream)>>>(frames, sigma, out, B,
+                                                                                                      H, W, Cpad, round_tf32);
     SCI_CHECK_LAUNCH("fastdvd_pack_input");
     return SCI_OK;
 }
