@@ -176,61 +176,61 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_slot, 0);
     const int k_steps = 9 * p.k_chunks;
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ===== TMA producer =====
-            int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, n = tile / (p.tiles_w * p.tiles_h);
-                const int iw0 = tw * TILE_W * p.stride - 1, ih0 = th * TILE_H * p.stride - 1;
-                for (int tap = 0; tap < 9; ++tap) {
-                    const int r = tap / 3, s = tap % 3;
-                    for (int kc = 0; kc < p.k_chunks; ++kc) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        // ===== TMA producer (warp-uniform loop, one elected lane issues) =====
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, n = tile / (p.tiles_w * p.tiles_h);
+            const int iw0 = tw * TILE_W * p.stride - 1, ih0 = th * TILE_H * p.stride - 1;
+            for (int tap = 0; tap < 9; ++tap) {
+                const int r = tap / 3, s = tap % 3;
+                for (int kc = 0; kc < p.k_chunks; ++kc) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    if (elect_one()) {
                         mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
                         const uint32_t a_dst = smem_base + (uint32_t)stage * stage_bytes;
                         tma_load_4d(a_dst, &tmA, &full_bar[stage], kc * KCH, iw0 + s, ih0 + r, n);
                         tma_load_3d(a_dst + A_BYTES, &tmB, &full_bar[stage], kc * KCH, 0, tap);
                         if (p.wsplit) tma_load_3d(a_dst + A_BYTES + b_bytes, &tmB, &full_bar[stage], kc * KCH, 0, tap + 9);
-                        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                     }
+                    __syncwarp();
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer =====
-            // instruction descriptor: D=f32, A=B=tf32, K-major both, N = Cout, M = 128
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Cout >> 3) << 17) | ((128u >> 4) << 24);
-            int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        // ===== MMA issuer (warp-uniform loop, election folded into the instruction predicate) =====
+        // instruction descriptor: D=f32, A=B=tf32, K-major both, N = Cout, M = 128
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Cout >> 3) << 17) | ((128u >> 4) << 24);
+        const uint64_t desc_hi = umma_desc(0, 16, 1024);
+        int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
+            for (int ks = 0; ks < k_steps; ++ks) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
-                for (int ks = 0; ks < k_steps; ++ks) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes, b_addr = a_addr + A_BYTES;
+                const uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes, b_addr = a_addr + A_BYTES;
 #pragma unroll
-                    for (int k = 0; k < KCH / 8; ++k) {
-                        tc_mma_tf32(d_tmem, umma_desc(a_addr + k * 32, 16, 1024), umma_desc(b_addr + k * 32, 16, 1024), idesc,
-                                    (uint32_t)((ks | k) != 0));
-                    }
-                    if (p.wsplit) {
-#pragma unroll
-                        for (int k = 0; k < KCH / 8; ++k)
-                            tc_mma_tf32(d_tmem, umma_desc(a_addr + k * 32, 16, 1024), umma_desc(b_addr + b_bytes + k * 32, 16, 1024),
-                                        idesc, 1u);
-                    }
-                    tc_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
-                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                for (int k = 0; k < KCH / 8; ++k) {
+                    tc_mma_tf32_elect(d_tmem, desc_hi | (uint64_t)(((a_addr + k * 32) & 0x3FFFFu) >> 4),
+                                      desc_hi | (uint64_t)(((b_addr + k * 32) & 0x3FFFFu) >> 4), idesc, (uint32_t)((ks | k) != 0));
                 }
-                tc_commit(&tfull_bar[acc]);                // accumulator complete -> epilogue
-                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                if (p.wsplit) {
+#pragma unroll
+                    for (int k = 0; k < KCH / 8; ++k)
+                        tc_mma_tf32_elect(d_tmem, desc_hi | (uint64_t)(((a_addr + k * 32) & 0x3FFFFu) >> 4),
+                                          desc_hi | (uint64_t)(((b_addr + b_bytes + k * 32) & 0x3FFFFu) >> 4), idesc, 1u);
+                }
+                tc_commit_elect(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
+            tc_commit_elect(&tfull_bar[acc]);                // accumulator complete -> epilogue
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
     } else if (warp >= 4) {
         // ===== epilogue: TMEM -> registers -> global =====
@@ -434,7 +434,7 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
     } else if (warp >= 4) {
-        // ===== epilogue =====
+        // ===== epilogue: TMEM -> registers -> (scale/shift, ReLU, skip-add, TF32 round) -> swizzled staging -> TMA store
         const int q = warp & 3;
         const int m = q * 32 + lane;
         const int Cq = p.Cout >> 2;
@@ -444,15 +444,53 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int wt = tile % p.tiles_w, ho = (tile / p.tiles_w) % p.H, n = tile / (p.tiles_w * p.H);
             const int wo = wt * 128 + m;
             const bool valid = wo < p.W;
+            // element offset of this lane's 32-channel segment of chunk c0 in the output / residual tensor
+            auto out_offset = [&](int c0) -> long {
+                if (p.ps) {
+                    const int qq = c0 / Cq, cc = c0 % Cq;
+                    return (((long)n * 2 * p.H + 2 * ho + (qq >> 1)) * 2 * p.W + 2 * wo + (qq & 1)) * Cq + cc;
+                }
+                return (((long)n * p.H + ho) * p.W + wo) * p.Cout + c0;
+            };
+            // the skip tensor of the first chunk is fetched while the MMAs of this tile are still running
+            float4 rr[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.residual && valid) {
+                const float4* rp = reinterpret_cast<const float4*>(p.residual + out_offset(0));
+#pragma unroll
+                for (int j = 0; j < 8; ++j) rr[j] = __ldg(rp + j);
+            }
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (uint32_t)(acc * p.acc_stride) + ((uint32_t)(q * 32) << 16);
             for (int c0 = 0; c0 < p.Cout; c0 += 32) {
                 float v[32];
                 tmem_ld32(t_row + c0, v);
+                float4 rn[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) rn[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.residual && valid && c0 + 32 < p.Cout) {          // prefetch the next chunk's skip values
+                    const float4* rp = reinterpret_cast<const float4*>(p.residual + out_offset(c0 + 32));
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) rn[j] = __ldg(rp + j);
+                }
+                float out[32];
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float radd[4] = {rr[j >> 2].x, rr[j >> 2].y, rr[j >> 2].z, rr[j >> 2].w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float t = v[j + e] * s_scale[c0 + j + e] + s_shift[c0 + j + e];
+                        if (p.relu) t = fmaxf(t, 0.f);
+                        t += radd[e];
+                        out[j + e] = p.round_tf32 ? rna_tf32(t) : t;
+                    }
+                }
                 if (p.tma_store) {
-                    // coalesced path: the warp's 32 pixels x 32 channels go through a 128B-swizzled 4 KB staging tile
-                    // and leave as ONE TMA store (box {32 ch, 32 px}); out-of-image pixels are clipped by TMA
+                    // coalesced path: the warp's 32 pixels x 32 channels go through a 128B-swizzled 4 KB staging tile and
+                    // leave as ONE TMA store (box {32 ch, 32 px}; PixelShuffle = element stride 2 on the pixel axis of a map
+                    // over the up-sampled tensor); out-of-image pixels are clipped by TMA
                     const uint32_t sbuf = stage_out_base + (uint32_t)(q * p.out_bufs + (p.out_bufs == 2 ? (st_cnt & 1) : 0)) * 4096u;
                     if (lane == 0) {
                         if (p.out_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -461,50 +499,27 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     __syncwarp();
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        float out[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            float t = v[j + e] * s_scale[c0 + j + e] + s_shift[c0 + j + e];
-                            if (p.relu) t = fmaxf(t, 0.f);
-                            out[e] = p.round_tf32 ? rna_tf32(t) : t;
-                        }
                         const uint32_t a = sbuf + (uint32_t)lane * 128u + (uint32_t)(((j >> 2) ^ (lane & 7)) << 4);
-                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(out[0]), "f"(out[1]), "f"(out[2]), "f"(out[3]) : "memory");
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(out[j]), "f"(out[j + 1]), "f"(out[j + 2]), "f"(out[j + 3]) : "memory");
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) {
+                        int cx = c0, cw = wt * 128 + q * 32, chh = ho;
+                        if (p.ps) { const int qq = c0 / Cq; cx = c0 % Cq; cw = 2 * cw + (qq & 1); chh = 2 * ho + (qq >> 1); }
                         asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                                     ::"l"(&tmY), "r"(sbuf), "r"(c0), "r"(wt * 128 + q * 32), "r"(ho), "r"(n) : "memory");
+                                     ::"l"(&tmY), "r"(sbuf), "r"(cx), "r"(cw), "r"(chh), "r"(n) : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                     ++st_cnt;
-                    continue;
-                }
-                if (valid) {
-                    long o;
-                    if (p.ps) {
-                        const int qq = c0 / Cq, cc = c0 % Cq;
-                        o = (((long)n * 2 * p.H + 2 * ho + (qq >> 1)) * 2 * p.W + 2 * wo + (qq & 1)) * Cq + cc;
-                    } else {
-                        o = (((long)n * p.H + ho) * p.W + wo) * p.Cout + c0;
-                    }
+                } else if (valid) {
+                    float* yp = p.y + out_offset(c0);
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (p.residual) r4 = *reinterpret_cast<const float4*>(p.residual + o + j);
-                        float out[4];
-                        const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            float t = v[j + e] * s_scale[c0 + j + e] + s_shift[c0 + j + e];
-                            if (p.relu) t = fmaxf(t, 0.f);
-                            t += rr[e];
-                            out[e] = p.round_tf32 ? rna_tf32(t) : t;
-                        }
-                        *reinterpret_cast<float4*>(p.y + o + j) = make_float4(out[0], out[1], out[2], out[3]);
-                    }
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(yp + j) = make_float4(out[j], out[j + 1], out[j + 2], out[j + 3]);
                 }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) rr[j] = rn[j];
             }
             tc_fence_before();
             __syncwarp();
@@ -647,7 +662,7 @@ int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream) {
     p.num_tiles = p.tiles_w * p.H * p.N;
     p.k_chunks = p.Cin / KCH;
     const int b_bytes = p.Cout * KCH * 4;
-    p.tma_store = (!d->pixel_shuffle && !d->residual && env_int("SCI_CONV_TMA_STORE", 1)) ? 1 : 0;
+    p.tma_store = env_int("SCI_CONV_TMA_STORE", 1) ? 1 : 0;
     const int w_bytes = 9 * p.k_chunks * b_bytes;
     // shared-memory plan: [resident weights] [pipeline stages] [store staging: 4 warps x out_bufs x 4 KB]
     const int total_budget = 214 * 1024;
@@ -688,10 +703,14 @@ int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream) {
     CUtensorMap tmY = tmA;
     if (p.tma_store) {
         EncodeTiledFn fn = get_encode_fn();
-        const cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
-        const cuuint64_t strides[3] = {(cuuint64_t)d->Cout * 4, (cuuint64_t)d->W * d->Cout * 4, (cuuint64_t)d->H * d->W * d->Cout * 4};
-        const cuuint32_t box[4] = {KCH, 32, 1, 1};
-        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        // plain layers: [N][H][W][Cout], box {32 ch, 32 px}.  PixelShuffle layers: the map covers the up-sampled tensor
+        // [N][2H][2W][Cout/4]; the 32 pixels of a warp land on every second column (element stride 2).
+        const int ps = d->pixel_shuffle ? 1 : 0;
+        const cuuint64_t oc = (cuuint64_t)(ps ? d->Cout / 4 : d->Cout), ow = (cuuint64_t)(d->W << ps), oh = (cuuint64_t)(d->H << ps);
+        const cuuint64_t dims[4] = {oc, ow, oh, (cuuint64_t)d->N};
+        const cuuint64_t strides[3] = {oc * 4, ow * oc * 4, oh * ow * oc * 4};
+        const cuuint32_t box[4] = {KCH, (cuuint32_t)(32 << ps), 1, 1};
+        const cuuint32_t estr[4] = {1, (cuuint32_t)(1 << ps), 1, 1};
         CUresult r = fn(&tmY, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d->y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return sci_fail(SCI_ELAUNCH, "cuTensorMapEncodeTiled(output) failed");
@@ -765,16 +784,16 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_slot, 0);
 
     if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, n = tile / (p.tiles_w * p.tiles_h);
-                const int ow0 = tw * WG_TILE, oh0 = th * WG_TILE;
-                for (int s = 0; s < 3; ++s) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, n = tile / (p.tiles_w * p.tiles_h);
+            const int ow0 = tw * WG_TILE, oh0 = th * WG_TILE;
+            for (int s = 0; s < 3; ++s) {
+                mbar_wait(&empty_bar[stage], phase ^ 1u);
+                if (elect_one()) {
                     mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
                     const uint32_t base = smem_base + (uint32_t)stage * stage_bytes;
                     for (int c = 0; c < a_chunks; ++c)
@@ -782,36 +801,37 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
                     for (int c = 0; c < p.b_chunks; ++c)
                         tma_load_4d(base + a_region + c * WG_CHUNK_BYTES, &tmX, &full_bar[stage], c * KCH,
                                     ow0 * p.stride + s - 1, oh0 * p.stride + frow - 1, n);
-                    if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
                 }
+                __syncwarp();
+                if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // D=f32, A=B=tf32, both MN-major (bits 15/16), N = Cin, M = 128
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
-                                   ((uint32_t)(p.Cin >> 3) << 17) | ((128u >> 4) << 24);
-            int stage = 0; uint32_t phase = 0; bool first = true;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                for (int s = 0; s < 3; ++s) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes, b_addr = a_addr + a_region;
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(s * p.Cin);
+        // D=f32, A=B=tf32, both MN-major (bits 15/16), N = Cin, M = 128
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                               ((uint32_t)(p.Cin >> 3) << 17) | ((128u >> 4) << 24);
+        // MN-major SWIZZLE_128B_BASE32B (atom = 32 channels x 4 pixels): LBO = stride between 32-channel chunks,
+        // SBO = stride between 4-pixel groups; one K=8 MMA spans two atoms
+        const uint64_t desc_hi = umma_desc(0, WG_CHUNK_BYTES, 512, 1);
+        int stage = 0; uint32_t phase = 0; uint32_t first = 1;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int s = 0; s < 3; ++s) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes, b_addr = a_addr + a_region;
+                const uint32_t d_tmem = tmem_base + (uint32_t)(s * p.Cin);
 #pragma unroll
-                    for (int k8 = 0; k8 < WG_TILE * WG_TILE / 8; ++k8) {
-                        // MN-major SWIZZLE_128B_BASE32B (atom = 32 channels x 4 pixels): LBO = stride between
-                        // 32-channel chunks, SBO = stride between 4-pixel groups; one K=8 MMA spans two atoms
-                        tc_mma_tf32(d_tmem, umma_desc(a_addr + k8 * 1024, WG_CHUNK_BYTES, 512, 1),
-                                    umma_desc(b_addr + k8 * 1024, WG_CHUNK_BYTES, 512, 1), idesc, (uint32_t)(!first || k8 != 0));
-                    }
-                    tc_commit(&empty_bar[stage]);
-                    if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
+                for (int k8 = 0; k8 < WG_TILE * WG_TILE / 8; ++k8) {
+                    tc_mma_tf32_elect(d_tmem, desc_hi | (uint64_t)(((a_addr + k8 * 1024) & 0x3FFFFu) >> 4),
+                                      desc_hi | (uint64_t)(((b_addr + k8 * 1024) & 0x3FFFFu) >> 4), idesc,
+                                      (uint32_t)(!first || k8 != 0));
                 }
-                first = false;
+                tc_commit_elect(&empty_bar[stage]);
+                if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
             }
-            tc_commit(&done_bar);
+            first = 0;
         }
+        tc_commit_elect(&done_bar);
     } else if (warp >= 4) {
         const int q = warp & 3;
         const int co = mt * 128 + q * 32 + lane;
