@@ -253,8 +253,12 @@ def main():
     conv_s = sum(p[0].elapsed_time(p[1]) for p in prof) * 1e-3
     achieved = flops / conv_s / 1e12
     peak_bf16 = pk["bf16_tflops_sustained"]
-    roofline = {"bound": "tensor", "kernel": "conv_fwd_tc_kernel (tcgen05.mma kind::tf32)", "achieved": achieved,
-                "peak": peak_bf16, "unit": "TFLOP/s", "frac": achieved / peak_bf16, "traffic": None,
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "conv_traffic_r1.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath))["dram_bytes_per_launch"]          # ncu --set full capture, per launch
+    roofline = {"bound": "tensor", "kernel": "conv_fwd2_tc_kernel / conv_fwd_tc_kernel (tcgen05.mma kind::tf32)", "achieved": achieved,
+                "peak": peak_bf16, "unit": "TFLOP/s", "frac": achieved / peak_bf16, "traffic": traffic,
                 "peak_kind": pk_kind + " cuBLAS bf16 (sustained); TF32 operands run at half the bf16 rate",
                 "frac_of_tf32_rate": achieved / (peak_bf16 / 2),
                 "flops_per_pass": flops, "launches_per_pass": len(prof), "avg_launch_ms": 1e3 * conv_s / len(prof)}
