@@ -27,7 +27,8 @@ constexpr int TV_HALO = 8;                 // 4 half-res pixels
 constexpr int TV_RW = TV_TW + 2 * TV_HALO; // 80
 constexpr int TV_RH = TV_TH + 2 * TV_HALO; // 48
 constexpr int TV_NPIX = TV_RW * TV_RH;     // 3840
-constexpr int TV_THREADS = 256;
+constexpr int TV_ROWGROUPS = 4;            // 80 columns x 4 row groups
+constexpr int TV_THREADS = TV_RW * TV_ROWGROUPS;   // 320
 constexpr int TV_MAX_UPD = 4;              // out_1..out_4 are the candidate results
 
 // workspace: double epart[B][4 iters][2 kinds][4 phases][nblk], then int nstop[B*4]
@@ -44,7 +45,7 @@ __global__ void __launch_bounds__(TV_THREADS) tv_chambolle_kernel(
     float* so = sf + TV_NPIX;         // current iterate out_i
     float* sp0 = so + TV_NPIX;        // dual variable, row direction
     float* sp1 = sp0 + TV_NPIX;       // dual variable, column direction
-    __shared__ double sred[TV_THREADS / 32][16][2];
+    __shared__ double sred[TV_THREADS / 32][16][2];   // 10 warps
     __shared__ int s_stop[4];
 
     const int t = blockIdx.z;
@@ -59,51 +60,62 @@ __global__ void __launch_bounds__(TV_THREADS) tv_chambolle_kernel(
     const float* bp = b ? b + t * plane : nullptr;
     const int gr0 = blockIdx.y * TV_TH - TV_HALO, gc0 = blockIdx.x * TV_TW - TV_HALO;
 
-    for (int i = threadIdx.x; i < TV_NPIX; i += TV_THREADS) {
-        const int rr = i / TV_RW, cc = i % TV_RW, gr = gr0 + rr, gc = gc0 + cc;
-        float v = 0.f;
-        if (gr >= 0 && gr < H && gc >= 0 && gc < W) {
-            v = xp[(long)gr * W + gc];
-            if (bp) v = v + c_b * bp[(long)gr * W + gc];
+    // thread -> fixed column cx of the 80-wide region, rows ry, ry+4, ... (no per-pixel
+    // div/mod, column predicates hoisted out of the row loops)
+    const int cx = threadIdx.x % TV_RW, ry = threadIdx.x / TV_RW;
+    const bool t_active = true;
+    const int gc = gc0 + cx;
+    const bool col_in = gc >= 0 && gc < W;
+    const bool col_interior = cx >= TV_HALO && cx < TV_HALO + TV_TW && gc < W;
+    const bool col_has_left = gc >= 2 && cx >= 2;            // neighbour (c-2) exists in the image and in the tile
+    const bool col_has_right = gc + 2 < W && cx + 2 < TV_RW;
+
+    if (t_active) {
+        for (int rr = ry; rr < TV_RH; rr += TV_ROWGROUPS) {
+            const int gr = gr0 + rr, i = rr * TV_RW + cx;
+            float v = 0.f;
+            if (col_in && gr >= 0 && gr < H) {
+                v = xp[(long)gr * W + gc];
+                if (bp) v = v + c_b * bp[(long)gr * W + gc];
+            }
+            sf[i] = v; so[i] = v; sp0[i] = 0.f; sp1[i] = 0.f;
         }
-        sf[i] = v; so[i] = v; sp0[i] = 0.f; sp1[i] = 0.f;
     }
     __syncthreads();
 
-    // energy accumulators: [iteration 0..3][row parity] for (sum d^2, sum |g|); column parity is
-    // fixed per thread because TV_RW and TV_THREADS are even.
+    // energy accumulators: [iteration 0..3][row parity] for (sum d^2, sum |g|); the column parity is fixed per thread
     double e_d[TV_MAX_UPD][2], e_n[TV_MAX_UPD][2];
 #pragma unroll
     for (int k = 0; k < TV_MAX_UPD; ++k) { e_d[k][0] = e_d[k][1] = e_n[k][0] = e_n[k][1] = 0.0; }
-    const int cpar = (gc0 + (threadIdx.x % TV_RW)) & 1;   // TV_HALO even -> same parity as local column
+    const int cpar = gc & 1;
 
 #pragma unroll
     for (int it = 0; it <= TV_MAX_UPD; ++it) {
         if (it > last_iter) break;
-        // ---- phase A: d = -div p, out = f + d (it > 0); capture/write the result of channels stopping here
+        // ---- phase A: d = -div p, out = f + d (it > 0); write the result of the channels stopping here
         if (it > 0) {
-            for (int i = threadIdx.x; i < TV_NPIX; i += TV_THREADS) {
-                const int rr = i / TV_RW, cc = i % TV_RW, gr = gr0 + rr, gc = gc0 + cc;
-                float d = -(sp0[i] + sp1[i]);
-                if (gr >= 2 && rr >= 2) d += sp0[i - 2 * TV_RW];
-                if (gc >= 2 && cc >= 2) d += sp1[i - 2];
-                const float o = sf[i] + d;
-                so[i] = o;
-                const bool interior = rr >= TV_HALO && rr < TV_HALO + TV_TH && cc >= TV_HALO && cc < TV_HALO + TV_TW &&
-                                      gr < H && gc < W;
-                if (interior) {
-                    const int rpar = gr & 1;
-                    if (it < TV_MAX_UPD && !is_fix) {
-                        const double dd = (double)(d * d);
-                        if (rpar) e_d[it][1] += dd; else e_d[it][0] += dd;
-                    }
-                    const int stop = s_stop[rpar * 2 + cpar];
-                    if (it == stop && (!is_fix || stop < last_iter)) {
-                        const long g = (long)gr * W + gc;
-                        float th = o;
-                        if (clip) th = fminf(fmaxf(th, 0.f), 1.f);
-                        theta[t * plane + g] = th;
-                        if (bp) b_out[t * plane + g] = bp[g] + s_b * (xp[g] - th);
+            if (t_active) {
+                for (int rr = ry; rr < TV_RH; rr += TV_ROWGROUPS) {
+                    const int gr = gr0 + rr, i = rr * TV_RW + cx;
+                    float d = -(sp0[i] + sp1[i]);
+                    if (gr >= 2 && rr >= 2) d += sp0[i - 2 * TV_RW];
+                    if (col_has_left) d += sp1[i - 2];
+                    const float o = sf[i] + d;
+                    so[i] = o;
+                    if (col_interior && rr >= TV_HALO && rr < TV_HALO + TV_TH && gr < H) {
+                        const int rpar = gr & 1;
+                        if (it < TV_MAX_UPD && !is_fix) {
+                            const double dd = (double)(d * d);
+                            if (rpar) e_d[it][1] += dd; else e_d[it][0] += dd;
+                        }
+                        const int stop = s_stop[rpar * 2 + cpar];
+                        if (it == stop && (!is_fix || stop < last_iter)) {
+                            const long g = (long)gr * W + gc;
+                            float th = o;
+                            if (clip) th = fminf(fmaxf(th, 0.f), 1.f);
+                            theta[t * plane + g] = th;
+                            if (bp) b_out[t * plane + g] = bp[g] + s_b * (xp[g] - th);
+                        }
                     }
                 }
             }
@@ -111,23 +123,22 @@ __global__ void __launch_bounds__(TV_THREADS) tv_chambolle_kernel(
         }
         if (it == TV_MAX_UPD || it == last_iter) break;   // the last dual update never shapes the result
         // ---- phase B: forward differences, energy, dual update
-        for (int i = threadIdx.x; i < TV_NPIX; i += TV_THREADS) {
-            const int rr = i / TV_RW, cc = i % TV_RW, gr = gr0 + rr, gc = gc0 + cc;
-            const bool in_img = gr >= 0 && gr < H && gc >= 0 && gc < W;
-            const float o = so[i];
-            float g0 = 0.f, g1 = 0.f;
-            if (in_img && gr + 2 < H && rr + 2 < TV_RH) g0 = so[i + 2 * TV_RW] - o;
-            if (in_img && gc + 2 < W && cc + 2 < TV_RW) g1 = so[i + 2] - o;
-            const float nrm = sqrtf(g0 * g0 + g1 * g1);
-            const bool interior = rr >= TV_HALO && rr < TV_HALO + TV_TH && cc >= TV_HALO && cc < TV_HALO + TV_TW &&
-                                  gr < H && gc < W;
-            if (interior && !is_fix) {
-                if (gr & 1) e_n[it][1] += (double)nrm; else e_n[it][0] += (double)nrm;
+        if (t_active) {
+            for (int rr = ry; rr < TV_RH; rr += TV_ROWGROUPS) {
+                const int gr = gr0 + rr, i = rr * TV_RW + cx;
+                const bool in_img = col_in && gr >= 0 && gr < H;
+                const float o = so[i];
+                float g0 = 0.f, g1 = 0.f;
+                if (in_img && gr + 2 < H && rr + 2 < TV_RH) g0 = so[i + 2 * TV_RW] - o;
+                if (in_img && col_has_right) g1 = so[i + 2] - o;
+                const float nrm = sqrtf(g0 * g0 + g1 * g1);
+                if (col_interior && rr >= TV_HALO && rr < TV_HALO + TV_TH && gr < H && !is_fix) {
+                    if (gr & 1) e_n[it][1] += (double)nrm; else e_n[it][0] += (double)nrm;
+                }
+                const float inv = 1.0f / (nrm * tw + 1.0f);          // one IEEE division shared by both components
+                sp0[i] = in_img ? (sp0[i] - tau * g0) * inv : 0.f;
+                sp1[i] = in_img ? (sp1[i] - tau * g1) * inv : 0.f;
             }
-            const float den = nrm * tw + 1.0f;
-            const float p0 = in_img ? (sp0[i] - tau * g0) / den : 0.f;
-            const float p1 = in_img ? (sp1[i] - tau * g1) / den : 0.f;
-            sp0[i] = p0; sp1[i] = p1;
         }
         __syncthreads();
     }
@@ -157,7 +168,7 @@ __global__ void __launch_bounds__(TV_THREADS) tv_chambolle_kernel(
         const int lp = threadIdx.x & 1, kind = (threadIdx.x >> 1) & 1, rp = (threadIdx.x >> 2) & 1, k = threadIdx.x >> 3;
         double s = 0.0;
         for (int w8 = 0; w8 < TV_THREADS / 32; ++w8) s += sred[w8][(k * 2 + rp) * 2 + kind][lp];
-        // lane parity lp corresponds to column parity (threadIdx.x % TV_RW parity == threadIdx.x parity)
+        // lane parity lp == column parity: cx = threadIdx.x % 80 keeps the parity of threadIdx.x, gc0 is even
         const int cp = (gc0 + lp) & 1;
         const int phase = rp * 2 + cp;
         epart[((((size_t)t * 4 + k) * 2 + kind) * 4 + phase) * nblk + blk] = s;
