@@ -899,6 +899,209 @@ int conv_wgrad_tc_launch(const sci_wgrad_desc* d, void* stream) {
     return SCI_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// weight-gradient kernel, version 2: operand orientation and tap fusion chosen per layer
+//   The version-1 launch list (profiles/) showed the full-resolution 32-channel layers at 0.73-0.89 ms each: with
+//   M = Cout = 32 of 128 rows used, three quarters of every MMA were wasted and each tap reloaded the dz tile.
+//   * swap = 0: M side = dz (Cout), N side = x.  swap = 1: M side = x (Cin), N side = dz (Cout) - chosen when that
+//     fills the 128 MMA rows better.
+//   * fuse = 1: the three horizontal taps of the filter row are ONE operand (their 32-channel chunks are simply
+//     consecutive chunks of the MN-major operand), so one MMA per 8 pixels covers all three taps and the unshifted
+//     operand is loaded once per tile instead of once per tap.
+// ---------------------------------------------------------------------------------------------------
+struct Wgrad2Params {
+    const float* oscale; float* dw;
+    int N, Ho, Wo, Cin, Cout, stride;
+    int tiles_w, tiles_h, num_tiles;
+    int swap, fuse, p_chunks, q_chunks, n_mma, accs, m_tiles, tmem_cols, stages;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_wgrad2_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmX, const Wgrad2Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], done_bar;
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int frow = blockIdx.y / p.m_tiles, mt = blockIdx.y % p.m_tiles;
+    const int cin_chunks = p.Cin / KCH, cout_chunks = p.Cout / KCH;
+    const int p_chunks = p.swap ? p.p_chunks : min(cout_chunks - mt * 4, 4);
+    const uint32_t p_region = 4 * WG_CHUNK_BYTES;
+    const uint32_t stage_bytes = p_region + (uint32_t)p.q_chunks * WG_CHUNK_BYTES;
+    const uint32_t tx_bytes = (uint32_t)(p_chunks + p.q_chunks) * WG_CHUNK_BYTES;
+    const int sub_steps = p.fuse ? 1 : 3;            // pipeline stages per pixel tile
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmZ) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&done_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_slot, 0);
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, n = tile / (p.tiles_w * p.tiles_h);
+            const int ow0 = tw * WG_TILE, oh0 = th * WG_TILE;
+            const int ix0 = ow0 * p.stride - 1, iy = oh0 * p.stride + frow - 1;
+            for (int ss = 0; ss < sub_steps; ++ss) {
+                mbar_wait(&empty_bar[stage], phase ^ 1u);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+                    const uint32_t pb = smem_base + (uint32_t)stage * stage_bytes, qb = pb + p_region;
+                    // dz chunks (unshifted operand)
+                    const uint32_t zb = p.swap ? qb : pb;
+                    const int zc0 = p.swap ? 0 : mt * 4, zn = p.swap ? cout_chunks : p_chunks;
+                    for (int c = 0; c < zn; ++c)
+                        tma_load_4d(zb + c * WG_CHUNK_BYTES, &tmZ, &full_bar[stage], (zc0 + c) * KCH, ow0, oh0, n);
+                    // x chunks (tap-shifted operand): fused -> slots [s][c] for s = 0..2, else slots [c] for s = ss
+                    const uint32_t xb = p.swap ? pb : qb;
+                    for (int s = (p.fuse ? 0 : ss); s < (p.fuse ? 3 : ss + 1); ++s)
+                        for (int c = 0; c < cin_chunks; ++c)
+                            tma_load_4d(xb + (uint32_t)((p.fuse ? s * cin_chunks : 0) + c) * WG_CHUNK_BYTES, &tmX, &full_bar[stage],
+                                        c * KCH, ix0 + s, iy, n);
+                }
+                __syncwarp();
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: D=f32, A=B=tf32, both MN-major, N = n_mma, M = 128 =====
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                               ((uint32_t)(p.n_mma >> 3) << 17) | ((128u >> 4) << 24);
+        const uint64_t desc_hi = umma_desc(0, WG_CHUNK_BYTES, 512, 1);
+        int stage = 0; uint32_t phase = 0; uint32_t first = 1;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int ss = 0; ss < sub_steps; ++ss) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t pb = smem_base + (uint32_t)stage * stage_bytes, qb = pb + p_region;
+                const uint32_t d_tmem = tmem_base + (uint32_t)(ss * p.n_mma);
+#pragma unroll
+                for (int k8 = 0; k8 < WG_TILE * WG_TILE / 8; ++k8) {
+                    tc_mma_tf32_elect(d_tmem, desc_hi | (uint64_t)(((pb + k8 * 1024) & 0x3FFFFu) >> 4),
+                                      desc_hi | (uint64_t)(((qb + k8 * 1024) & 0x3FFFFu) >> 4), idesc,
+                                      (uint32_t)(!first || k8 != 0));
+                }
+                tc_commit_elect(&empty_bar[stage]);
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+            first = 0;
+        }
+        tc_commit_elect(&done_bar);
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> registers -> red.global.add into the packed gradient =====
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        mbar_wait(&done_bar, 0);
+        tc_fence_after();
+        for (int a = 0; a < p.accs; ++a) {
+            const uint32_t t_row = tmem_base + (uint32_t)(a * p.n_mma) + ((uint32_t)(q * 32) << 16);
+            for (int c0 = 0; c0 < p.n_mma; c0 += 32) {
+                float v[32];
+                tmem_ld32(t_row + c0, v);
+                if (!p.swap) {
+                    // row = output channel, columns = (tap s, input channel): 32 consecutive ci of one tap
+                    const int co = mt * 128 + m;
+                    const int s = p.fuse ? c0 / p.Cin : a, ci0 = p.fuse ? c0 % p.Cin : c0;
+                    if (co < p.Cout) {
+                        const float sc = p.oscale ? p.oscale[co] : 1.f;
+                        float* dst = p.dw + ((long)(frow * 3 + s) * p.Cout + co) * p.Cin + ci0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v[j] * sc),
+                                         "f"(v[j + 1] * sc), "f"(v[j + 2] * sc), "f"(v[j + 3] * sc) : "memory");
+                    }
+                } else {
+                    // row = (tap s, input channel), columns = output channels: lanes are consecutive ci -> coalesced reds
+                    const int s = p.fuse ? m / p.Cin : a, ci = p.fuse ? m % p.Cin : m;
+                    if (ci < p.Cin && s < 3 && m < (p.fuse ? 3 * p.Cin : p.Cin)) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int co = c0 + j;
+                            const float sc = p.oscale ? __ldg(p.oscale + co) : 1.f;
+                            atomicAdd(p.dw + ((long)(frow * 3 + s) * p.Cout + co) * p.Cin + ci, v[j] * sc);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
+}
+
+int conv_wgrad2_tc_launch(const sci_wgrad_desc* d, void* stream) {
+    Wgrad2Params p;
+    p.oscale = d->oscale; p.dw = d->dw;
+    p.N = d->N; p.stride = d->stride; p.Cin = d->Cin; p.Cout = d->Cout;
+    p.Ho = (d->H - 1) / d->stride + 1; p.Wo = (d->W - 1) / d->stride + 1;
+    p.tiles_w = (p.Wo + WG_TILE - 1) / WG_TILE; p.tiles_h = (p.Ho + WG_TILE - 1) / WG_TILE;
+    p.num_tiles = p.tiles_w * p.tiles_h * p.N;
+    const int cin_chunks = p.Cin / KCH, cout_chunks = p.Cout / KCH;
+    // orientation: put the wider channel dimension on the (128-row padded) M side
+    p.swap = (p.Cout < p.Cin || (p.Cin == 32 && p.Cout == 32)) ? 1 : 0;
+    if (p.swap) {
+        p.fuse = (3 * p.Cin <= 128) ? 1 : 0;                   // taps stacked along M
+        p.p_chunks = p.fuse ? 3 * cin_chunks : cin_chunks;
+        p.q_chunks = cout_chunks;
+        p.n_mma = p.Cout;
+        p.accs = p.fuse ? 1 : 3;
+        p.m_tiles = 1;
+    } else {
+        p.fuse = (3 * p.Cin <= 256) ? 1 : 0;                   // taps side by side along N
+        p.p_chunks = 0;                                        // per-CTA (depends on the M tile)
+        p.q_chunks = p.fuse ? 3 * cin_chunks : cin_chunks;
+        p.n_mma = p.fuse ? 3 * p.Cin : p.Cin;
+        p.accs = p.fuse ? 1 : 3;
+        p.m_tiles = (p.Cout + 127) / 128;
+    }
+    if (p.swap && (p.Cin > 128 || p.Cout > 256)) return sci_fail(SCI_EUNSUPPORTED, "wgrad tc v2: shape");
+    p.tmem_cols = next_pow2_cols(p.accs * p.n_mma);
+    if (p.tmem_cols > 512) return sci_fail(SCI_EUNSUPPORTED, "wgrad tc v2: accumulators exceed TMEM");
+    const size_t stage_bytes = (size_t)4 * WG_CHUNK_BYTES + (size_t)p.q_chunks * WG_CHUNK_BYTES;
+    p.stages = (int)min((size_t)4, (size_t)(214 * 1024) / stage_bytes);
+    if (p.stages < 2) return sci_fail(SCI_EUNSUPPORTED, "wgrad tc v2: pipeline does not fit");
+    CUtensorMap tmZ, tmX;
+    int rc = make_act_map(&tmZ, d->dz, d->N, p.Ho, p.Wo, d->Cout, 1, WG_TILE, WG_TILE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+    rc = make_act_map(&tmX, d->x, d->N, d->H, d->W, d->Cin, d->stride, WG_TILE, WG_TILE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+    const size_t smem = p.stages * stage_bytes + 1024;
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(conv_wgrad2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        if (e != cudaSuccess) return sci_fail(SCI_ELAUNCH, "wgrad tc v2: smem attribute", e);
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    const int groups = 3 * p.m_tiles;
+    const int gx = max(1, min(p.num_tiles, SCI_NUM_SMS / groups));
+    conv_wgrad2_tc_kernel<<<dim3(gx, groups), TC_THREADS, smem, sci_stream(stream)>>>(tmZ, tmX, p);
+    SCI_CHECK_LAUNCH("conv tc wgrad v2");
+    return SCI_OK;
+}
+
 int check_conv_desc(const sci_conv_desc* d) {
     SCI_REQUIRE(d && d->x && d->w && d->y, "conv: null pointer");
     SCI_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "conv: shape");
@@ -933,6 +1136,10 @@ extern "C" int sci_conv3x3_wgrad(const sci_wgrad_desc* d, int impl, void* stream
                 "wgrad: shape");
     SCI_REQUIRE(d->Cin % 4 == 0 && d->Cout % 4 == 0, "wgrad: channels % 4");
     if (impl == SCI_CONV_REF) return sci_wgrad_ref_launch(d, stream);
-    if (impl == SCI_CONV_TC) return conv_wgrad_tc_launch(d, stream);
+    if (impl == SCI_CONV_TC) {
+        if (d->Cin % 32 != 0 || d->Cout % 32 != 0 || d->Cin > 128 || d->Cout > 256)
+            return sci_fail(SCI_EUNSUPPORTED, "wgrad tc: needs Cin % 32 == 0 (<= 128), Cout % 32 == 0 (<= 256)");
+        return env_int("SCI_WGRAD_V2", 1) ? conv_wgrad2_tc_launch(d, stream) : conv_wgrad_tc_launch(d, stream);
+    }
     return sci_fail(SCI_EINVAL, "wgrad: unknown impl");
 }
