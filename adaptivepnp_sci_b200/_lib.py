@@ -67,7 +67,8 @@ PROTOTYPES = {
     "sci_fastdvd_pack_input_grad": [_p, _p, _i, _i, _i, _i, _i, _p],
     "sci_fastdvd_noisy_input": [_p, _p, _p, _l, _p],
     "sci_host_legacy_normal": [_p, _p, _p, _p, _d, _d, _p, _l, _i],
-    "sci_meas_loss_fwd_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "sci_meas_loss_fwd_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _l, _p],
+    "sci_axpy": [_p, _f, _p, _p, _l, _p],
     "sci_adam_step": [_p, _p, _p, _p, _l, _d, _d, _d, _d, _i, _p],
 }
 _SPECIAL_RESTYPE = {"sci_last_error": ctypes.c_char_p, "sci_tv_workspace_bytes": _sz}

@@ -279,7 +279,8 @@ __global__ void noisy_input_kernel(const float* __restrict__ v, const double* __
 // ---- measurement loss -------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) meas_loss_kernel(const float* __restrict__ xhat, const float* __restrict__ phi,
                                                          const float* __restrict__ y, float* __restrict__ dxhat,
-                                                         double* __restrict__ loss, int H, int W, int B, float norm) {
+                                                         double* __restrict__ loss, int H, int W, int B, float norm,
+                                                         double inv_count) {
     __shared__ double red[32];
     const long plane = (long)H * W;
     const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(256) meas_loss_kernel(const float* __restrict_
         }
     }
     const double s = block_sum(err, red);
-    if (threadIdx.x == 0) atomicAdd(loss, s / (double)plane);
+    if (threadIdx.x == 0) atomicAdd(loss, s * inv_count);
 }
 
 __global__ void adam_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
@@ -461,11 +462,25 @@ extern "C" int sci_fastdvd_noisy_input(const float* v, const double* noise, floa
 }
 
 extern "C" int sci_meas_loss_fwd_bwd(const float* xhat, const float* phi, const float* y, float* dxhat, double* loss, int H,
-                                     int W, int B, void* stream) {
-    SCI_REQUIRE(xhat && phi && y && loss && H > 0 && W > 0 && B > 0, "meas_loss");
+                                     int W, int B, long norm_pixels, void* stream) {
+    SCI_REQUIRE(xhat && phi && y && loss && H > 0 && W > 0 && B > 0 && norm_pixels >= 0, "meas_loss");
+    // mean over `norm_pixels` (0 = this tensor's H*W; a row strip of a larger frame passes the frame's pixel count)
+    const double cnt = norm_pixels > 0 ? (double)norm_pixels : (double)H * (double)W;
     meas_loss_kernel<<<grid1d((long)H * W), 256, 0, sci_stream(stream)>>>(xhat, phi, y, dxhat, loss, H, W, B,
-                                                                          (float)(2.0 / ((double)H * (double)W)));
+                                                                          (float)(2.0 / cnt), 1.0 / cnt);
     SCI_CHECK_LAUNCH("meas_loss");
+    return SCI_OK;
+}
+
+__global__ void axpy_kernel(const float* __restrict__ x, float a, const float* __restrict__ y, float* __restrict__ out, long n) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = x[i] + a * y[i];
+}
+
+extern "C" int sci_axpy(const float* x, float a, const float* y, float* out, long n, void* stream) {
+    SCI_REQUIRE(x && y && out && n > 0, "axpy");
+    axpy_kernel<<<(int)((n + 255) / 256), 256, 0, sci_stream(stream)>>>(x, a, y, out, n);
+    SCI_CHECK_LAUNCH("axpy");
     return SCI_OK;
 }
 

@@ -144,6 +144,56 @@ def admm_denoise_bayer_demosaic_pre(y_bayer, Phi_bayer, _lambda=1, gamma=0.01,
     return x_bayer_np, psnr_, ssim_, psnr_all
 
 
+class _TileView:
+    """What an adapter needs to know about a halo-extended strip: where the own rows sit and how to normalise the loss."""
+
+    def __init__(self, tile, top, ext_rows):
+        self.top, self.rows = top, tile.rows
+        self.total_pixels, self.H_total = tile.total_pixels, tile.H_total
+        self.g0 = tile.r0 - top                      # global row of the first row of the extended strip
+
+
+def _tiled_demosaic_denoise(tile, adapter, halo, x, b, inv_rou, w, tau, x_rgb, u, pb, nsig, model, lr_, do_update,
+                            update_per_iter, grad_sync):
+    """One demosaic + denoise step of a row strip: 2-row mosaic halo for Malvar, `halo` rows of the denoiser
+    input, overlap-tile denoising, crop.  x_rgb and u (own rows) are filled in place; returns xhat (own rows)."""
+    B, rows, W = x.shape
+    m_ext, top2 = tile.exchange(ops.axpy(x, inv_rou, b).view(B, 1, rows, W), 2)        # merged mosaic x + b/rho
+    rgb_ext = torch.empty((B, 3, m_ext.shape[2], W), dtype=torch.float32, device=x.device)
+    ops.malvar2004(m_ext.view(B, m_ext.shape[2], W), None, 0.0, None, 0.0, rgb_ext, None)
+    x_rgb.copy_(rgb_ext[:, :, top2:top2 + rows])
+    ops.axpy(x_rgb, -float(np.float32(1 / tau)), w, out=u)                              # u = x_rgb - w/tau (:198)
+    u_ext, top = tile.exchange(u, halo)
+    view = _TileView(tile, top, u_ext.shape[2])
+    xhat_ext = adapter.denoise_planar(u_ext, pb, nsig, model, lr_, do_update, update_per_iter, grad_sync=grad_sync, tile=view)
+    return xhat_ext[:, :, top:top + rows].contiguous()
+
+
+def _tiled_outputs(tile, pb, xhat, theta, sse, X_orig, denoiser, sched, noise_estimate, logf, model_denoise, model_demosaic):
+    """Gather the strips into full-frame results on every rank; PSNR from all-reduced squared errors."""
+    B = pb.B
+    Ht, W = tile.H_total, tile.W
+    psnr_all = []
+    if sse is not None:
+        tile.all_reduce_sum(sse)
+        psnr_all = list(iqa.psnr_from_sse(sse.cpu().numpy()[:len(sched)], Ht * W * B))
+        if tile.rank == 0:
+            _log_iterations(denoiser, sched, psnr_all, noise_estimate, logf)
+    theta_full = tile.gather_rows(theta)                                    # [B, Ht, W]
+    xhat_full = tile.gather_rows(xhat)                                      # [B, 3, Ht, W]
+    x_bayer_np = cuda2np(ops.planar_to_pixlast(theta_full.contiguous(), 1, B).view(Ht, W, B))
+    xbgr3_np = cuda2np(ops.planar_to_pixlast(xhat_full.contiguous(), 3, B).view(Ht, W, 3, B))
+    psnr_, ssim_ = [], []
+    if X_orig is not None:
+        fsse = torch.zeros(B, dtype=torch.float64, device=theta.device)
+        ops.psnr_accum(theta, pb.orig, fsse)
+        tile.all_reduce_sum(fsse)
+        psnr_ = list(iqa.psnr_from_sse(fsse.cpu().numpy(), Ht * W))
+        orig_full = cuda2np(ops.planar_to_pixlast(tile.gather_rows(pb.orig).contiguous(), 1, B).view(Ht, W, B))
+        ssim_ = [iqa.ssim(orig_full[:, :, t], x_bayer_np[:, :, t], data_range=1.) for t in range(B)]
+    return xbgr3_np, x_bayer_np, psnr_, ssim_, psnr_all, model_denoise, model_demosaic
+
+
 def twoStageAdmm_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, gamma=0.01,
                                denoiser='tv', iter_max=50, noise_estimate=True, sigma=None,
                                x0_bayer=None,
@@ -151,7 +201,7 @@ def twoStageAdmm_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, gamma=0.01,
                                demosaic_method='malvar2004', lr_=0.000001,
                                inital_iter=1, interval_iter=5, logf=None, useGPU=True, update_=False, update_per_iter=1,
                                close_form_demosaic=False,
-                               large=False, update_times=-1, args=None, grad_sync=None, return_device=False):
+                               large=False, update_times=-1, args=None, grad_sync=None, return_device=False, tile=None):
     """Stage 2: ADMM with a plug-in denoiser ('tv', 'ffdnet_color', 'fastdvd_color') and optional
     online fine-tuning of the denoiser on the measurement-consistency loss.
 
@@ -161,6 +211,10 @@ def twoStageAdmm_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, gamma=0.01,
     flat gradient bucket before each Adam step; the multi-GPU driver passes an NCCL all-reduce.
     ``return_device`` (extension) returns the planar device tensors ``(xhat[B,3,H,W], theta[B,H,W])`` instead of
     numpy arrays (no D2H copy, no host sync) — used by bench.py for the HBM-resident measurement.
+    ``tile`` (extension, ``parallel.TileContext``): spatial row-strip tiling of one large frame over the ranks (BASELINE
+    config 5).  Every rank passes ITS rows of y / Phi / x0 / X_orig; the mosaic (2 rows) and the denoiser input (80 rows
+    for FastDVDnet, 28 for FFDNet) are halo-exchanged with the neighbouring ranks once per iteration, PSNR sums and the
+    fine-tune gradients are all-reduced, and the returned arrays are the full frame (gathered on every rank).
     """
     name = denoiser if denoiser == 'tv' else str(denoiser).lower()
     if name not in ('tv', 'ffdnet_color', 'fastdvd_color'):
@@ -172,6 +226,14 @@ def twoStageAdmm_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, gamma=0.01,
     pb = _Problem(y_bayer, Phi_bayer, x0_bayer, X_orig)
     dev = pb.y.device
     H, W, B = pb.H, pb.W, pb.B
+    if tile is not None:
+        if name == 'tv':
+            raise NotImplementedError("tiled mode covers the deep denoisers (the TV prior would need a halo exchange per "
+                                      "inner iteration; stage 1 shards over measurement groups instead)")
+        if H != tile.rows or W != tile.W:
+            raise ValueError("tiled mode: pass this rank's rows (%d x %d), got %d x %d" % (tile.rows, tile.W, H, W))
+        if grad_sync is None:
+            grad_sync = tile.all_reduce_sum          # loss is normalised by the whole frame -> gradients ADD over strips
     alpha = 0.01 if name == 'tv' else 1                                  # :101-104
     rou = 0.55 if name == 'fastdvd_color' else 1                         # :106-109
     tau = 100                                                            # :110
@@ -212,16 +274,18 @@ def twoStageAdmm_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, gamma=0.01,
                     ops.psnr_accum(theta.view(1, -1), pb.orig.view(1, -1), sse[k:k + 1])
             else:
                 # x_rgb = Malvar(merge(x + b/rho)) for all frames ; u = x_rgb - w/tau                 (:169-198)
-                ops.malvar2004(x, b, inv_rou, w, 1 / tau, x_rgb, u)
                 do_update = bool(update_ and k > inital_iter and k % interval_iter == 0)
-                if name == 'ffdnet_color':
-                    xhat = ffdnet_adapter.denoise_planar(u, pb, nsig, model_denoise, lr_, do_update, update_per_iter,
-                                                         grad_sync=grad_sync)
-                else:
+                if name == 'fastdvd_color':
                     do_update = do_update and (update_i < update_times or update_times < 0)   # :247
-                    xhat = fastdvdnet_adapter.denoise_planar(u, pb, nsig, model_denoise, lr_, do_update,
-                                                             update_per_iter, grad_sync=grad_sync)
                     update_i += int(do_update)
+                adapter = ffdnet_adapter if name == 'ffdnet_color' else fastdvdnet_adapter
+                if tile is None:
+                    ops.malvar2004(x, b, inv_rou, w, 1 / tau, x_rgb, u)
+                    xhat = adapter.denoise_planar(u, pb, nsig, model_denoise, lr_, do_update, update_per_iter,
+                                                  grad_sync=grad_sync)
+                else:
+                    xhat = _tiled_demosaic_denoise(tile, adapter, 28 if name == 'ffdnet_color' else 80, x, b, inv_rou, w, tau,
+                                                   x_rgb, u, pb, nsig, model_denoise, lr_, do_update, update_per_iter, grad_sync)
                 # theta = clip(RGGB samples of xhat) ; b += x - theta ; w += x_rgb - xhat [+ PSNR]    (:206-209, :265-280)
                 ops.dual_update_rgb(xhat, x_rgb, w, x, b, theta, first_iter=(k == 0),
                                     orig=pb.orig if want_iqa else None, sse=sse[k:k + 1] if want_iqa else None)
@@ -229,6 +293,9 @@ def twoStageAdmm_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, gamma=0.01,
             k += 1
     if return_device:
         return xhat, theta
+    if tile is not None:
+        return _tiled_outputs(tile, pb, xhat, theta, sse if want_iqa else None, X_orig, denoiser, sched, noise_estimate,
+                              logf, model_denoise, model_demosaic)
     psnr_all = []
     if want_iqa:
         psnr_all = list(iqa.psnr_from_sse(sse.cpu().numpy()[:n_total], pb.npix * B))

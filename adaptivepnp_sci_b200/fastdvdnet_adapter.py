@@ -171,8 +171,11 @@ class NoiseStream:
 noise_stream = NoiseStream()
 
 
-def finetune_and_denoise(v, phi, y, sigma, model, lr, update_per_iter, grad_sync=None, noise=None):
-    """v [B,3,H,W], phi [B,H,W], y [H,W] planar; returns the denoised CLEAN sequence [B,3,H,W]."""
+def finetune_and_denoise(v, phi, y, sigma, model, lr, update_per_iter, grad_sync=None, noise=None, tile=None):
+    """v [B,3,H,W], phi [B,H,W], y [H,W] planar; returns the denoised CLEAN sequence [B,3,H,W].
+    ``tile`` (parallel.TileView): v is a halo-extended row strip of a larger frame, phi / y cover the own rows; the
+    noise is drawn for the WHOLE frame (same global-RNG stream on every rank) and the strip's rows are cut out."""
+    from .ffdnet_adapter import _tile_loss
     eng = _unwrap(model).engine()
     B, _, H, W = v.shape
     dev = v.device
@@ -181,21 +184,22 @@ def finetune_and_denoise(v, phi, y, sigma, model, lr, update_per_iter, grad_sync
     else:
         n_update_iter, lr_all = list(update_per_iter), list(lr)
     if noise is None:
-        noise = noise_stream.get((B, 3, H, W))
+        if tile is None:
+            noise = noise_stream.get((B, 3, H, W))
+        else:
+            noise = noise_stream.get((B, 3, tile.H_total, W))[:, :, tile.g0:tile.g0 + H]
     noise_d = torch.from_numpy(np.ascontiguousarray(noise, dtype=np.float64)).to(dev, non_blocking=True)
     vplus = eng.ws.get("vplus", (B, 3, H, W), dev)
     call("sci_fastdvd_noisy_input", ptr(v), ptr(noise_d), ptr(vplus), v.numel(), stream())    # :359
     eng.prepare(training=True)
     n_steps = int(sum(n_update_iter))
     loss = torch.zeros(n_steps + 1, dtype=torch.float64, device=dev)
-    dout = eng.ws.get("dout", (B, 3, H, W), dev)
     k = 0
     for lr_i, nit in zip(lr_all, n_update_iter):
         eng.bucket.new_optimizer()                                                        # :385
         for _ in range(nit):
             out = eng.forward(vplus, sigma, train=True)                                   # :412-419
-            call("sci_meas_loss_fwd_bwd", ptr(out), ptr(phi), ptr(y), ptr(dout), ptr(loss[k:k + 1]), H, W, B,
-                 stream())                                                                # :428-431
+            dout = _tile_loss(eng, out, phi, y, "dout", loss[k:k + 1], tile, True)        # :428-431
             eng.backward(dout)                                                            # :445
             if grad_sync is not None:
                 grad_sync(eng.bucket.grad)
@@ -203,17 +207,17 @@ def finetune_and_denoise(v, phi, y, sigma, model, lr, update_per_iter, grad_sync
             eng.after_step()
             k += 1
     out = eng.forward(v, sigma, train=False)                                              # :453-458
-    call("sci_meas_loss_fwd_bwd", ptr(out), ptr(phi), ptr(y), None, ptr(loss[n_steps:]), H, W, B, stream())
+    _tile_loss(eng, out, phi, y, "dout", loss[n_steps:], tile, False)
     last_losses[:] = [loss]
     return out
 
 
-def denoise_planar(u, pb, sigma, model, lr, do_update, update_per_iter, grad_sync=None, noise=None):
+def denoise_planar(u, pb, sigma, model, lr, do_update, update_per_iter, grad_sync=None, noise=None, tile=None):
     """Solver-facing entry: planar in, planar out (engine buffer, consumed before the next call)."""
     if model is None:
         raise SciError("model_denoise is required")
     if do_update:
-        return finetune_and_denoise(u, pb.phi, pb.y, sigma, model, lr, update_per_iter, grad_sync, noise)
+        return finetune_and_denoise(u, pb.phi, pb.y, sigma, model, lr, update_per_iter, grad_sync, noise, tile)
     return _unwrap(model).engine().forward(u, sigma, train=False)
 
 

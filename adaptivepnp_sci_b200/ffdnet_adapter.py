@@ -23,36 +23,58 @@ def _unwrap(model):
     return m
 
 
-def finetune_and_denoise(u, phi, y, sigma, model, lr, update_per_iter, grad_sync=None):
-    """u [B,3,H,W], phi [B,H,W], y [H,W] planar.  update_per_iter Adam steps, then the eval forward."""
+def _tile_loss(eng, out_ext, phi, y, dbuf_name, loss_slot, tile, want_grad):
+    """Measurement loss (+ gradient) of a network output.  Tiled mode: the loss lives on this rank's own rows of the
+    halo-extended strip and is normalised by the pixel count of the whole frame."""
+    B = out_ext.shape[0]
+    dev = out_ext.device
+    if tile is None:
+        H, W = out_ext.shape[2:]
+        d = eng.ws.get(dbuf_name, tuple(out_ext.shape), dev) if want_grad else None
+        call("sci_meas_loss_fwd_bwd", ptr(out_ext), ptr(phi), ptr(y), ptr(d), ptr(loss_slot), H, W, B, 0, stream())
+        return d
+    top, rows, W = tile.top, tile.rows, out_ext.shape[3]
+    own = out_ext[:, :, top:top + rows].contiguous()
+    d_own = eng.ws.get(dbuf_name + "_own", tuple(own.shape), dev) if want_grad else None
+    call("sci_meas_loss_fwd_bwd", ptr(own), ptr(phi), ptr(y), ptr(d_own), ptr(loss_slot), rows, W, B,
+         tile.total_pixels, stream())
+    if not want_grad:
+        return None
+    d = eng.ws.get(dbuf_name, tuple(out_ext.shape), dev)
+    d.zero_()
+    d[:, :, top:top + rows].copy_(d_own)
+    return d
+
+
+def finetune_and_denoise(u, phi, y, sigma, model, lr, update_per_iter, grad_sync=None, tile=None):
+    """u [B,3,H,W], phi [B,H,W], y [H,W] planar.  update_per_iter Adam steps, then the eval forward.
+    ``tile`` (parallel.TileView): u is a halo-extended row strip, phi / y cover this rank's own rows."""
     eng = _unwrap(model).engine()
     B, _, H, W = u.shape
     dev = u.device
     eng.prepare(training=True)
     eng.bucket.new_optimizer()
     loss = torch.zeros(update_per_iter + 1, dtype=torch.float64, device=dev)
-    dxhat = eng.ws.get("dxhat", (B, 3, H, W), dev)
     for it in range(update_per_iter):
         xhat = eng.forward(u, sigma, train=True)                                        # :266-273
-        call("sci_meas_loss_fwd_bwd", ptr(xhat), ptr(phi), ptr(y), ptr(dxhat), ptr(loss[it:it + 1]), H, W, B,
-             stream())                                                                  # :275-291
+        dxhat = _tile_loss(eng, xhat, phi, y, "dxhat", loss[it:it + 1], tile, True)     # :275-291
         eng.backward(dxhat)                                                             # :293
         if grad_sync is not None:
             grad_sync(eng.bucket.grad)
         eng.bucket.adam_step(lr)                                                        # :294
         eng.after_step()
     out = eng.forward(u, sigma, train=False)                                            # :303-315 (model.eval())
-    call("sci_meas_loss_fwd_bwd", ptr(out), ptr(phi), ptr(y), None, ptr(loss[update_per_iter:]), H, W, B, stream())
+    _tile_loss(eng, out, phi, y, "dxhat", loss[update_per_iter:], tile, False)
     last_losses[:] = [loss]          # device tensor; read lazily by whoever wants to print it
     return out
 
 
-def denoise_planar(u, pb, sigma, model, lr, do_update, update_per_iter, grad_sync=None):
+def denoise_planar(u, pb, sigma, model, lr, do_update, update_per_iter, grad_sync=None, tile=None):
     """Solver-facing entry: planar in, planar out (a view of an engine buffer, consumed before the next call)."""
     if model is None:
         raise SciError("model_denoise is required")
     if do_update:
-        return finetune_and_denoise(u, pb.phi, pb.y, sigma, model, lr, update_per_iter, grad_sync)
+        return finetune_and_denoise(u, pb.phi, pb.y, sigma, model, lr, update_per_iter, grad_sync, tile)
     return _unwrap(model).engine().forward(u, sigma, train=False)
 
 

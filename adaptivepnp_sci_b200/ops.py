@@ -121,3 +121,12 @@ def psnr_accum(a, orig, sse_per_frame):
     B = a.shape[0]
     npix = a.numel() // B
     call("sci_psnr_accum", ptr(a), ptr(orig), npix, B, ptr(sse_per_frame), stream())
+
+
+def axpy(x, a, y, out=None):
+    """out = x + a*y (elementwise, fp32)."""
+    require_cuda_f32(x, y, out)
+    if out is None:
+        out = torch.empty_like(x)
+    call("sci_axpy", ptr(x), float(a), ptr(y), ptr(out), x.numel(), stream())
+    return out

@@ -66,6 +66,92 @@ class Context:
                 dist.destroy_process_group()
 
 
+class TileContext:
+    """Row-strip spatial tiling of ONE large frame over the ranks (BASELINE config 5).
+
+    Rank r owns the contiguous rows [r*rows, (r+1)*rows) of every plane (rows % 4 == 0 keeps the Bayer phase, the
+    stride-2 and the PixelShuffle phases aligned).  Pixel-wise kernels (projection, dual updates) need nothing from
+    the neighbours; stencils do:
+
+    * Malvar demosaic: 2 rows of the merged mosaic,
+    * denoiser: ``halo`` rows of its RGB input (FastDVDnet two-stage cascade: receptive field -77..+73 rows -> 80;
+      FFDNet-colour: -24..+25 -> 28), exchanged once per ADMM iteration; the strip is then denoised with its halo and
+      cropped ("overlap-tile"), so zero padding is only ever applied at true image borders.
+
+    ``exchange`` moves the halo rows with point-to-point sends between neighbouring ranks (NCCL over NVLink on GPUs,
+    gloo in the CPU/one-GPU tests).  No collective is on the per-iteration path; the only reductions are the scalar
+    PSNR sums, the fine-tune loss/gradient all-reduce (SUM: the loss is normalised by the pixel count of the whole frame)
+    and the final gather of the result strips."""
+
+    def __init__(self, ctx, H_total, W):
+        if H_total % (4 * ctx.world) != 0:
+            raise ValueError("tiled mode needs H divisible by 4*world_size (got H=%d, world=%d)" % (H_total, ctx.world))
+        self.ctx = ctx
+        self.rank, self.world = ctx.rank, ctx.world
+        self.H_total, self.W = H_total, W
+        self.rows = H_total // ctx.world
+        self.r0 = self.rank * self.rows
+        self.total_pixels = H_total * W
+
+    def slice_rows(self, a):
+        """numpy/torch [H_total, ...] -> this rank's rows."""
+        return a[self.r0:self.r0 + self.rows]
+
+    def halo_sizes(self, halo):
+        halo = min(halo, self.rows)
+        return (halo if self.rank > 0 else 0), (halo if self.rank < self.world - 1 else 0)
+
+    def exchange(self, own, halo):
+        """own [B,C,rows,W] (contiguous, this rank's rows) -> (ext [B,C,top+rows+bot,W], top)."""
+        import torch.distributed as dist
+        top, bot = self.halo_sizes(halo)
+        B, C, rows, W = own.shape
+        ext = torch.empty((B, C, top + rows + bot, W), dtype=own.dtype, device=own.device)
+        ext[:, :, top:top + rows].copy_(own)
+        if self.world == 1:
+            return ext, 0
+        host = self.ctx.backend != "nccl"          # gloo moves CUDA halos through host memory (tests / CPU runs)
+        ops, bufs = [], []
+        if top:      # upper neighbour: send my first rows, receive its last rows
+            snd = own[:, :, :top].contiguous()
+            snd = snd.cpu() if host else snd
+            rcv = torch.empty_like(snd)
+            ops += [dist.P2POp(dist.isend, snd, self.rank - 1), dist.P2POp(dist.irecv, rcv, self.rank - 1)]
+            bufs.append(("top", rcv, snd))
+        if bot:
+            snd = own[:, :, rows - bot:].contiguous()
+            snd = snd.cpu() if host else snd
+            rcv = torch.empty_like(snd)
+            ops += [dist.P2POp(dist.isend, snd, self.rank + 1), dist.P2POp(dist.irecv, rcv, self.rank + 1)]
+            bufs.append(("bot", rcv, snd))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        for where, rcv, _ in bufs:
+            if where == "top":
+                ext[:, :, :top].copy_(rcv)
+            else:
+                ext[:, :, top + rows:].copy_(rcv)
+        return ext, top
+
+    def all_reduce_sum(self, t):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t
+
+    def gather_rows(self, strip):
+        """strip [..., rows, W] on every rank -> full [..., H_total, W] on every rank."""
+        if self.world == 1:
+            return strip
+        import torch.distributed as dist
+        src = strip.contiguous()
+        if self.ctx.backend != "nccl":
+            src = src.cpu()
+        parts = [torch.empty_like(src) for _ in range(self.world)]
+        dist.all_gather(parts, src)
+        return torch.cat(parts, dim=-2).to(strip.device)
+
+
 def init(backend=None):
     """Reads RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* (torchrun) and initialises the process group."""
     rank = int(os.environ.get("RANK", "0"))

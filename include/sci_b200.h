@@ -265,9 +265,12 @@ int sci_host_legacy_normal(uint32_t* key_host, int* pos_host, int* has_gauss_hos
 /* Measurement-consistency loss of the online fine-tune (test_ffdnet_ipol.py:275-291,
  * test_fastdvdnet.py:428-431):  m = RGGB samples of xhat; up = sum_t m_t*phi_t;
  * loss += mean((up - y)^2) over H*W (fp64 accumulate);  dxhat[t][c][p] = phi_t * 2(up-y)/(H*W) at the
- * Bayer colour of p, 0 elsewhere.  dxhat may be NULL (loss only). */
+ * Bayer colour of p, 0 elsewhere.  dxhat may be NULL (loss only).  norm_pixels = 0 normalises by this tensor's
+ * H*W; a row strip of a spatially tiled frame passes the pixel count of the WHOLE frame. */
 int sci_meas_loss_fwd_bwd(const float* xhat, const float* phi, const float* y, float* dxhat, double* loss,
-                          int H, int W, int B, void* stream);
+                          int H, int W, int B, long norm_pixels, void* stream);
+/* out = x + a*y (the merged mosaic x + b/rho of a row strip before its halo rows are exchanged). */
+int sci_axpy(const float* x, float a, const float* y, float* out, long n, void* stream);
 
 /* Adam step over a flat parameter bucket (torch.optim.Adam defaults: betas (0.9,0.999), eps 1e-8, no weight
  * decay; test_ffdnet_ipol.py:251, test_fastdvdnet.py:385).  step is 1-based. */
