@@ -48,6 +48,71 @@ def _worker(rank, world, port, q):
     ctx.finalize()
 
 
+def _fdvd():
+    from adaptivepnp_sci_b200.fastdvdnet_adapter import DataParallelLike
+    from adaptivepnp_sci_b200.fastdvdnet_models import FastDVDnet
+    from adaptivepnp_sci_b200.synthetic import fastdvdnet_synthetic_state_dict
+    m = DataParallelLike(FastDVDnet())
+    m.load_state_dict({"module." + k: v for k, v in fastdvdnet_synthetic_state_dict().items()}, strict=True)
+    return m.eval().cuda()
+
+
+FH, FW, FB = 352, 32, 3          # 2 strips of 176 rows: 80-row halo < strip, FastDVDnet sees only part of the neighbour
+
+
+def _fcase():
+    from adaptivepnp_sci_b200.synthetic import make_case
+    meas, mask, orig = make_case(FH, FW, FB, 77, bayer=True)
+    warm = np.clip(meas[:, :, None] * mask / np.maximum(mask.sum(2, keepdims=True), 1), 0, 1).astype(np.float32)
+    return meas, mask, orig, warm
+
+
+def _fworker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK="0", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                      SCI_CONV_IMPL="ref")
+    from adaptivepnp_sci_b200 import parallel
+    from adaptivepnp_sci_b200.dvp_linear_inv_2_stage_ADMM_tensor_online import twoStageAdmm_denoise_bayer
+    from adaptivepnp_sci_b200.utilspy import worker_init_fn
+    ctx = parallel.init(backend="gloo")
+    tile = parallel.TileContext(ctx, FH, FW)
+    meas, mask, orig, warm = _fcase()
+    m = _fdvd()
+    worker_init_fn(0)
+    r = twoStageAdmm_denoise_bayer(tile.slice_rows(meas), tile.slice_rows(mask), 1, 0.01, 'fastdvd_color', [4], False,
+                                   [12 / 255], x0_bayer=torch.from_numpy(tile.slice_rows(warm)).cuda(),
+                                   X_orig=tile.slice_rows(orig), model_denoise=m, logf=io.StringIO(), tile=tile,
+                                   update_times=-1, **KW)
+    q.put((rank, r[0], r[1], np.array(r[4]), m.state_dict()["module.temp2.inc.convblock.3.weight"].cpu().numpy()))
+    ctx.finalize()
+
+
+def test_tiled_fastdvdnet_equals_untiled(cuda, monkeypatch):
+    monkeypatch.setenv("SCI_CONV_IMPL", "ref")
+    from adaptivepnp_sci_b200.dvp_linear_inv_2_stage_ADMM_tensor_online import twoStageAdmm_denoise_bayer
+    from adaptivepnp_sci_b200.utilspy import worker_init_fn
+    meas, mask, orig, warm = _fcase()
+    m = _fdvd()
+    worker_init_fn(0)
+    ref = twoStageAdmm_denoise_bayer(meas, mask, 1, 0.01, 'fastdvd_color', [4], False, [12 / 255],
+                                     x0_bayer=torch.from_numpy(warm).cuda(), X_orig=orig, model_denoise=m,
+                                     logf=io.StringIO(), update_times=-1, **KW)
+    w_ref = m.state_dict()["module.temp2.inc.convblock.3.weight"].cpu().numpy()
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    procs = [ctxm.Process(target=_fworker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = sorted((q.get(timeout=300) for _ in range(2)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, rgb, xb, psnr_all, w in outs:
+        assert np.max(np.abs(rgb - ref[0])) < 2e-5 and np.max(np.abs(xb - ref[1])) < 2e-5
+        assert np.max(np.abs(psnr_all - np.array(ref[4]))) < 1e-3
+        assert np.max(np.abs(w - w_ref)) <= 2 * 2e-6 * 1.01 and np.mean(np.abs(w - w_ref)) < 0.1 * 2e-6
+
+
 def test_tiled_equals_untiled(cuda, monkeypatch):
     monkeypatch.setenv("SCI_CONV_IMPL", "ref")          # fp32 engine: the comparison isolates the tiling logic
     from adaptivepnp_sci_b200.dvp_linear_inv_2_stage_ADMM_tensor_online import twoStageAdmm_denoise_bayer
