@@ -58,16 +58,17 @@ PROTOTYPES = {
     "sci_bn_param_grad": [_p, _p, _p, _p, _p, _p, _i, _p],
     "sci_nhwc_pixel_unshuffle": [_p, _p, _i, _i, _i, _i, _p],
     "sci_nhwc_dilate2": [_p, _p, _i, _i, _i, _i, _p],
-    "sci_ffdnet_pack_input": [_p, _f, _p, _i, _i, _i, _i, _i, _p],
-    "sci_ffdnet_unpack_output": [_p, _p, _i, _i, _i, _i, _p],
-    "sci_ffdnet_unpack_output_grad": [_p, _p, _i, _i, _i, _i, _p],
+    "sci_ffdnet_pack_input": [_p, _f, _p, _i, _i, _i, _i, _i, _i, _p],
+    "sci_ffdnet_unpack_output": [_p, _p, _i, _i, _i, _i, _i, _p],
+    "sci_ffdnet_unpack_output_grad": [_p, _p, _i, _i, _i, _i, _i, _p],
+    "sci_dual_update_gray": [_p, _p, _p, _p, _p, _p, _i, _l, _p, _p, _p],
     "sci_fastdvd_pack_input": [_p, _f, _p, _i, _i, _i, _i, _i, _p],
     "sci_fastdvd_output": [_p, _p, _p, _i, _i, _i, _i, _p],
     "sci_fastdvd_output_grad": [_p, _p, _i, _i, _i, _i, _p],
     "sci_fastdvd_pack_input_grad": [_p, _p, _i, _i, _i, _i, _i, _p],
     "sci_fastdvd_noisy_input": [_p, _p, _p, _l, _p],
     "sci_host_legacy_normal": [_p, _p, _p, _p, _d, _d, _p, _l, _i],
-    "sci_meas_loss_fwd_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _l, _p],
+    "sci_meas_loss_fwd_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _l, _p],
     "sci_axpy": [_p, _f, _p, _p, _l, _p],
     "sci_adam_step": [_p, _p, _p, _p, _l, _d, _d, _d, _d, _i, _p],
 }

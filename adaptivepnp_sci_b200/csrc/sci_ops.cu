@@ -465,6 +465,41 @@ extern "C" int sci_dual_update_rgb(const float* xhat, const float* x_rgb, float*
     return SCI_OK;
 }
 
+// Gray-scale variant of the stage-2 bookkeeping (derived FFDNet-gray config): no Bayer sampling,
+// theta = clip(xhat); b += x - theta; w += x_pre - xhat; optional PSNR.  One thread = 4 pixels.
+__global__ void __launch_bounds__(256) dual_update_gray_kernel(const float* __restrict__ xhat, const float* __restrict__ x_pre,
+                                                                float* __restrict__ w, const float* __restrict__ x,
+                                                                float* __restrict__ b, float* __restrict__ theta,
+                                                                int first_iter, long n, const float* __restrict__ orig,
+                                                                double* __restrict__ sse) {
+    __shared__ double red[32];
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    double err = 0.0;
+    if (i < n) {
+        const float xh = xhat[i];
+        const float th = fminf(fmaxf(xh, 0.f), 1.f);
+        w[i] = w[i] + (x_pre[i] - xh);
+        const float xv = first_iter ? xh : x[i];
+        b[i] = b[i] + (xv - th);
+        theta[i] = th;
+        if (orig) { const float d = th - orig[i]; err = (double)(d * d); }
+    }
+    if (orig) {
+        const double s = block_sum(err, red);
+        if (threadIdx.x == 0) atomicAdd(sse, s);
+    }
+}
+
+extern "C" int sci_dual_update_gray(const float* xhat, const float* x_pre, float* w, const float* x, float* b, float* theta,
+                                    int first_iter, long n, const float* orig, double* sse, void* stream) {
+    SCI_REQUIRE(xhat && x_pre && w && x && b && theta && n > 0, "dual_update_gray: null pointer / size");
+    SCI_REQUIRE(!orig || sse, "dual_update_gray: orig given without sse");
+    dual_update_gray_kernel<<<sci_ceil_div(n, 256), 256, 0, sci_stream(stream)>>>(xhat, x_pre, w, x, b, theta, first_iter, n,
+                                                                                 orig, sse);
+    SCI_CHECK_LAUNCH("dual_update_gray");
+    return SCI_OK;
+}
+
 // ---------------------------------------------------------------------------
 // RGB <-> Bayer index remaps (bit-exact).
 // ---------------------------------------------------------------------------

@@ -136,8 +136,8 @@ __global__ void dilate2_kernel(const float* __restrict__ in, float* __restrict__
 }
 
 // ---- FFDNet boundary -----------------------------------------------------------------------------
-__global__ void ffdnet_pack_kernel(const float* __restrict__ u, float sigma, float* __restrict__ out, int B, int H, int W,
-                                   int Cpad, int round_tf32) {
+__global__ void ffdnet_pack_kernel(const float* __restrict__ u, float sigma, float* __restrict__ out, int B, int C, int H,
+                                   int W, int Cpad, int round_tf32) {
     const int h2 = H >> 1, w2 = W >> 1;
     const long total = (long)B * h2 * w2 * Cpad;
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -148,10 +148,10 @@ __global__ void ffdnet_pack_kernel(const float* __restrict__ u, float sigma, flo
     // round_tf32: channel k holds tf32(v), channel k+16 the remainder tf32(v - tf32(v)) (weights duplicated)
     const int kk = (round_tf32 && k >= 16) ? k - 16 : k;
     float v = 0.f;
-    if (kk < 12) {
+    if (kk < 4 * C) {                                  // KAIR pixel-unshuffle: channel c*4 + dy*2 + dx (basicblock.py:104-126)
         const int c = kk >> 2, dy = (kk >> 1) & 1, dx = kk & 1;
-        v = u[(((long)n * 3 + c) * H + 2 * h + dy) * W + 2 * w + dx];
-    } else if (kk == 12) {
+        v = u[(((long)n * C + c) * H + 2 * h + dy) * W + 2 * w + dx];
+    } else if (kk == 4 * C) {                          // sigma map appended after the image channels (network_ffdnet.py:63-64)
         v = sigma;
     }
     if (round_tf32) {
@@ -162,18 +162,19 @@ __global__ void ffdnet_pack_kernel(const float* __restrict__ u, float sigma, flo
 }
 
 // xhat[n][c][2h+dy][2w+dx] = y[n][h][w][c*4+dy*2+dx]   (nn.PixelShuffle(2), network_ffdnet.py:66)
-__global__ void ffdnet_unpack_kernel(const float* __restrict__ y, float* __restrict__ xhat, int B, int H, int W, int Cpad) {
-    const long total = (long)B * 3 * H * W;
+__global__ void ffdnet_unpack_kernel(const float* __restrict__ y, float* __restrict__ xhat, int B, int C, int H, int W,
+                                     int Cpad) {
+    const long total = (long)B * C * H * W;
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
-    const int wf = (int)(idx % W), hf = (int)((idx / W) % H), c = (int)((idx / ((long)W * H)) % 3);
-    const int n = (int)(idx / (3L * W * H));
+    const int wf = (int)(idx % W), hf = (int)((idx / W) % H), c = (int)((idx / ((long)W * H)) % C);
+    const int n = (int)(idx / ((long)C * W * H));
     const int k = c * 4 + (hf & 1) * 2 + (wf & 1);
     xhat[idx] = y[(((long)n * (H >> 1) + (hf >> 1)) * (W >> 1) + (wf >> 1)) * Cpad + k];
 }
 
-// adjoint: dy[n][h][w][k] = dxhat[n][k>>2][2h+dy][2w+dx] for k < 12, 0 in the padded columns
-__global__ void ffdnet_unpack_grad_kernel(const float* __restrict__ dxhat, float* __restrict__ dy, int B, int H, int W,
+// adjoint: dy[n][h][w][k] = dxhat[n][k>>2][2h+dy][2w+dx] for k < 4C, 0 in the padded columns
+__global__ void ffdnet_unpack_grad_kernel(const float* __restrict__ dxhat, float* __restrict__ dy, int B, int C, int H, int W,
                                           int Cpad) {
     const int h2 = H >> 1, w2 = W >> 1;
     const long total = (long)B * h2 * w2 * Cpad;
@@ -183,9 +184,9 @@ __global__ void ffdnet_unpack_grad_kernel(const float* __restrict__ dxhat, float
     const long p = idx / Cpad;
     const int w = (int)(p % w2), h = (int)((p / w2) % h2), n = (int)(p / ((long)w2 * h2));
     float v = 0.f;
-    if (k < 12) {
+    if (k < 4 * C) {
         const int c = k >> 2, dy_ = (k >> 1) & 1, dx_ = k & 1;
-        v = dxhat[(((long)n * 3 + c) * H + 2 * h + dy_) * W + 2 * w + dx_];
+        v = dxhat[(((long)n * C + c) * H + 2 * h + dy_) * W + 2 * w + dx_];
     }
     dy[idx] = v;
 }
@@ -279,7 +280,7 @@ __global__ void noisy_input_kernel(const float* __restrict__ v, const double* __
 // ---- measurement loss -------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) meas_loss_kernel(const float* __restrict__ xhat, const float* __restrict__ phi,
                                                          const float* __restrict__ y, float* __restrict__ dxhat,
-                                                         double* __restrict__ loss, int H, int W, int B, float norm,
+                                                         double* __restrict__ loss, int H, int W, int B, int C, float norm,
                                                          double inv_count) {
     __shared__ double red[32];
     const long plane = (long)H * W;
@@ -287,17 +288,16 @@ __global__ void __launch_bounds__(256) meas_loss_kernel(const float* __restrict_
     double err = 0.0;
     if (p < plane) {
         const int row = (int)(p / W), col = (int)(p % W);
-        const int c = (row & 1) + (col & 1);
+        const int c = (C == 3) ? (row & 1) + (col & 1) : 0;       // colour: RGGB sample; gray: the pixel itself
         float up = 0.f;
-        for (int t = 0; t < B; ++t) up += xhat[((long)t * 3 + c) * plane + p] * phi[t * plane + p];
+        for (int t = 0; t < B; ++t) up += xhat[((long)t * C + c) * plane + p] * phi[t * plane + p];
         const float diff = up - y[p];
         err = (double)(diff * diff);
         if (dxhat) {
             const float g = norm * diff;                      // mse_loss backward: (2/N) * (input - target)
             for (int t = 0; t < B; ++t) {
                 const float gv = g * phi[t * plane + p];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) dxhat[((long)t * 3 + k) * plane + p] = (k == c) ? gv : 0.f;
+                for (int k = 0; k < C; ++k) dxhat[((long)t * C + k) * plane + p] = (k == c) ? gv : 0.f;
             }
         }
     }
@@ -392,27 +392,29 @@ extern "C" int sci_nhwc_dilate2(const float* in, float* out, int N, int H, int W
     return SCI_OK;
 }
 
-extern "C" int sci_ffdnet_pack_input(const float* u, float sigma, float* out, int B, int H, int W, int Cpad, int round_tf32,
-                                     void* stream) {
-    SCI_REQUIRE(u && out && B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && Cpad >= (round_tf32 ? 32 : 13),
-                "ffdnet_pack_input");
-    ffdnet_pack_kernel<<<grid1d((long)B * (H / 2) * (W / 2) * Cpad), 256, 0, sci_stream(stream)>>>(u, sigma, out, B, H, W, Cpad,
-                                                                                                 round_tf32);
+extern "C" int sci_ffdnet_pack_input(const float* u, float sigma, float* out, int B, int C, int H, int W, int Cpad,
+                                     int round_tf32, void* stream) {
+    SCI_REQUIRE(u && out && B > 0 && (C == 1 || C == 3) && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 &&
+                Cpad >= (round_tf32 ? 32 : 4 * C + 1), "ffdnet_pack_input");
+    ffdnet_pack_kernel<<<grid1d((long)B * (H / 2) * (W / 2) * Cpad), 256, 0, sci_stream(stream)>>>(u, sigma, out, B, C, H, W,
+                                                                                                 Cpad, round_tf32);
     SCI_CHECK_LAUNCH("ffdnet_pack_input");
     return SCI_OK;
 }
 
-extern "C" int sci_ffdnet_unpack_output(const float* y, float* xhat, int B, int H, int W, int Cpad, void* stream) {
-    SCI_REQUIRE(y && xhat && B > 0 && H % 2 == 0 && W % 2 == 0 && Cpad >= 12, "ffdnet_unpack_output");
-    ffdnet_unpack_kernel<<<grid1d((long)B * 3 * H * W), 256, 0, sci_stream(stream)>>>(y, xhat, B, H, W, Cpad);
+extern "C" int sci_ffdnet_unpack_output(const float* y, float* xhat, int B, int C, int H, int W, int Cpad, void* stream) {
+    SCI_REQUIRE(y && xhat && B > 0 && (C == 1 || C == 3) && H % 2 == 0 && W % 2 == 0 && Cpad >= 4 * C, "ffdnet_unpack_output");
+    ffdnet_unpack_kernel<<<grid1d((long)B * C * H * W), 256, 0, sci_stream(stream)>>>(y, xhat, B, C, H, W, Cpad);
     SCI_CHECK_LAUNCH("ffdnet_unpack_output");
     return SCI_OK;
 }
 
-extern "C" int sci_ffdnet_unpack_output_grad(const float* dxhat, float* dy, int B, int H, int W, int Cpad, void* stream) {
-    SCI_REQUIRE(dy && dxhat && B > 0 && H % 2 == 0 && W % 2 == 0 && Cpad >= 12, "ffdnet_unpack_output_grad");
-    ffdnet_unpack_grad_kernel<<<grid1d((long)B * (H / 2) * (W / 2) * Cpad), 256, 0, sci_stream(stream)>>>(dxhat, dy, B, H, W,
-                                                                                                          Cpad);
+extern "C" int sci_ffdnet_unpack_output_grad(const float* dxhat, float* dy, int B, int C, int H, int W, int Cpad,
+                                             void* stream) {
+    SCI_REQUIRE(dy && dxhat && B > 0 && (C == 1 || C == 3) && H % 2 == 0 && W % 2 == 0 && Cpad >= 4 * C,
+                "ffdnet_unpack_output_grad");
+    ffdnet_unpack_grad_kernel<<<grid1d((long)B * (H / 2) * (W / 2) * Cpad), 256, 0, sci_stream(stream)>>>(dxhat, dy, B, C, H,
+                                                                                                          W, Cpad);
     SCI_CHECK_LAUNCH("ffdnet_unpack_output_grad");
     return SCI_OK;
 }
@@ -462,11 +464,11 @@ extern "C" int sci_fastdvd_noisy_input(const float* v, const double* noise, floa
 }
 
 extern "C" int sci_meas_loss_fwd_bwd(const float* xhat, const float* phi, const float* y, float* dxhat, double* loss, int H,
-                                     int W, int B, long norm_pixels, void* stream) {
-    SCI_REQUIRE(xhat && phi && y && loss && H > 0 && W > 0 && B > 0 && norm_pixels >= 0, "meas_loss");
+                                     int W, int B, int C, long norm_pixels, void* stream) {
+    SCI_REQUIRE(xhat && phi && y && loss && H > 0 && W > 0 && B > 0 && (C == 1 || C == 3) && norm_pixels >= 0, "meas_loss");
     // mean over `norm_pixels` (0 = this tensor's H*W; a row strip of a larger frame passes the frame's pixel count)
     const double cnt = norm_pixels > 0 ? (double)norm_pixels : (double)H * (double)W;
-    meas_loss_kernel<<<grid1d((long)H * W), 256, 0, sci_stream(stream)>>>(xhat, phi, y, dxhat, loss, H, W, B,
+    meas_loss_kernel<<<grid1d((long)H * W), 256, 0, sci_stream(stream)>>>(xhat, phi, y, dxhat, loss, H, W, B, C,
                                                                           (float)(2.0 / cnt), 1.0 / cnt);
     SCI_CHECK_LAUNCH("meas_loss");
     return SCI_OK;

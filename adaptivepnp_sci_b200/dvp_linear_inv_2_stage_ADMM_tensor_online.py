@@ -27,7 +27,8 @@ import torch
 from . import iqa, ops
 from .utils_image import cuda2np, np2tch_cuda  # noqa: F401  (np2tch_cuda is imported from here by the scripts)
 
-__all__ = ["admm_denoise_bayer_demosaic_pre", "twoStageAdmm_denoise_bayer", "np2tch_cuda", "cuda2np"]
+__all__ = ["admm_denoise_bayer_demosaic_pre", "twoStageAdmm_denoise_bayer", "twoStageAdmm_denoise_gray", "np2tch_cuda",
+           "cuda2np"]
 
 
 def _as_list(sigma, iter_max):
@@ -310,3 +311,59 @@ def twoStageAdmm_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, gamma=0.01,
         return x_bayer_np, psnr_, ssim_, psnr_all
     xbgr3_np = cuda2np(ops.planar_to_pixlast(xhat, 3, B).view(H, W, 3, B))
     return xbgr3_np, x_bayer_np, psnr_, ssim_, psnr_all, model_denoise, model_demosaic
+
+
+def twoStageAdmm_denoise_gray(y, Phi, denoiser='ffdnet_gray', iter_max=50, sigma=None, x0=None, X_orig=None,
+                              model_denoise=None, show_iqa=True, lr_=0.000001, inital_iter=1, interval_iter=5, logf=None,
+                              update_=False, update_per_iter=1, noise_estimate=False, grad_sync=None):
+    """BASELINE config 2: two-stage ADMM + online FFDNet-gray on a GRAYSCALE cube.
+
+    The reference has no function for this configuration (``twoStageAdmm_denoise_bayer`` only knows 'tv', 'ffdnet_color'
+    and 'fastdvd_color', dvp...online.py:147,164,214,262; the gray network is only constructed by the script's ``else``
+    branch, two_stage_ADMM_Online_FFD_Warm.py:37-40).  Following SURVEY §8(c) this is the SAME loop with the Bayer split /
+    demosaic replaced by the identity (alpha = 1, rho = 1, tau = 100, k = 0 aliasing included); parity is checked against the
+    derived oracle ``oracle.admm.twoStageAdmm_denoise_gray`` and reported as "parity vs derived oracle".
+
+    y [H,W], Phi [H,W,B], x0 [H,W,B] (warm start) -> (xhat_np[H,W,B], theta_np[H,W,B], psnr_, ssim_, psnr_all, model)."""
+    if denoiser != 'ffdnet_gray':
+        raise ValueError('Unsupported denoiser {}!'.format(denoiser))
+    from . import ffdnet_adapter
+    sigma, iter_max = _as_list(sigma, iter_max)
+    pb = _Problem(y, Phi, x0, X_orig)
+    dev = pb.y.device
+    H, W, B = pb.H, pb.W, pb.B
+    tau = 100
+    n_total = int(sum(iter_max))
+    want_iqa = bool(show_iqa and X_orig is not None)
+    sse = torch.zeros(max(n_total, 1), dtype=torch.float64, device=dev) if want_iqa else None
+    theta, b, x = pb.theta, pb.b, pb.x
+    w = torch.zeros((B, 1, H, W), dtype=torch.float32, device=dev)
+    x_pre = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+    u = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
+    sched, k, xhat = [], 0, None
+    for idx, nsig in enumerate(sigma):
+        for _ in range(iter_max[idx]):
+            ops.project_stage2(theta, b, pb.phi, pb.y, pb.phisum, x, 1, 1)                # alpha = rho = 1
+            ops.axpy(x, 1.0, b, out=x_pre)                                                # x + b/rho
+            ops.axpy(x_pre.view(B, 1, H, W), -float(np.float32(1 / tau)), w, out=u)       # - w/tau
+            do_update = bool(update_ and k > inital_iter and k % interval_iter == 0)
+            xhat = ffdnet_adapter.denoise_planar(u, pb, nsig, model_denoise, lr_, do_update, update_per_iter,
+                                                 grad_sync=grad_sync)
+            _lib_call("sci_dual_update_gray", xhat, x_pre, w, x, b, theta, k == 0, pb.orig if want_iqa else None,
+                      sse[k:k + 1] if want_iqa else None)
+            sched.append(nsig)
+            k += 1
+    psnr_all = []
+    if want_iqa:
+        psnr_all = list(iqa.psnr_from_sse(sse.cpu().numpy()[:n_total], pb.npix * B))
+        _log_iterations(denoiser, sched, psnr_all, noise_estimate, logf)
+    theta_np = pb.to_hwb(theta)
+    psnr_, ssim_ = pb.frame_iqa(theta, theta_np, X_orig)
+    xhat_np = pb.to_hwb(xhat.view(B, H, W))
+    return xhat_np, theta_np, psnr_, ssim_, psnr_all, model_denoise
+
+
+def _lib_call(name, xhat, x_pre, w, x, b, theta, first, orig, sse):
+    from ._lib import call, ptr, stream
+    call(name, ptr(xhat), ptr(x_pre), ptr(w), ptr(x), ptr(b), ptr(theta), int(bool(first)), theta.numel(), ptr(orig), ptr(sse),
+         stream())

@@ -297,12 +297,11 @@ class FFDNetEngine(_EngineBase):
             self.layers_inf = [ConvLayer(c, None, relu=(i < len(convs) - 1), first=(i == 0), wsplit=True, dup_in=(i > 0))
                                for i, c in enumerate(convs)]
         self.in_nc, self.out_nc = module.in_nc, module.out_nc
-        if (self.in_nc, self.out_nc) != (3, 3):
-            raise NotImplementedError("native FFDNet engine: colour model (in_nc=out_nc=3); the gray model of "
-                                      "BASELINE config 2 is a next-round row")
+        if (self.in_nc, self.out_nc) not in ((3, 3), (1, 1)):
+            raise NotImplementedError("native FFDNet engine: colour (3->3) and gray (1->1) models")
 
     def forward(self, u, sigma, train=False):
-        """u [B,3,H,W] planar fp32 -> xhat [B,3,H,W].  train=True keeps every activation for backward()."""
+        """u [B,C,H,W] planar fp32 (C = 3 colour / 1 gray) -> xhat [B,C,H,W].  train=True keeps the activations."""
         B, _, H, W = u.shape
         if H % 2 or W % 2:
             raise _lib.SciError("native FFDNet engine needs even H and W (Bayer frames always are)")
@@ -313,15 +312,15 @@ class FFDNetEngine(_EngineBase):
             return self._forward_precise(u, sigma, B, H, W)
         L0 = self.layers[0]
         a = self.ws.get("in", (B, h2, w2, L0.Ci_pad), dev)
-        call("sci_ffdnet_pack_input", ptr(u), float(sigma), ptr(a), B, H, W, L0.Ci_pad, int(self.tf32), stream())
+        call("sci_ffdnet_pack_input", ptr(u), float(sigma), ptr(a), B, self.in_nc, H, W, L0.Ci_pad, int(self.tf32), stream())
         acts = [a]
         for i, L in enumerate(self.layers):
             name = ("act%d" % i) if train else ("pp%d" % (i % 2) if i < len(self.layers) - 1 else "tail")
             y = self.ws.get(name, (B, h2, w2, L.Co_pad), dev)
             self.conv(L, acts[-1], B, h2, w2, y, round_out=i < len(self.layers) - 1)
             acts.append(y)
-        xhat = self.ws.get("xhat_train" if train else "xhat", (B, 3, H, W), dev)
-        call("sci_ffdnet_unpack_output", ptr(acts[-1]), ptr(xhat), B, H, W, self.layers[-1].Co_pad, stream())
+        xhat = self.ws.get("xhat_train" if train else "xhat", (B, self.out_nc, H, W), dev)
+        call("sci_ffdnet_unpack_output", ptr(acts[-1]), ptr(xhat), B, self.out_nc, H, W, self.layers[-1].Co_pad, stream())
         if train:
             self._saved = (acts, B, H, W)
         return xhat
@@ -331,14 +330,14 @@ class FFDNetEngine(_EngineBase):
         h2, w2 = H // 2, W // 2
         Ls = self.layers_inf
         a = self.ws.get("in", (B, h2, w2, Ls[0].Ci_pad), dev)
-        call("sci_ffdnet_pack_input", ptr(u), float(sigma), ptr(a), B, H, W, Ls[0].Ci_pad, 1, stream())
+        call("sci_ffdnet_pack_input", ptr(u), float(sigma), ptr(a), B, self.in_nc, H, W, Ls[0].Ci_pad, 1, stream())
         for i, L in enumerate(Ls):
             last = i == len(Ls) - 1
             y = self.ws.get("tail" if last else "ppx%d" % (i % 2), (B, h2, w2, L.Co_pad * (1 if last else 2)), dev)
             self.conv(L, a, B, h2, w2, y, round_out=not last, emit_lo=not last)
             a = y
-        xhat = self.ws.get("xhat", (B, 3, H, W), dev)
-        call("sci_ffdnet_unpack_output", ptr(a), ptr(xhat), B, H, W, Ls[-1].Co_pad, stream())
+        xhat = self.ws.get("xhat", (B, self.out_nc, H, W), dev)
+        call("sci_ffdnet_unpack_output", ptr(a), ptr(xhat), B, self.out_nc, H, W, Ls[-1].Co_pad, stream())
         return xhat
 
     def backward(self, dxhat):
@@ -350,7 +349,7 @@ class FFDNetEngine(_EngineBase):
         self.dw_flat.zero_()
         Lt = self.layers[-1]
         dy = self.ws.get("g_tail", (B, h2, w2, Lt.Co_pad), dev)
-        call("sci_ffdnet_unpack_output_grad", ptr(dxhat), ptr(dy), B, H, W, Lt.Co_pad, stream())
+        call("sci_ffdnet_unpack_output_grad", ptr(dxhat), ptr(dy), B, self.out_nc, H, W, Lt.Co_pad, stream())
         for i in range(len(self.layers) - 1, -1, -1):
             L = self.layers[i]
             dz = self.act_bwd(L, dy, acts[i + 1], n_pix, L.Co_pad)

@@ -31,12 +31,13 @@ def _tile_loss(eng, out_ext, phi, y, dbuf_name, loss_slot, tile, want_grad):
     if tile is None:
         H, W = out_ext.shape[2:]
         d = eng.ws.get(dbuf_name, tuple(out_ext.shape), dev) if want_grad else None
-        call("sci_meas_loss_fwd_bwd", ptr(out_ext), ptr(phi), ptr(y), ptr(d), ptr(loss_slot), H, W, B, 0, stream())
+        call("sci_meas_loss_fwd_bwd", ptr(out_ext), ptr(phi), ptr(y), ptr(d), ptr(loss_slot), H, W, B, out_ext.shape[1], 0,
+             stream())
         return d
     top, rows, W = tile.top, tile.rows, out_ext.shape[3]
     own = out_ext[:, :, top:top + rows].contiguous()
     d_own = eng.ws.get(dbuf_name + "_own", tuple(own.shape), dev) if want_grad else None
-    call("sci_meas_loss_fwd_bwd", ptr(own), ptr(phi), ptr(y), ptr(d_own), ptr(loss_slot), rows, W, B,
+    call("sci_meas_loss_fwd_bwd", ptr(own), ptr(phi), ptr(y), ptr(d_own), ptr(loss_slot), rows, W, B, own.shape[1],
          tile.total_pixels, stream())
     if not want_grad:
         return None

@@ -228,15 +228,15 @@ int sci_bn_param_grad(const float* s1, const float* s2, const float* gamma, cons
 int sci_nhwc_pixel_unshuffle(const float* in, float* out, int N, int H, int W, int C, void* stream);
 int sci_nhwc_dilate2(const float* in, float* out, int N, int H, int W, int C, void* stream);
 
-/* FFDNet boundary (models/network_ffdnet.py:56-68, models/basicblock.py:104-126):
- * pack:   u [B][3][H][W] planar -> head input [B][H/2][W/2][Cpad]: channel c*4+dy*2+dx = u[c][2h+dy][2w+dx],
- *         channel 12 = sigma, rest 0 (TF32-rounded if round_tf32).
+/* FFDNet boundary (models/network_ffdnet.py:56-68, models/basicblock.py:104-126); C = 3 (colour) or 1 (gray):
+ * pack:   u [B][C][H][W] planar -> head input [B][H/2][W/2][Cpad]: channel c*4+dy*2+dx = u[c][2h+dy][2w+dx],
+ *         channel 4C = sigma, rest 0 (round_tf32: tf32(v) in channel k and the remainder in channel k+16).
  * unpack: tail output [B][H/2][W/2][Cpad] (column c*4+dy*2+dx) -> xhat [B][3][H][W] planar (PixelShuffle(2)).
  * unpack_grad: d xhat planar -> d tail output (adjoint of unpack). */
-int sci_ffdnet_pack_input(const float* u, float sigma, float* out, int B, int H, int W, int Cpad, int round_tf32,
+int sci_ffdnet_pack_input(const float* u, float sigma, float* out, int B, int C, int H, int W, int Cpad, int round_tf32,
                           void* stream);
-int sci_ffdnet_unpack_output(const float* y, float* xhat, int B, int H, int W, int Cpad, void* stream);
-int sci_ffdnet_unpack_output_grad(const float* dxhat, float* dy, int B, int H, int W, int Cpad, void* stream);
+int sci_ffdnet_unpack_output(const float* y, float* xhat, int B, int C, int H, int W, int Cpad, void* stream);
+int sci_ffdnet_unpack_output_grad(const float* dxhat, float* dy, int B, int C, int H, int W, int Cpad, void* stream);
 
 /* FastDVDnet boundary (packages/fastdvdnet/models.py:185,196,234; fastdvdnet.py:115 circular window):
  * pack:   frames [B][3][H][W] planar -> DenBlock input [B][H][W][Cpad], for block f the channels
@@ -265,10 +265,14 @@ int sci_host_legacy_normal(uint32_t* key_host, int* pos_host, int* has_gauss_hos
 /* Measurement-consistency loss of the online fine-tune (test_ffdnet_ipol.py:275-291,
  * test_fastdvdnet.py:428-431):  m = RGGB samples of xhat; up = sum_t m_t*phi_t;
  * loss += mean((up - y)^2) over H*W (fp64 accumulate);  dxhat[t][c][p] = phi_t * 2(up-y)/(H*W) at the
- * Bayer colour of p, 0 elsewhere.  dxhat may be NULL (loss only).  norm_pixels = 0 normalises by this tensor's
+ * Bayer colour of p, 0 elsewhere (C = 3; with C = 1 xhat is a gray cube [B][1][H][W] and m = xhat).  dxhat may be NULL (loss only).  norm_pixels = 0 normalises by this tensor's
  * H*W; a row strip of a spatially tiled frame passes the pixel count of the WHOLE frame. */
 int sci_meas_loss_fwd_bwd(const float* xhat, const float* phi, const float* y, float* dxhat, double* loss,
-                          int H, int W, int B, long norm_pixels, void* stream);
+                          int H, int W, int B, int C, long norm_pixels, void* stream);
+/* Gray-scale stage-2 bookkeeping (derived FFDNet-gray configuration, no Bayer sampling): theta = clip(xhat);
+ * b += x - theta (first_iter: x := xhat, the k=0 aliasing of dvp...online.py:87-89); w += x_pre - xhat; optional PSNR. */
+int sci_dual_update_gray(const float* xhat, const float* x_pre, float* w, const float* x, float* b, float* theta,
+                         int first_iter, long n, const float* orig, double* sse, void* stream);
 /* out = x + a*y (the merged mosaic x + b/rho of a row strip before its halo rows are exchanged). */
 int sci_axpy(const float* x, float a, const float* y, float* out, long n, void* stream);
 

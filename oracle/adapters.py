@@ -122,3 +122,33 @@ def fastdvdnet_denoiser_full_tensor_v2(vnoisy, sigma, y_bayer=None, Phi=None, mo
     with torch.no_grad():
         v = vnoisy.permute(3, 2, 0, 1)
         return fastdvdnet_seqdenoise(v, noisestd, NUM_IN_FR_EXT, model).permute(2, 3, 1, 0)
+
+
+def ffdnet_gray_denoise_full_tensor(x, y, Phi, sigma, model, lr_=1e-6, updata_=False, update_per_iter=4, losses=None):
+    """DERIVED restatement (no reference function exists, SURVEY §8(c) "config without a reference function"):
+    ``ffdnet_rgb_denoise_full_tensor`` (test_ffdnet_ipol.py:240-359) with the colour/Bayer handling removed —
+    x [H,W,B] gray cube, frames denoised one by one with FFDNet-gray (two_stage_ADMM_Online_FFD_Warm.py:37-40 builds
+    FFDNet(1,1,64,15,'R')), loss MSE(sum_t xhat_t * Phi_t, y) over H*W, fresh Adam per call."""
+    def frames(m):
+        outs = []
+        for t in range(x.shape[2]):
+            img = x[:, :, t].float()[None, None]
+            s = torch.full((1, 1, 1, 1), sigma).type_as(img)
+            outs.append(m(img, s)[0, 0])
+        return torch.stack(outs, dim=2)
+    if updata_:
+        model.train()
+        opt = torch.optim.Adam(model.parameters(), lr=lr_)
+        mse = nn.MSELoss()
+        for _ in range(update_per_iter):
+            loss = mse(torch.sum(frames(model) * Phi, dim=2), y)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            if losses is not None:
+                losses.append(float(loss.detach()))
+        model.eval()
+        with torch.no_grad():
+            return frames(model), model
+    with torch.no_grad():
+        return frames(model)

@@ -160,3 +160,54 @@ def twoStageAdmm_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, gamma=0.01, denois
     if denoiser == 'tv':
         return x_bayer_np, psnr_, ssim_, psnr_all
     return xbgr3.detach().numpy(), x_bayer_np, psnr_, ssim_, psnr_all, model_denoise, model_demosaic
+
+
+def twoStageAdmm_denoise_gray(y, Phi, denoiser='ffdnet_gray', iter_max=50, sigma=None, x0=None, X_orig=None,
+                              model_denoise=None, show_iqa=True, lr_=1e-6, inital_iter=1, interval_iter=5, update_=False,
+                              update_per_iter=1, trace=None):
+    """DERIVED oracle for BASELINE config 2 (two-stage ADMM + online FFDNet-gray on a grayscale cube).  The reference's
+    ``twoStageAdmm_denoise_bayer`` has no gray branch (dvp...online.py:147,164,214,262); this is the same loop
+    (:121-305) with the Bayer split / demosaic replaced by the identity, as specified in SURVEY §8(c):
+        p = theta - b/rho ; x = p + Phi*((y - A p)/(alpha*rho + Phi_sum))      (alpha = 1, rho = 1, tau = 100)
+        x_pre = x + b/rho ; xhat = FFDNet_gray(x_pre - w/tau) [online fine-tune] ; theta = clip(xhat)
+        b += x - theta ; w += x_pre - xhat
+    including the k = 0 aliasing of xall/theta_all.  Returns (xhat_np[H,W,B], theta_np[H,W,B], psnr_, ssim_, psnr_all, model)."""
+    from .adapters import ffdnet_gray_denoise_full_tensor
+    from .sci_ops import A_
+    y = torch.from_numpy(np.ascontiguousarray(y))
+    Phi = torch.from_numpy(np.ascontiguousarray(Phi))
+    sigma, iter_max = _listify(sigma, iter_max)
+    Phi_sum = torch.sum(Phi, dim=2)
+    Phi_sum[Phi_sum == 0] = 1
+    x0all = (y.unsqueeze(2) * Phi) if x0 is None else x0.clone()
+    xall = x0all
+    theta = x0all
+    ball = torch.zeros_like(x0all)
+    w = torch.zeros_like(x0all)
+    alpha, rou, tau = 1, 1, 100
+    psnr_all, k = [], 0
+    xhat = None
+    for idx, nsig in enumerate(sigma):
+        for it in range(iter_max[idx]):
+            p = theta - (1 / rou) * ball
+            t = (y - A_(p, Phi)) / (alpha * rou + Phi_sum)
+            xall[...] = p + Phi * t.unsqueeze(2)                       # in place: aliases theta at k = 0
+            x_pre = xall + (1 / rou) * ball
+            x_w = x_pre - (1 / tau) * w
+            do_update = update_ and k > inital_iter and k % interval_iter == 0
+            losses = None if trace is None else trace.setdefault('losses', [])
+            if do_update:
+                xhat, model_denoise = ffdnet_gray_denoise_full_tensor(x_w, y, Phi, nsig, model_denoise, lr_, True,
+                                                                      update_per_iter, losses=losses)
+            else:
+                xhat = ffdnet_gray_denoise_full_tensor(x_w, y, Phi, nsig, model_denoise, lr_)
+            theta[...] = xhat                                          # writes into xall too while they alias (k = 0)
+            theta = torch.clip(theta, 0, 1)
+            ball = ball + (xall - theta)
+            w = w + (x_pre - xhat)
+            if show_iqa and X_orig is not None:
+                psnr_all.append(compare_psnr(X_orig, theta.numpy(), data_range=1.))
+            k += 1
+    theta_np = theta.numpy()
+    psnr_, ssim_ = _final_iqa(X_orig, theta_np, Phi.shape[2])
+    return xhat.detach().numpy(), theta_np, psnr_, ssim_, psnr_all, model_denoise

@@ -233,6 +233,6 @@ def test_adam_and_loss_kernels(cuda):
     dx = torch.empty(B, 3, H, W, device=cuda)
     lo = torch.zeros(1, dtype=torch.float64, device=cuda)
     xd, pd_, yd = xhat.detach().cuda(), phi.cuda(), y.cuda()       # keep the device tensors alive across the launch
-    call("sci_meas_loss_fwd_bwd", ptr(xd), ptr(pd_), ptr(yd), ptr(dx), ptr(lo), H, W, B, 0, stream())
+    call("sci_meas_loss_fwd_bwd", ptr(xd), ptr(pd_), ptr(yd), ptr(dx), ptr(lo), H, W, B, 3, 0, stream())
     assert abs(float(lo) - float(loss.detach())) < 1e-5 * float(loss.detach())
     assert _rel(dx.cpu(), xhat.grad) < 1e-5

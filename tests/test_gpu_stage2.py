@@ -62,3 +62,28 @@ def test_stage2_fastdvd_color(cuda, impl):
     assert np.max(np.abs(r[0] - d["s2fdvd_rgb"])) < tol and np.max(np.abs(r[1] - d["s2fdvd_x"])) < tol
     assert abs(_psnr(r[1], orig) - _psnr(d["s2fdvd_x"], orig)) < 0.05
     assert np.max(np.abs(np.array(r[4]) - d["s2fdvd_psnr_all"])) < 0.05
+
+
+def test_stage2_ffdnet_gray_vs_derived_oracle(cuda, impl):
+    """BASELINE config 2 (two-stage ADMM + online FFDNet-gray, grayscale): the reference has no function for it, so this is
+    'parity vs derived oracle' (SURVEY §8(c)): the same loop with the Bayer/demosaic stage replaced by the identity."""
+    from adaptivepnp_sci_b200.dvp_linear_inv_2_stage_ADMM_tensor_online import (admm_denoise_bayer_demosaic_pre,
+                                                                                twoStageAdmm_denoise_gray)
+    from adaptivepnp_sci_b200.network_ffdnet import FFDNet
+    from oracle import admm, networks, synthetic
+    meas, mask, orig = synthetic.make_case(64, 64, 8, 1001, bayer=False)
+    warm = admm.admm_denoise_bayer_demosaic_pre(meas, mask, 1, 0.01, 'tv', [40], False, [0], X_orig=orig, show_iqa=False)[0]
+    sd = torch.load(os.path.join(ROOT, "model_zoo", "ffdnet_gray.pth"))
+    mo = networks.FFDNet(1, 1, 64, 15, 'R'); mo.load_state_dict(sd, strict=True); mo.eval()
+    kw = dict(iter_max=[4, 3], sigma=[25 / 255, 12 / 255], X_orig=orig, lr_=2e-6, interval_iter=3, update_=True, update_per_iter=2)
+    ref = admm.twoStageAdmm_denoise_gray(meas, mask, 'ffdnet_gray', x0=torch.from_numpy(warm), model_denoise=mo, **kw)
+    m = FFDNet(1, 1, 64, 15, 'R'); m.load_state_dict(sd, strict=True); m = m.eval().cuda()
+    got = twoStageAdmm_denoise_gray(meas, mask, 'ffdnet_gray', x0=torch.from_numpy(warm).cuda(), model_denoise=m,
+                                    logf=io.StringIO(), **kw)
+    tol = {"ref": 2e-4, "tc": 1e-3}[impl]
+    assert got[0].shape == (64, 64, 8) and got[5] is m
+    assert np.max(np.abs(got[0] - ref[0])) < tol and np.max(np.abs(got[1] - ref[1])) < tol
+    assert np.max(np.abs(np.array(got[4]) - np.array(ref[4]))) < 0.05 and abs(np.mean(got[2]) - np.mean(ref[2])) < 0.05
+    # the warm start itself (stage 1 on a gray cube = 4 interleaved sub-problems) is the reference's own function
+    w_gpu = admm_denoise_bayer_demosaic_pre(meas, mask, 1, 0.01, 'tv', [40], False, [0], X_orig=orig, show_iqa=False)[0]
+    assert np.max(np.abs(w_gpu - warm)) < 2e-5
