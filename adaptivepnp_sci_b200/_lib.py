@@ -67,6 +67,12 @@ PROTOTYPES = {
     "sci_fastdvd_output_grad": [_p, _p, _i, _i, _i, _i, _p],
     "sci_fastdvd_pack_input_grad": [_p, _p, _i, _i, _i, _i, _i, _p],
     "sci_fastdvd_noisy_input": [_p, _p, _p, _l, _p],
+    "sci_rgb_sum": [_p, _p, _i, _i, _i, _p],
+    "sci_ddnet_pack_input1": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "sci_ddnet_pack_input4": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "sci_ddnet_stage2_input": [_p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _p],
+    "sci_ddnet_upsample4": [_p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _p],
+    "sci_ddnet_output": [_p, _p, _p, _i, _p, _p, _i, _i, _i, _p],
     "sci_host_legacy_normal": [_p, _p, _p, _p, _d, _d, _p, _l, _i],
     "sci_meas_loss_fwd_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _l, _p],
     "sci_axpy": [_p, _f, _p, _p, _l, _p],

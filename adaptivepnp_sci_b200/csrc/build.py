@@ -26,6 +26,7 @@ SOURCES = [
     ("sci_conv_ref.cu", []),
     ("sci_conv_tc.cu", []),
     ("sci_train.cu", ["--fmad=false"]),
+    ("sci_ddnet.cu", ["--fmad=false"]),
     ("sci_host_rng.cu", ["-Xcompiler", "-ffp-contract=off"]),
 ]
 

@@ -12,9 +12,10 @@ __device__ __forceinline__ float rna_tf32(float v) {
     return __uint_as_float(r);
 }
 
-// column of the GEMM output that holds PyTorch output channel co
-__device__ __forceinline__ int out_column(int co, int Co, int ps) {
-    return ps ? (co & 3) * (Co >> 2) + (co >> 2) : co;
+// column of the GEMM output that holds PyTorch output channel co.  PixelShuffle layers: the four sub-pixel groups are
+// Co_pad/4 columns wide each (the up-sampled tensor's padded channel count), channel co -> group co&3, slot co>>2
+__device__ __forceinline__ int out_column(int co, int Co_pad, int ps) {
+    return ps ? (co & 3) * (Co_pad >> 2) + (co >> 2) : co;
 }
 
 __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restrict__ packed, int Co, int Ci, int groups,
@@ -28,9 +29,10 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restri
     else        { col = (int)(idx % Co_pad); ci = (int)((idx / Co_pad) % Ci_pad); tap = (int)(idx / ((long)Ci_pad * Co_pad)); }
     float v = 0.f;
     if (ci_dup > 0 && ci >= ci_dup && ci < ci_dup + Ci) ci -= ci_dup;     // remainder copy of the input: same weights
-    if (col < Co && ci < Ci) {
-        // invert the column permutation: which torch channel lives in this column?
-        const int co = ps ? (col % (Co >> 2)) * 4 + col / (Co >> 2) : col;
+    // invert the column permutation: which torch channel lives in this column?
+    const int q = Co_pad >> 2;
+    const int co = ps ? (col % q) * 4 + col / q : col;
+    if ((ps ? (col % q) < (Co >> 2) : col < Co) && ci < Ci) {
         const int cig = Ci / groups, cog = Co / groups, g = co / cog;
         if (ci / cig == g) {
             const int src_tap = tflip ? 8 - tap : tap;
@@ -56,7 +58,7 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ packed, float* __r
     if (idx >= total) return;
     const int tap = (int)(idx % 9), cil = (int)((idx / 9) % cig), co = (int)(idx / (9L * cig));
     const int ci = (co / cog) * cig + cil;
-    const int col = out_column(co, Co, ps);
+    const int col = out_column(co, Co_pad, ps);
     float g = packed[((long)tap * Co_pad + col) * Ci_pad + ci];
     if (ci_dup > 0) g += packed[((long)tap * Co_pad + col) * Ci_pad + ci + ci_dup];
     dw[idx] = g;
@@ -328,7 +330,7 @@ extern "C" int sci_conv_pack_weights(const float* w, float* packed, int Co, int 
                                      void* stream) {
     SCI_REQUIRE(w && packed && Co > 0 && Ci > 0 && groups > 0 && Co % groups == 0 && Ci % groups == 0, "pack_weights");
     SCI_REQUIRE(Co_pad >= Co && Ci_pad >= Ci && (!ps || Co % 4 == 0), "pack_weights: padding / pixel-shuffle");
-    SCI_REQUIRE(!ps || Co_pad == Co, "pack_weights: pixel-shuffle columns cannot be padded");
+    SCI_REQUIRE(!ps || Co_pad % 4 == 0, "pack_weights: pixel-shuffle needs Co_pad % 4 == 0");
     SCI_REQUIRE(ci_dup == 0 || (ci_dup >= Ci && ci_dup + Ci <= Ci_pad), "pack_weights: ci_dup block does not fit");
     SCI_REQUIRE(round_tf32 != 2 || !transpose_flip, "pack_weights: split form is for forward weights only");
     const long total = (long)9 * Co_pad * Ci_pad;

@@ -220,9 +220,8 @@ def twoStageAdmm_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, gamma=0.01,
     name = denoiser if denoiser == 'tv' else str(denoiser).lower()
     if name not in ('tv', 'ffdnet_color', 'fastdvd_color'):
         raise ValueError('Unsupported denoiser {}!'.format(denoiser))
-    if model_demosaic is not None or close_form_demosaic:
-        raise NotImplementedError("deep demosaicking (DDnet) and the closed-form demosaic branch are not built yet "
-                                  "(SURVEY §8(f) rows 1 and 3); pass model_demosaic=None")
+    if close_form_demosaic:
+        raise NotImplementedError("the closed-form demosaic branch is not built yet (SURVEY §8(f) row 3)")
     sigma, iter_max = _as_list(sigma, iter_max)
     pb = _Problem(y_bayer, Phi_bayer, x0_bayer, X_orig)
     dev = pb.y.device
@@ -248,7 +247,8 @@ def twoStageAdmm_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, gamma=0.01,
         ws = ops.TvWorkspace(H, W, B, dev)
         b_next = torch.empty_like(b)
     else:
-        from . import fastdvdnet_adapter, ffdnet_adapter
+        from . import ddnet_adapter, fastdvdnet_adapter, ffdnet_adapter
+        mosaic = torch.empty_like(x) if model_demosaic is not None else None
         w = torch.zeros((B, 3, H, W), dtype=torch.float32, device=dev)
         x_rgb = torch.empty_like(w)
         u = torch.empty_like(w)
@@ -280,7 +280,15 @@ def twoStageAdmm_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, gamma=0.01,
                     do_update = do_update and (update_i < update_times or update_times < 0)   # :247
                     update_i += int(do_update)
                 adapter = ffdnet_adapter if name == 'ffdnet_color' else fastdvdnet_adapter
-                if tile is None:
+                if model_demosaic is not None:
+                    # deep demosaicking: x_rgb = DDnet(merge(x + b/rho)) ; u = x_rgb - w/tau          (:192-198, :241-246)
+                    if tile is not None:
+                        raise NotImplementedError("tiled mode uses the Malvar demosaic (DDnet would need its own halo)")
+                    x_rgb = ddnet_adapter.demosaic_planar(ops.axpy(x, inv_rou, b, out=mosaic), model_demosaic)
+                    ops.axpy(x_rgb, -float(np.float32(1 / tau)), w, out=u)
+                    xhat = adapter.denoise_planar(u, pb, nsig, model_denoise, lr_, do_update, update_per_iter,
+                                                  grad_sync=grad_sync)
+                elif tile is None:
                     ops.malvar2004(x, b, inv_rou, w, 1 / tau, x_rgb, u)
                     xhat = adapter.denoise_planar(u, pb, nsig, model_denoise, lr_, do_update, update_per_iter,
                                                   grad_sync=grad_sync)

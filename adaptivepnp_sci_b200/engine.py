@@ -122,7 +122,9 @@ class ConvLayer:
         if dup_in:
             self.ci_half = self.Ci_pad
             self.Ci_pad *= 2
-        self.Co_pad = self.Co if ps else _pad(self.Co, 32)   # multiple of 32: it is the K extent of the data-gradient GEMM
+        # multiple of 32: it is the K extent of the data-gradient GEMM.  PixelShuffle layers: four sub-pixel groups of
+        # pad(Co/4, 32) columns each, so that the up-sampled tensor is itself 32-channel padded
+        self.Co_pad = 4 * _pad(self.Co // 4, 32) if ps else _pad(self.Co, 32)
         self.out_ch = self.Co_pad // 4 if ps else self.Co_pad       # channels of the stored output tensor
         dev = conv.weight.device
         self.wsplit = wsplit     # TF32 path: keep tf32(w) AND the remainder tf32(w - tf32(w)); both are multiplied
@@ -516,3 +518,99 @@ class FastDVDnetEngine(_EngineBase):
         self._block_forward("w1", self.t1, frames, sigma, t1, False)      # centres 1,2,3 are the window's triples
         self._block_forward("w2", self.t2, t1, sigma, out, False)         # block 2 reads temp1 results 1,2,3
         return out[2:3].clone()
+
+
+class DDnetEngine(_EngineBase):
+    """models/network_demosaicking.py:377-463 + the circular sequence driver packages/DDnet/DDnet_test.py:166-204 on the
+    native kernels (inference; the solvers never fine-tune the demosaicker, dvp:193,243 pass no ``args``).
+
+    The three temp1 triples / three temp11 triples of all B centre frames run as ONE batch of 3B images each, the two
+    temp2 evaluations as one batch of 2B.  Real channel widths 20/40/80/90 are zero-padded to 32/64/96/96."""
+
+    def __init__(self, module):
+        def body(block):
+            return [ConvLayer(c, None, relu=r, stride=st, ps=ps, first=(i == 0))
+                    for i, (c, r, st, ps) in enumerate(block.conv_specs())]
+        self.t1, self.t11, self.t2 = body(module.temp1), body(module.temp11), body(module.temp2)
+        self.fus = [ConvLayer(c, None, relu=r, stride=st, ps=ps, first=(i == 0))
+                    for i, (c, r, st, ps) in enumerate(module.temp11.fusion_specs())]
+        super().__init__(module, self.t1 + self.t11 + self.fus + self.t2)
+
+    def _body(self, L, a_in, N, H, W):
+        """The 16-conv U-shaped body shared by all DenBlock variants (:232-241): returns the last conv's output."""
+        dev = a_in.device
+        g = self.ws.get
+        h2, w2, h4, w4 = H // 2, W // 2, H // 4, W // 4
+
+        def run(i, x, n_h, n_w, name, residual=None, round_out=True):
+            Li = L[i]
+            ho, wo = (n_h // 2, n_w // 2) if Li.stride == 2 else ((n_h * 2, n_w * 2) if Li.ps else (n_h, n_w))
+            y = g("dd_" + name, (N, ho, wo, Li.out_ch), dev)
+            self.conv(Li, x, N, n_h, n_w, y, residual=residual, round_out=round_out)
+            return y
+        a0 = run(0, a_in, H, W, "a0")
+        x0 = run(1, a0, H, W, "x0")
+        d0a = run(2, x0, H, W, "d0a")
+        d0b = run(3, d0a, h2, w2, "d0b")
+        x1 = run(4, d0b, h2, w2, "x1")
+        d1a = run(5, x1, h2, w2, "d1a")
+        d1b = run(6, d1a, h4, w4, "d1b")
+        x2 = run(7, d1b, h4, w4, "x2")
+        u2a = run(8, x2, h4, w4, "u2a")
+        u2b = run(9, u2a, h4, w4, "u2b")
+        s1 = run(10, u2b, h4, w4, "s1", residual=x1)           # x1 + PixelShuffle(conv)
+        u1a = run(11, s1, h2, w2, "u1a")
+        u1b = run(12, u1a, h2, w2, "u1b")
+        s0 = run(13, u1b, h2, w2, "s0", residual=x0)
+        o0 = run(14, s0, H, W, "o0")
+        return run(15, o0, H, W, "xo", round_out=False)
+
+    def forward(self, mosaic):
+        """mosaic [B,H,W] planar (whole circular sequence) -> demosaicked [B,3,H,W]."""
+        B, H, W = mosaic.shape
+        if H % 8 or W % 8:
+            raise NotImplementedError("native DDnet engine needs H, W multiples of 8 (half-resolution path with two "
+                                      "stride-2 levels; the reference reflect-pads to 4, DDnet_test.py:180-187, and "
+                                      "would itself fail on sizes that are not multiples of 8)")
+        self.prepare(training=False)
+        dev = mosaic.device
+        m = self.module
+        a, a2, a3 = m.weight_tensor_in.data, m.weight_tensor_in2.data, m.weight_tensor_out.data
+        sp = int(self.tf32)
+        g = self.ws.get
+        t2in = g("dd_t2in", (2 * B, H, W, 32), dev)
+        res1, res2 = g("dd_res1", (B, 3, H, W), dev), g("dd_res2", (B, 3, H, W), dev)
+        # path 1: full-resolution single-channel triples
+        in1 = g("dd_in1", (3 * B, H, W, 32), dev)
+        call("sci_ddnet_pack_input1", ptr(mosaic), ptr(a), ptr(in1), B, H, W, 32, sp, stream())
+        xo1 = self._body(self.t1, in1, 3 * B, H, W)
+        call("sci_ddnet_stage2_input", ptr(mosaic), ptr(a), ptr(xo1), xo1.shape[-1], ptr(t2in), ptr(res1), B, H, W, 32, sp,
+             stream())
+        # path 2: half-resolution RGGB planes, residual, bilinear x2, fusion convs
+        in4 = g("dd_in4", (3 * B, H // 2, W // 2, 32), dev)
+        call("sci_ddnet_pack_input4", ptr(mosaic), ptr(a2), ptr(in4), B, H, W, 32, sp, stream())
+        xo4 = self._body(self.t11, in4, 3 * B, H // 2, W // 2)
+        up = g("dd_up", (3 * B, H, W, 32), dev)
+        call("sci_ddnet_upsample4", ptr(mosaic), ptr(a2), ptr(xo4), xo4.shape[-1], ptr(up), B, H, W, 32, sp, stream())
+        f0 = g("dd_f0", (3 * B, H, W, self.fus[0].out_ch), dev)
+        self.conv(self.fus[0], up, 3 * B, H, W, f0)
+        xf = g("dd_xf", (3 * B, H, W, self.fus[1].out_ch), dev)
+        self.conv(self.fus[1], f0, 3 * B, H, W, xf, round_out=False)
+        call("sci_ddnet_stage2_input", None, None, ptr(xf), xf.shape[-1], ptr(t2in[B:]), ptr(res2), B, H, W, 32, sp, stream())
+        # temp2 on both paths (one batch of 2B), then the learnable output mix
+        xo2 = self._body(self.t2, t2in, 2 * B, H, W)
+        out = g("dd_out", (B, 3, H, W), dev)
+        call("sci_ddnet_output", ptr(res1), ptr(res2), ptr(xo2), xo2.shape[-1], ptr(a3), ptr(out), B, H, W, stream())
+        self.n_launch += 6
+        return out
+
+    def forward_window(self, x):
+        """Reference call convention model(x[1,15,H,W]) for ONE 5-frame window (network_demosaicking.py:406-463);
+        API parity only — the solvers use forward().  With B = 5 the centre frame 2 reads the frames 0..4 in order."""
+        if x.shape[0] != 1 or x.shape[1] != 15:
+            raise _lib.SciError("expected x of shape [1,15,H,W]")
+        H, W = x.shape[2], x.shape[3]
+        rgb = x.view(5, 3, H, W).contiguous().float()
+        mosaic = self.ws.get("dd_win_mosaic", (5, H, W), rgb.device)
+        call("sci_rgb_sum", ptr(rgb), ptr(mosaic), H, W, 5, stream())
+        return self.forward(mosaic)[2:3].clone()

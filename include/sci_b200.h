@@ -251,6 +251,30 @@ int sci_fastdvd_output(const float* frames, const float* y, float* out, int B, i
 int sci_fastdvd_output_grad(const float* dout, float* dy, int B, int H, int W, int Cpad, void* stream);
 int sci_fastdvd_pack_input_grad(const float* din, float* dframes, int B, int H, int W, int Cpad, int accumulate,
                                 void* stream);
+/* ---- DDnet deep-demosaic boundary (models/network_demosaicking.py:377-463; packages/DDnet/DDnet_test.py:166-204) ----
+ * mosaic [B][H][W] planar (the sum over the three sparse colour planes DDnet takes, :411-416 — sci_rgb_sum).
+ * The triples of the circular 5-window are stacked as batch n = j*B + f (j = triple 0..2, f = centre frame); triple j,
+ * slot k reads frame (f-2+j+k) mod B scaled by the learnable scalar a[3j+k] (:398-399, :442-448).  Every packed tensor
+ * is NHWC with Cpad == 32; split_tf32 != 0 stores tf32(v) in channel k and the remainder in channel k+16.
+ *   pack_input1 : path 1 (temp1) input  [3B][H][W][32],   channels 0..2   = the three scaled mosaics
+ *   pack_input4 : path 2 (temp11) input [3B][H/2][W/2][32], channel 4k+ib = RGGB plane ib of slot k, scaled by a2[3j+k][ib]
+ *   stage2_input: xo [3B][H][W][xo_cpad] = last conv of a path; v[j][c] = in1 + xo (residual :242; in1 = mosaic*a[3j+1],
+ *                 or 0 when mosaic == NULL: path 2, whose residual was applied before the up-sampling);
+ *                 t2in[f][p][3j+c] = v[j][c] (temp2 input), res[f][c][p] = v[1][c] (temp2's own in1, full fp32)
+ *   upsample4   : y4 = in1 + xo4 at half resolution, nn.UpsamplingBilinear2d(x2, align_corners=True) (:371) ->
+ *                 [3B][H][W][32] input of the fusion convs
+ *   output      : out[f][c] = a3[0][c]*(res1 + xo2[f]) + a3[1][c]*(res2 + xo2[B+f])   (:452-462), xo2 [2B][H][W][xo_cpad] */
+int sci_rgb_sum(const float* rgb, float* mosaic, int H, int W, int B, void* stream);
+int sci_ddnet_pack_input1(const float* mosaic, const float* a, float* out, int B, int H, int W, int Cpad, int split_tf32,
+                          void* stream);
+int sci_ddnet_pack_input4(const float* mosaic, const float* a2, float* out, int B, int H, int W, int Cpad, int split_tf32,
+                          void* stream);
+int sci_ddnet_stage2_input(const float* mosaic, const float* a, const float* xo, int xo_cpad, float* t2in, float* res,
+                           int B, int H, int W, int Cpad, int split_tf32, void* stream);
+int sci_ddnet_upsample4(const float* mosaic, const float* a2, const float* xo4, int xo_cpad, float* out, int B, int H,
+                        int W, int Cpad, int split_tf32, void* stream);
+int sci_ddnet_output(const float* res1, const float* res2, const float* xo2, int xo_cpad, const float* a3, float* out,
+                     int B, int H, int W, void* stream);
 /* training input of the FastDVDnet fine-tune (test_fastdvdnet.py:359 with utils_image.py:183-192):
  * vplus = v + float32(float64(v) + noise), noise float64 from the host RNG. */
 int sci_fastdvd_noisy_input(const float* v, const double* noise, float* vplus, long n, void* stream);

@@ -4,6 +4,7 @@ Test infrastructure.  CPU restatements of
   * ``ffdnet_rgb_denoise_full_tensor``      packages/ffdnet/test_ffdnet_ipol.py:240-359
   * ``fastdvdnet_seqdenoise``               packages/fastdvdnet/fastdvdnet.py:82-146
   * ``fastdvdnet_denoiser_full_tensor_v2``  packages/fastdvdnet/test_fastdvdnet.py:325-500
+  * ``ddnet_seqdenoise`` / ``test_ddnet``   packages/DDnet/DDnet_test.py:166-321
 """
 import numpy as np
 import torch
@@ -152,3 +153,63 @@ def ffdnet_gray_denoise_full_tensor(x, y, Phi, sigma, model, lr_=1e-6, updata_=F
             return frames(model), model
     with torch.no_grad():
         return frames(model)
+
+
+# ---------------------------------------------------------------------------------------------------
+# DDnet deep demosaic plug-in (packages/DDnet/DDnet_test.py)
+# ---------------------------------------------------------------------------------------------------
+def ddnet_seqdenoise(seq, windsize, model):
+    """DDnet_test.py:166-204.  seq [N,C,H,W]: circular window of ``windsize`` frames around every frame, reflect
+    pad (right/bottom) to multiples of 4, ``model(window[1, windsize*C, H, W])``, un-pad."""
+    N, C, H, W = seq.shape
+    hw = (windsize - 1) // 2
+    wpad, hpad = (-W) % 4, (-H) % 4
+    out = torch.empty((N, C, H, W))
+    for f in range(N):
+        idx = (torch.arange(f, f + windsize) - hw) % N
+        win = F.pad(seq[idx].reshape(1, -1, H, W), (0, wpad, 0, hpad), mode='reflect')
+        out[f] = model(win)[:, :, :H, :W]
+    return out
+
+
+def sparse_rgb_sites(rgb):
+    """DDnet_test.py:208-216 ``gen_bayer_img``: [H,W,3,B] -> the RGGB sites only, as [B,3,H,W]."""
+    s = torch.zeros_like(rgb)
+    s[0::2, 0::2, 0, :] = rgb[0::2, 0::2, 0, :]
+    s[0::2, 1::2, 1, :] = rgb[0::2, 1::2, 1, :]
+    s[1::2, 0::2, 1, :] = rgb[1::2, 0::2, 1, :]
+    s[1::2, 1::2, 2, :] = rgb[1::2, 1::2, 2, :]
+    return s.permute(3, 2, 0, 1)
+
+
+def test_ddnet(vnoisy, yall, Phiall, model=None, useGPU=True, args=None, gray=False, losses=None):
+    """DDnet_test.py:218-321.  vnoisy [H,W,3,B] sparse RGB mosaic -> demosaicked [H,W,3,B].
+    ``args.dm_update`` switches on the self-supervised fine-tune (loss = MSE between the input mosaic and the
+    re-mosaicked output, a fresh Adam per step, :268-276); the solvers never pass ``args`` (dvp:193,243)."""
+    updata_ = False
+    if args is not None:
+        lr_, update_per_iter, updata_ = args.dm_lr, args.dm_update_per_iter, args.dm_update
+    if gray:
+        vnoisy = vnoisy.unsqueeze(3)
+    seq = vnoisy.permute(3, 2, 0, 1)
+    if updata_:
+        model.train()
+        for _ in range(update_per_iter):
+            outv = ddnet_seqdenoise(seq, NUM_IN_FR_EXT, model).permute(2, 3, 1, 0)
+            if gray:
+                outv = outv.squeeze(3)
+            loss = nn.MSELoss()(seq, sparse_rgb_sites(outv))
+            opt = torch.optim.Adam(model.parameters(), lr=lr_)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            if losses is not None:
+                losses.append(float(loss.detach()))
+    else:
+        model.eval()
+    with torch.no_grad():
+        outv = ddnet_seqdenoise(seq, NUM_IN_FR_EXT, model)
+    outv = outv.permute(2, 3, 1, 0)
+    if gray:
+        outv = outv.squeeze(3)
+    return (outv, model) if updata_ else outv

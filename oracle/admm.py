@@ -8,16 +8,17 @@ both names are bound to ``x0all`` until ``torch.clip`` / the TV result rebinds
 ``theta_all``, so in stage 2 the k=0 assignment ``theta_all[...,c] = ...``
 also overwrites ``xall`` and ``b`` receives ``theta_unclipped - theta_clipped``.
 Only the branches reachable from the three scripts are restated
-('tv', 'ffdnet_color', 'fastdvd_color', Malvar demosaic, model_demosaic=None).
+('tv', 'ffdnet_color', 'fastdvd_color'; Malvar demosaic or the DDnet deep demosaic ``model_demosaic``).
 """
 import numpy as np
 import torch
 
 from . import BAYER
-from .adapters import fastdvdnet_denoiser_full_tensor_v2, ffdnet_rgb_denoise_full_tensor
+from .adapters import fastdvdnet_denoiser_full_tensor_v2, ffdnet_rgb_denoise_full_tensor, test_ddnet
 from .demosaic import malvar2004_tensor
 from .iqa import compare_psnr, compare_ssim
-from .sci_ops import (bayer_merge, bayer_split_init, masks_CFA_Bayer_tensor, project_stage1, project_stage2)
+from .sci_ops import (bayer_merge, bayer_split_init, masks_CFA_Bayer_tensor, oneCh2ThreeCh, project_stage1,
+                      project_stage2)
 from .tv_chambolle import denoise_tv_chambolle
 
 
@@ -87,8 +88,8 @@ def twoStageAdmm_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, gamma=0.01, denois
                                args=None, trace=None):
     """Stage 2.  'tv' -> 4-tuple; deep denoisers -> (xbgr3_np[H,W,3,B], x_bayer_np, psnr_, ssim_,
     psnr_all, model_denoise, model_demosaic)."""
-    if model_demosaic is not None or close_form_demosaic:
-        raise NotImplementedError('oracle: DDnet / closed-form demosaic are SURVEY §8(f) "next" rows')
+    if close_form_demosaic:
+        raise NotImplementedError('oracle: closed-form demosaic is a SURVEY §8(f) "next" row')
     y_bayer = torch.from_numpy(np.ascontiguousarray(y_bayer))
     Phi_bayer = torch.from_numpy(np.ascontiguousarray(Phi_bayer))
     sigma, iter_max = _listify(sigma, iter_max)
@@ -116,7 +117,9 @@ def twoStageAdmm_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, gamma=0.01, denois
                 TV = False
                 x_rgb = torch.zeros([nrow, ncol, 3, nmask])
                 x_bayer = bayer_merge(xall + (1 / rou) * ball)                                   # :169-172
-                if demosaic_method == 'malvar2004':                                              # :185-191 (App. D.2)
+                if model_demosaic is not None:                                                   # :192-194, :241-243
+                    x_rgb = test_ddnet(oneCh2ThreeCh(x_bayer), yall, Phiall, model_demosaic)
+                elif demosaic_method == 'malvar2004':                                            # :185-191 (App. D.2)
                     for t in range(nmask):
                         x_rgb[:, :, :, t] = malvar2004_tensor(x_bayer[:, :, t], R_m, G_m, B_m)
                 x_rgb_w = x_rgb - (1 / tau) * w                                                  # :198

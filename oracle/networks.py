@@ -141,3 +141,98 @@ class Wrapped(nn.Module):
 
     def forward(self, *a):
         return self.module(*a)
+
+
+# ---------------------------------------------------------------------------------------------------
+# DDnet deep demosaicker (models/network_demosaicking.py).  No BatchNorm, no bias, base width 20.
+# ---------------------------------------------------------------------------------------------------
+def _seq_cv2(ci, co):            # network_demosaicking.py:34-46 (CvBlock): conv,ReLU,conv,ReLU
+    return nn.Sequential(_cv(ci, co), nn.ReLU(inplace=True), _cv(co, co), nn.ReLU(inplace=True))
+
+
+class _Blk(nn.Module):
+    """Thin holder so that parameters appear under ``<name>.convblock.<i>`` as in the reference."""
+
+    def __init__(self, seq):
+        super().__init__()
+        self.convblock = seq
+
+    def forward(self, x):
+        return self.convblock(x)
+
+
+def _dd_input(nfr, per_frame, co):   # :48-81 InputCvBlock / InputCvBlock_2
+    return _Blk(nn.Sequential(_cv(nfr * per_frame, nfr * 30, groups=nfr), nn.ReLU(inplace=True),
+                              _cv(nfr * 30, co), nn.ReLU(inplace=True)))
+
+
+def _dd_down(ci, co):                # :83-95
+    return _Blk(nn.Sequential(_cv(ci, co, stride=2), nn.ReLU(inplace=True), _Blk(_seq_cv2(co, co))))
+
+
+def _dd_up(ci, co):                  # :97-109
+    return _Blk(nn.Sequential(_Blk(_seq_cv2(ci, ci)), _cv(ci, co * 4), nn.PixelShuffle(2)))
+
+
+def _dd_out(ci, co):                 # :111-123
+    return _Blk(nn.Sequential(_cv(ci, ci), nn.ReLU(inplace=True), _cv(ci, co)))
+
+
+class DDDenBlock(nn.Module):
+    """network_demosaicking.py:184-246 (``DenBlock``) and :310-375 (``DenBlock4ChBayer``, ``bayer4=True``).
+    The noise-map input block ``inc`` exists (it is in the state_dict) but DDnet never uses it (:431-440)."""
+
+    def __init__(self, ch_each_frame=3, bayer4=False):
+        super().__init__()
+        c0, c1, c2 = 20, 40, 80                                        # base_layer = 20 (:22)
+        self.inc = _dd_input(3, 3 + 1, c0)
+        self.inc_1 = _dd_input(3, ch_each_frame, c0)
+        self.downc0 = _dd_down(c0, c1)
+        self.downc1 = _dd_down(c1, c2)
+        self.upc2 = _dd_up(c2, c1)
+        self.upc1 = _dd_up(c1, c0)
+        self.outc = _dd_out(c0, 4 if bayer4 else 3)
+        self.bayer4 = bayer4
+        if bayer4:
+            self.upscale = nn.UpsamplingBilinear2d(scale_factor=2)     # align_corners=True
+            self.fusion = _dd_out(4, 3)
+
+    def forward(self, in0, in1, in2):
+        x0 = self.inc_1(torch.cat((in0, in1, in2), dim=1))
+        x1 = self.downc0(x0)
+        x2 = self.downc1(x1)
+        x2 = self.upc2(x2)
+        x1 = self.upc1(x1 + x2)
+        x = self.outc(x0 + x1)
+        x = in1 + x                                                    # :242 (1-channel in1 broadcasts over 3)
+        if self.bayer4:
+            x = self.fusion(self.upscale(x))                           # :371-372
+        return x
+
+
+def _mosaic_to_4ch(m):
+    """[N,H,W] -> [N,4,h,w], channel order (0,0),(0,1),(1,0),(1,1) (utils_image.py:145-151 via :420-424)."""
+    return torch.stack((m[:, 0::2, 0::2], m[:, 0::2, 1::2], m[:, 1::2, 0::2], m[:, 1::2, 1::2]), dim=1)
+
+
+class DDnet(nn.Module):
+    """network_demosaicking.py:377-463.  Input [N, 5*3, H, W]: five sparse-RGB (one colour per site) frames."""
+
+    def __init__(self, num_input_frames=5):
+        super().__init__()
+        self.num_input_frames = num_input_frames
+        self.temp1 = DDDenBlock(ch_each_frame=1)
+        self.temp2 = DDDenBlock(ch_each_frame=3)
+        self.temp11 = DDDenBlock(ch_each_frame=4, bayer4=True)
+        self.weight_tensor_in = nn.Parameter(torch.ones((9, 1, 1, 1, 1)))
+        self.weight_tensor_in2 = nn.Parameter(torch.ones((9, 1, 4, 1, 1)))
+        self.weight_tensor_out = nn.Parameter(torch.ones((2, 1, 3, 1, 1)))
+
+    def forward(self, x, noise_map=None):
+        fr = [x[:, 3 * m:3 * m + 3].sum(dim=1) for m in range(self.num_input_frames)]       # :411-416, [N,H,W]
+        f4 = [_mosaic_to_4ch(f) for f in fr]
+        f1 = [f.unsqueeze(1) for f in fr]
+        a, a2, a3 = self.weight_tensor_in, self.weight_tensor_in2, self.weight_tensor_out
+        y1 = [self.temp1(f1[j] * a[3 * j], f1[j + 1] * a[3 * j + 1], f1[j + 2] * a[3 * j + 2]) for j in range(3)]
+        y2 = [self.temp11(f4[j] * a2[3 * j], f4[j + 1] * a2[3 * j + 1], f4[j + 2] * a2[3 * j + 2]) for j in range(3)]
+        return a3[0] * self.temp2(*y1) + a3[1] * self.temp2(*y2)                              # :452-462

@@ -45,7 +45,7 @@ def _install_shims():
             _stub(name)
     if "matplotlib" not in sys.modules:
         mpl = _stub("matplotlib")
-        mpl.pyplot = _stub("matplotlib.pyplot")
+        mpl.pyplot = _stub("matplotlib.pyplot", xlim=None)
     if "tensorboardX" not in sys.modules:
         _stub("tensorboardX", SummaryWriter=object)
     if "colour" not in sys.modules:
@@ -96,6 +96,8 @@ def load():
     ns.fastdvd_adapter = importlib.import_module("packages.fastdvdnet.test_fastdvdnet")
     ns.fastdvd_driver = importlib.import_module("packages.fastdvdnet.fastdvdnet")
     ns.ffdnet_adapter = importlib.import_module("packages.ffdnet.test_ffdnet_ipol")
+    ns.network_demosaicking = importlib.import_module("models.network_demosaicking")
+    ns.ddnet_adapter = importlib.import_module("packages.DDnet.DDnet_test")
     import torch
     torch.autograd.set_detect_anomaly(False)   # test_ffdnet_ipol.py:26 turns it on globally (perf only)
     _loaded["ns"] = ns

@@ -156,6 +156,92 @@ def _orc_fastdvd():
     return m.eval()
 
 
+def _ddnet_sd():
+    return {"module." + k: v for k, v in synthetic.ddnet_synthetic_state_dict().items()}
+
+
+def _ref_ddnet(ns):
+    m = torch.nn.DataParallel(ns.network_demosaicking.DDnet())
+    m.load_state_dict(_ddnet_sd(), strict=True)
+    return m.eval()
+
+
+def _orc_ddnet():
+    m = networks.Wrapped(networks.DDnet())
+    m.load_state_dict(_ddnet_sd(), strict=True)
+    return m.eval()
+
+
+class _DmArgs:
+    dm_lr, dm_update_per_iter, dm_update = 1e-5, 2, True
+
+
+def ddnet_(ns):
+    """DDnet deep demosaic: network forward, the plug-in (inference and self-supervised update), and a stage-2 loop
+    with ``model_demosaic`` (the scripts' default ``deep_demosaicking=True`` path)."""
+    print("DDnet")
+    g = torch.Generator().manual_seed(31)
+    out = {}
+    x = torch.rand(2, 15, 16, 24, generator=g)
+    with torch.no_grad():
+        r = _ref_ddnet(ns)(x)
+        _eq(r, _orc_ddnet().module(x), "DDnet forward")
+    out.update(net_x=x.numpy(), net_y=r.numpy())
+    H, W, B = 32, 48, 8
+    meas, mask, orig = synthetic.make_case(H, W, B, 92, bayer=True)
+    yall, Phiall, _, _ = sci_ops.bayer_split_init(torch.from_numpy(meas), torch.from_numpy(mask), None)
+    mosaic = torch.from_numpy(orig) + 0.05 * torch.randn(H, W, B, generator=g)
+    v = sci_ops.oneCh2ThreeCh(mosaic)
+    r = ns.ddnet_adapter.test_ddnet(v, yall, Phiall, _ref_ddnet(ns))
+    _eq(r, adapters.test_ddnet(v, yall, Phiall, _orc_ddnet()), "test_ddnet inference")
+    out.update(ad_mosaic=mosaic.numpy(), ad_inf=r.numpy())
+    v_odd = v[:30, :46]                                    # reflect-pad-to-4 path (DDnet_test.py:180-187)
+    r = ns.ddnet_adapter.test_ddnet(v_odd, None, None, _ref_ddnet(ns))
+    _eq(r, adapters.test_ddnet(v_odd, None, None, _orc_ddnet()), "test_ddnet inference (30x46: reflect pad)")
+    out.update(ad_inf_odd=r.numpy())
+    rm, om = _ref_ddnet(ns), _orc_ddnet()
+    r, rm = ns.ddnet_adapter.test_ddnet(v, yall, Phiall, rm, True, _DmArgs)
+    losses = []
+    o, om = adapters.test_ddnet(v, yall, Phiall, om, True, _DmArgs, losses=losses)
+    _eq(r, o, "test_ddnet update output")
+    _eq(torch.cat([a.flatten() for a in rm.state_dict().values()]),
+        torch.cat([c.flatten() for c in om.state_dict().values()]), "ddnet fine-tuned weights (all keys)")
+    out.update(ad_upd=r.numpy(), ad_losses=np.array(losses),
+               ad_w_first_after=rm.state_dict()["module.temp1.inc_1.convblock.0.weight"].numpy(),
+               ad_mix_after=rm.state_dict()["module.weight_tensor_in2"].numpy())
+    # stage 2 with the deep demosaicker, 64x64x8 (same case / warm start as loops())
+    meas, mask, orig = synthetic.make_case(64, 64, 8, 3000, bayer=True)
+    warm = np.load(os.path.join(HERE, "loops.npz"))["s2_warm"]
+    kw = dict(show_iqa=True, demosaic_method='malvar2004', lr_=2e-6, interval_iter=3, update_=True, update_per_iter=2)
+    ns.utilspy.worker_init_fn(0)
+    r = ns.dvp.twoStageAdmm_denoise_bayer(meas, mask, 1, 0.01, 'ffdnet_color', [4, 3], False, [25 / 255, 12 / 255],
+                                          x0_bayer=torch.from_numpy(warm), X_orig=orig, model_denoise=_ref_ffdnet(ns),
+                                          model_demosaic=_ref_ddnet(ns), logf=io.StringIO(), **kw)
+    ns.utilspy.worker_init_fn(0)
+    o = admm.twoStageAdmm_denoise_bayer(meas, mask, 1, 0.01, 'ffdnet_color', [4, 3], False, [25 / 255, 12 / 255],
+                                        x0_bayer=torch.from_numpy(warm), X_orig=orig, model_denoise=_orc_ffdnet(),
+                                        model_demosaic=_orc_ddnet(), **kw)
+    _eq(r[0], o[0], "stage2 ffdnet+ddnet xbgr3")
+    _eq(r[1], o[1], "stage2 ffdnet+ddnet x_bayer")
+    _eq(np.array(r[4]), np.array(o[4]), "stage2 ffdnet+ddnet psnr_all")
+    print("   psnr_all:", np.round(np.array(r[4]), 2))
+    out.update(s2_rgb=r[0], s2_x=r[1], s2_psnr_all=np.array(r[4]), s2_psnr=np.array(r[2]), s2_ssim=np.array(r[3]))
+    kw = dict(kw, update_times=-1)
+    ns.utilspy.worker_init_fn(0)
+    r = ns.dvp.twoStageAdmm_denoise_bayer(meas, mask, 1, 0.01, 'fastdvd_color', [5, 2], False, [12 / 255, 6 / 255],
+                                          x0_bayer=torch.from_numpy(warm), X_orig=orig, model_denoise=_ref_fastdvd(ns),
+                                          model_demosaic=_ref_ddnet(ns), logf=io.StringIO(), **kw)
+    ns.utilspy.worker_init_fn(0)
+    o = admm.twoStageAdmm_denoise_bayer(meas, mask, 1, 0.01, 'fastdvd_color', [5, 2], False, [12 / 255, 6 / 255],
+                                        x0_bayer=torch.from_numpy(warm), X_orig=orig, model_denoise=_orc_fastdvd(),
+                                        model_demosaic=_orc_ddnet(), **kw)
+    _eq(r[0], o[0], "stage2 fastdvd+ddnet xbgr3")
+    _eq(r[1], o[1], "stage2 fastdvd+ddnet x_bayer")
+    print("   psnr_all:", np.round(np.array(r[4]), 2))
+    out.update(s2f_rgb=r[0], s2f_x=r[1], s2f_psnr_all=np.array(r[4]))
+    np.savez_compressed(os.path.join(HERE, "ddnet.npz"), **out)
+
+
 def nets(ns):
     print("networks")
     g = torch.Generator().manual_seed(11)
@@ -289,6 +375,10 @@ def loops(ns):
     np.savez_compressed(os.path.join(HERE, "loops.npz"), **out)
 
 
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "ddnet":
+    ddnet_(ref_harness.load())        # regenerate only tests/golden/ddnet.npz (needs loops.npz)
+    sys.exit(0)
+
 if __name__ == "__main__":
     if not ref_harness.available():
         sys.exit("reference tree not present: golden vectors can only be regenerated in the build container")
@@ -298,4 +388,5 @@ if __name__ == "__main__":
     nets(ns)
     adapters_(ns)
     loops(ns)
+    ddnet_(ns)
     print("golden vectors written to", HERE)

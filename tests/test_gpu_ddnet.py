@@ -1,0 +1,87 @@
+"""GPU parity of the DDnet deep-demosaic path against golden vectors produced by the
+reference (tests/golden/ddnet.npz; weights = oracle.synthetic.ddnet_synthetic_state_dict, the trained file is absent)."""
+import io
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+
+from test_gpu_conv import _fastdvd, _ffdnet, impl  # noqa: E402,F401
+
+TOL = {"ref": 2e-5, "tc": 1e-3}      # fp32 FFMA kernels / TF32 tensor-core kernels (north_star: 1e-3 max-abs)
+
+
+def _ddnet(cuda):
+    from adaptivepnp_sci_b200.fastdvdnet_adapter import DataParallelLike
+    from adaptivepnp_sci_b200.network_demosaicking import DDnet
+    from oracle import synthetic
+    m = DataParallelLike(DDnet())
+    m.load_state_dict({"module." + k: v for k, v in synthetic.ddnet_synthetic_state_dict().items()}, strict=True)
+    return m.eval().cuda()
+
+
+def _psnr(a, b):
+    return 10 * np.log10(1.0 / np.mean((np.asarray(a, np.float64) - np.asarray(b, np.float64)) ** 2))
+
+
+def test_ddnet_state_dict_keys(cuda):
+    from adaptivepnp_sci_b200.network_demosaicking import DDnet
+    from oracle import networks
+    a, b = DDnet().state_dict(), networks.DDnet().state_dict()
+    assert list(a.keys()) == list(b.keys()) and all(a[k].shape == b[k].shape for k in a)
+
+
+def test_ddnet_window_forward(cuda, impl):
+    d = np.load(os.path.join(G, "ddnet.npz"))
+    m = _ddnet(cuda)
+    x = torch.from_numpy(d["net_x"]).cuda()
+    for n in range(x.shape[0]):
+        y = m(x[n:n + 1]).cpu().numpy()
+        assert y.shape == (1, 3, 16, 24)
+        assert np.max(np.abs(y - d["net_y"][n:n + 1])) < TOL[impl]
+
+
+def test_ddnet_adapter(cuda, impl):
+    from adaptivepnp_sci_b200.ddnet_adapter import test_ddnet as ddnet_plugin
+    from adaptivepnp_sci_b200.utils_image import oneCh2ThreeCh
+    d = np.load(os.path.join(G, "ddnet.npz"))
+    v = oneCh2ThreeCh(torch.from_numpy(d["ad_mosaic"]).cuda())
+    out = ddnet_plugin(v, None, None, _ddnet(cuda))
+    assert out.shape == (32, 48, 3, 8)
+    assert np.max(np.abs(out.cpu().numpy() - d["ad_inf"])) < TOL[impl]
+
+    class Args:
+        dm_lr, dm_update_per_iter, dm_update = 1e-5, 2, True
+    with pytest.raises(NotImplementedError):
+        ddnet_plugin(v, None, None, _ddnet(cuda), True, Args)
+
+
+def test_stage2_with_deep_demosaic(cuda, impl):
+    """The scripts' default path (deep_demosaicking=True): stage 2 with model_demosaic, both denoisers, online update."""
+    from adaptivepnp_sci_b200.dvp_linear_inv_2_stage_ADMM_tensor_online import np2tch_cuda, twoStageAdmm_denoise_bayer
+    from adaptivepnp_sci_b200.utilspy import worker_init_fn
+    from oracle import synthetic
+    d = np.load(os.path.join(G, "ddnet.npz"))
+    warm = np.load(os.path.join(G, "loops.npz"))["s2_warm"]
+    meas, mask, orig = synthetic.make_case(64, 64, 8, 3000, bayer=True)
+    kw = dict(show_iqa=True, demosaic_method='malvar2004', lr_=2e-6, interval_iter=3, update_=True, update_per_iter=2,
+              logf=io.StringIO())
+    dm = _ddnet(cuda)
+    r = twoStageAdmm_denoise_bayer(meas, mask, 1, 0.01, 'ffdnet_color', [4, 3], False, [25 / 255, 12 / 255],
+                                   x0_bayer=np2tch_cuda(warm), X_orig=orig, model_denoise=_ffdnet(cuda), model_demosaic=dm, **kw)
+    tol = {"ref": 2e-4, "tc": 1e-3}[impl]
+    assert r[6] is dm
+    assert np.max(np.abs(r[0] - d["s2_rgb"])) < tol and np.max(np.abs(r[1] - d["s2_x"])) < tol
+    assert abs(_psnr(r[1], orig) - _psnr(d["s2_x"], orig)) < 0.05
+    assert np.max(np.abs(np.array(r[4]) - d["s2_psnr_all"])) < 0.05
+    worker_init_fn(0)
+    r = twoStageAdmm_denoise_bayer(meas, mask, 1, 0.01, 'fastdvd_color', [5, 2], False, [12 / 255, 6 / 255],
+                                   x0_bayer=np2tch_cuda(warm), X_orig=orig, model_denoise=_fastdvd(cuda), model_demosaic=dm,
+                                   update_times=-1, **kw)
+    assert np.max(np.abs(r[0] - d["s2f_rgb"])) < tol and np.max(np.abs(r[1] - d["s2f_x"])) < tol
+    assert np.max(np.abs(np.array(r[4]) - d["s2f_psnr_all"])) < 0.05
