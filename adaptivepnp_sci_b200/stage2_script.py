@@ -1,7 +1,8 @@
 """Shared body of the two stage-2 entry points (two_stage_ADMM_Online_FFD_Warm.py / ..._FastDVD_Warm.py).
 
 Keeps the reference scripts' flow: per-video hyper-parameter tables (two_stage_ADMM_Online_FFD_Warm.py:68-151,
-two_stage_ADMM_Online_FastDVD_Warm.py:66-166, ``deep_demosaicking=False`` columns — DDnet is a §8(f) next row),
+two_stage_ADMM_Online_FastDVD_Warm.py:66-166; ``--deep-demosaicking`` selects the scripts' ``deep_demosaicking=True``
+columns and demosaics with DDnet, the default is the Malvar columns),
 warm start from results/savedmat/_Admm_tv_<name>8.mat, loop over measurement groups with ``reuse_model``
 carry-over, log lines and the result .mat.  With torchrun the groups are sharded over ranks; ``--share-weights``
 keeps one set of denoiser weights across ranks via the NCCL gradient all-reduce (BASELINE config 4)."""
@@ -31,6 +32,34 @@ FASTDVD_TABLE = {      # two_stage_ADMM_Online_FastDVD_Warm.py:61-166, deep_demo
 }
 
 
+# overrides when deep_demosaicking=True (same script lines): (sigma*255, iter_max, interval_iter)
+FFD_DEEP = {
+    'Beauty_bayer': ([25, 12, 6], [6, 6, 4], 6), 'Bosphorus_bayer': ([25, 12, 6], [4, 4, 2], 8),
+    'Jockey_bayer': ([12, 6], [16, 8], 16), 'Runner_bayer': ([25, 12, 6], [8, 8, 4], 10),
+    'ShakeNDry_bayer': ([25, 12, 6], [8, 8, 4], 10), 'Traffic_bayer': ([25, 12], [14, 7], 14),
+}
+FASTDVD_DEEP = {
+    'Beauty_bayer': ([12, 6], [21, 2], 22), 'Bosphorus_bayer': ([8, 6], [24, 12], 25), 'Jockey_bayer': ([12, 6], [24, 6], 25),
+    'Runner_bayer': ([12, 6], [40, 15], 41), 'ShakeNDry_bayer': ([12, 6], [14, 4], 15), 'Traffic_bayer': ([25, 12, 6], [36, 6, 2], 43),
+}
+
+
+def build_demosaicker():
+    """two_stage_ADMM_Online_FFD_Warm.py:227-233: DataParallel(DDnet) + model_zoo/ddnet1.pth['state_dict']."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    from .fastdvdnet_adapter import DataParallelLike
+    from .network_demosaicking import DDnet
+    from .synthetic import ddnet_synthetic_state_dict
+    m = DataParallelLike(DDnet())
+    path = os.path.join(root, 'model_zoo', 'ddnet1.pth')
+    if os.path.exists(path):
+        m.load_state_dict(torch.load(path)['state_dict'], strict=True)
+    else:
+        print('DDnet weights %s absent (as in the reference tree): using the synthetic init' % path)
+        m.load_state_dict({'module.' + k: v for k, v in ddnet_synthetic_state_dict().items()}, strict=True)
+    return m.eval().cuda()
+
+
 def build_model(denoiser):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     if denoiser == 'ffdnet_color':
@@ -58,6 +87,7 @@ def main(denoiser):
     ap.add_argument("--videos", type=int, default=6)
     ap.add_argument("--nmea", type=int, default=4)
     ap.add_argument("--no-update", action="store_true", help="plain PnP (update=False)")
+    ap.add_argument("--deep-demosaicking", action="store_true", help="demosaic with DDnet (the reference scripts' default)")
     ap.add_argument("--share-weights", action="store_true", help="multi-GPU: one weight set, NCCL gradient all-reduce")
     args = ap.parse_args()
     ctx = parallel.init()
@@ -72,6 +102,8 @@ def main(denoiser):
     average_psnr, average_ssim = [], []
     for datname in matio.VIDEOS[:args.videos]:
         sig255, iter_max, lr, update_per_iter, interval_iter, update_times = table[datname]
+        if args.deep_demosaicking:
+            sig255, iter_max, interval_iter = (FFD_DEEP if denoiser == 'ffdnet_color' else FASTDVD_DEEP)[datname]
         sigma = [s / 255 for s in sig255]
         f.write(datname + ':\n')
         meas_bayer, mask_bayer, orig_bayer = matio.load_video(args.datasetdir, datname, args.nmea,
@@ -80,6 +112,7 @@ def main(denoiser):
         nrows, ncols, nmea = meas_bayer.shape
         nmask = mask_bayer.shape[2]
         model_denoise = build_model(denoiser)
+        model_demosaic = build_demosaicker() if args.deep_demosaicking else None
         MAXB = 255.
         results = {}
         for iframe in ctx.my_units(nmea):
@@ -90,7 +123,7 @@ def main(denoiser):
             begin = time.time()
             kw = dict(update_times=update_times) if denoiser == 'fastdvd_color' else {}
             out = reconstruct(meas_t, mask_bayer, 1, 0.01, denoiser, iter_max, False, sigma, x0_bayer=np2tch_cuda(v_tv),
-                              X_orig=orig_t, model_denoise=model_denoise, model_demosaic=None, show_iqa=True,
+                              X_orig=orig_t, model_denoise=model_denoise, model_demosaic=model_demosaic, show_iqa=True,
                               demosaic_method='malvar2004', lr_=lr, interval_iter=interval_iter, logf=f, update_=update,
                               update_per_iter=update_per_iter,
                               grad_sync=ctx.grad_sync if (args.share_weights and ctx.world > 1) else None, **kw)

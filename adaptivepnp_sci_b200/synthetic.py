@@ -79,3 +79,45 @@ def fastdvdnet_synthetic_state_dict(seed=4242, out_gain=0.005):
         conv(blk + ".outc.convblock.0", 32, 32); bn(blk + ".outc.convblock.1", 32)
         conv(blk + ".outc.convblock.3", 3, 32, gain=out_gain)
     return sd
+
+
+def ddnet_synthetic_state_dict(seed=777, out_gain=0.002):
+    """Random init for DDnet (the trained ``model_zoo/ddnet1.pth`` is absent, .MISSING_LARGE_BLOBS).
+    Kaiming-normal convs (models/network_demosaicking.py:402-405), the last conv of every DenBlock and of the
+    ``fusion`` block scaled by ``out_gain`` so the residual form ``in1 + net(.)`` (:242) stays bounded, the mixing
+    scalars perturbed off 1 so that every one of them matters, and the output mix set to about (1, 0.1): the result
+    is roughly the mosaic broadcast to three channels plus a small learned-looking correction (bounded ADMM loop).
+    Key order/names are those of ``DDnet().state_dict()``."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def conv(name, co, ci_per_group, gain=1.0):
+        std = float(np.sqrt(2.0 / (ci_per_group * 9)))
+        sd[name + ".weight"] = torch.randn(co, ci_per_group, 3, 3, generator=g) * (std * gain)
+
+    def cv2(prefix, ci, co):
+        conv(prefix + ".convblock.0", co, ci)
+        conv(prefix + ".convblock.2", co, co)
+
+    sd["weight_tensor_in"] = 1.0 + 0.1 * torch.randn(9, 1, 1, 1, 1, generator=g)
+    sd["weight_tensor_in2"] = 1.0 + 0.1 * torch.randn(9, 1, 4, 1, 1, generator=g)
+    sd["weight_tensor_in"][4] = 1.0         # gain of the residual path mosaic -> output: exactly 1 keeps the ADMM loop bounded
+    sd["weight_tensor_out"] = (torch.tensor([1.0, 0.1]).view(2, 1, 1, 1, 1)
+                               * (1.0 + torch.tensor([0.01, 0.05]).view(2, 1, 1, 1, 1) * torch.randn(2, 1, 3, 1, 1, generator=g)))
+    for blk, per_frame, co_out in (("temp1", 1, 3), ("temp2", 3, 3), ("temp11", 4, 4)):
+        conv(blk + ".inc.convblock.0", 90, 4)
+        conv(blk + ".inc.convblock.2", 20, 90)
+        conv(blk + ".inc_1.convblock.0", 90, per_frame)
+        conv(blk + ".inc_1.convblock.2", 20, 90)
+        for name, ci, co in (("downc0", 20, 40), ("downc1", 40, 80)):
+            conv(f"{blk}.{name}.convblock.0", co, ci)
+            cv2(f"{blk}.{name}.convblock.2", co, co)
+        for name, ci, co in (("upc2", 80, 40), ("upc1", 40, 20)):
+            cv2(f"{blk}.{name}.convblock.0", ci, ci)
+            conv(f"{blk}.{name}.convblock.1", co * 4, ci)
+        conv(blk + ".outc.convblock.0", 20, 20)
+        conv(blk + ".outc.convblock.2", co_out, 20, gain=out_gain)
+        if blk == "temp11":
+            conv(blk + ".fusion.convblock.0", 4, 4)
+            conv(blk + ".fusion.convblock.2", 3, 4, gain=0.1)
+    return sd

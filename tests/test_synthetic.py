@@ -23,3 +23,13 @@ def test_fastdvdnet_init_identical_and_loadable():
     for k in a:
         assert torch.equal(a[k], b[k])
     networks.FastDVDnet().load_state_dict(a, strict=True)
+
+
+def test_ddnet_init_identical_and_loadable():
+    from adaptivepnp_sci_b200 import synthetic as p
+    from oracle import networks, synthetic as o
+    a, b = p.ddnet_synthetic_state_dict(), o.ddnet_synthetic_state_dict()
+    assert sorted(a) == sorted(b)
+    for k in a:
+        assert torch.equal(a[k], b[k])
+    networks.DDnet().load_state_dict(a, strict=True)
