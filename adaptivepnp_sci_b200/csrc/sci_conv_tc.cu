@@ -317,6 +317,9 @@ struct Fwd2Params {
     const float* scale; const float* shift; const float* residual; float* y;
     int N, H, W, Cin, Cout, relu, ps, round_tf32;
     int tiles_w, num_tiles, k_chunks, stages, acc_stride, tmem_cols, resident, desc_mode, tma_store, out_bufs;
+    const float* planar_in1; float* planar_out;   // fused network output: out[n][c][h][w] = in1[n][c][h][w] - conv[c], c < 3
+    int R, tiles_h;   // rows per super-tile (R output rows share their R+2 input rows), super-tiles per image column strip
+    int dbg;   // SCI_CONV_DBG timing experiments (results invalid): 1 = no MMAs, 2 = no activation loads, 4 = no stores
 };
 
 __device__ __forceinline__ uint64_t umma_desc_off(uint32_t saddr, int mode) {
@@ -382,17 +385,20 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         int stage = 0; uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-            const int wt = tile % p.tiles_w, h = (tile / p.tiles_w) % p.H, n = tile / (p.tiles_w * p.H);
-            for (int r = 0; r < 3; ++r) {
+            const int wt = tile % p.tiles_w, hg = (tile / p.tiles_w) % p.tiles_h, n = tile / (p.tiles_w * p.tiles_h);
+            const int y0 = hg * p.R, rows = min(p.R, p.H - y0);
+            // input rows y0-1 .. y0+rows: row j feeds output row t = j - r as filter row r (R = 1: j is the filter row)
+            for (int j = 0; j < rows + 2; ++j) {
                 for (int kc = 0; kc < p.k_chunks; ++kc) {
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
                     if (elect_one()) {
-                        mbar_arrive_expect_tx(&full_bar[stage], ROW_BYTES + (p.resident ? 0u : 3u * b_bytes));
+                        const bool skip_a = (p.dbg & 2) != 0;
+                        mbar_arrive_expect_tx(&full_bar[stage], (skip_a ? 0u : ROW_BYTES) + (p.resident ? 0u : 3u * b_bytes));
                         const uint32_t a_dst = ring_base + (uint32_t)stage * stage_bytes;
-                        tma_load_4d(a_dst, &tmA, &full_bar[stage], kc * KCH, wt * 128 - 1, h + r - 1, n);
-                        if (!p.resident) {
+                        if (!skip_a) tma_load_4d(a_dst, &tmA, &full_bar[stage], kc * KCH, wt * 128 - 1, y0 + j - 1, n);
+                        if (!p.resident) {       // streamed weights: R == 1, j is the filter row
                             for (int s = 0; s < 3; ++s)
-                                tma_load_3d(a_dst + A2_STAGE + (uint32_t)s * b_bytes, &tmB, &full_bar[stage], kc * KCH, 0, r * 3 + s);
+                                tma_load_3d(a_dst + A2_STAGE + (uint32_t)s * b_bytes, &tmB, &full_bar[stage], kc * KCH, 0, j * 3 + s);
                         }
                     }
                     __syncwarp();
@@ -409,21 +415,51 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
-            for (int r = 0; r < 3; ++r) {
+            const int hg = (tile / p.tiles_w) % p.tiles_h;
+            const int rows = min(p.R, p.H - hg * p.R);
+            const uint32_t d_base = tmem_base + (uint32_t)(acc * p.R * p.acc_stride);
+            if (p.R == 1) {
+                // one output row per tile: straight-line issue (the issuing thread is the critical path of the wide layers)
+                for (int r = 0; r < 3; ++r) {
+                    for (int kc = 0; kc < p.k_chunks; ++kc) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a_addr = ring_base + (uint32_t)stage * stage_bytes;
+                        const uint32_t b_base = p.resident ? smem_base + (uint32_t)(r * 3 * p.k_chunks + kc) * b_bytes : a_addr + A2_STAGE;
+                        const uint32_t b_step = p.resident ? (uint32_t)p.k_chunks * b_bytes : b_bytes;
+#pragma unroll
+                        for (int s = 0; s < 3; ++s) {
+#pragma unroll
+                            for (int k = 0; k < KCH / 8; ++k) {
+                                const uint64_t ad = desc_hi | (uint64_t)(((a_addr + s * 128 + k * 32) & 0x3FFFFu) >> 4);
+                                const uint64_t bd = desc_hi | (uint64_t)(((b_base + s * b_step + k * 32) & 0x3FFFFu) >> 4);
+                                if (!(p.dbg & 1)) tc_mma_tf32_elect(d_base, ad, bd, idesc, (uint32_t)((r | kc | s | k) != 0));
+                            }
+                        }
+                        tc_commit_elect(&empty_bar[stage]);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            } else
+            for (int j = 0; j < rows + 2; ++j) {
                 for (int kc = 0; kc < p.k_chunks; ++kc) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t a_addr = ring_base + (uint32_t)stage * stage_bytes;
-                    const uint32_t b_base = p.resident ? smem_base + (uint32_t)(r * 3 * p.k_chunks + kc) * b_bytes : a_addr + A2_STAGE;
-                    const uint32_t b_step = p.resident ? (uint32_t)p.k_chunks * b_bytes : b_bytes;
+                    // the loaded input row is filter row r = j - t of every output row t of the super-tile it touches
+                    for (int t = max(0, j - 2); t <= min(rows - 1, j); ++t) {
+                        const int r = j - t;
+                        const uint32_t d_tmem = d_base + (uint32_t)(t * p.acc_stride);
+                        const uint32_t b_base = p.resident ? smem_base + (uint32_t)(r * 3 * p.k_chunks + kc) * b_bytes : a_addr + A2_STAGE;
+                        const uint32_t b_step = p.resident ? (uint32_t)p.k_chunks * b_bytes : b_bytes;
 #pragma unroll
-                    for (int s = 0; s < 3; ++s) {
+                        for (int s = 0; s < 3; ++s) {
 #pragma unroll
-                        for (int k = 0; k < KCH / 8; ++k) {
-                            const uint64_t ad = desc_hi | (uint64_t)(((a_addr + s * 128 + k * 32) & 0x3FFFFu) >> 4);
-                            const uint64_t bd = desc_hi | (uint64_t)(((b_base + s * b_step + k * 32) & 0x3FFFFu) >> 4);
-                            tc_mma_tf32_elect(d_tmem, ad, bd, idesc, (uint32_t)((r | kc | s | k) != 0));
+                            for (int k = 0; k < KCH / 8; ++k) {
+                                const uint64_t ad = desc_hi | (uint64_t)(((a_addr + s * 128 + k * 32) & 0x3FFFFu) >> 4);
+                                const uint64_t bd = desc_hi | (uint64_t)(((b_base + s * b_step + k * 32) & 0x3FFFFu) >> 4);
+                                if (!(p.dbg & 1)) tc_mma_tf32_elect(d_tmem, ad, bd, idesc, (uint32_t)((r | kc | s | k) != 0));
+                            }
                         }
                     }
                     tc_commit_elect(&empty_bar[stage]);
@@ -441,11 +477,12 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         int acc = 0; uint32_t acc_phase = 0;
         uint32_t st_cnt = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-            const int wt = tile % p.tiles_w, ho = (tile / p.tiles_w) % p.H, n = tile / (p.tiles_w * p.H);
+            const int wt = tile % p.tiles_w, hg = (tile / p.tiles_w) % p.tiles_h, n = tile / (p.tiles_w * p.tiles_h);
+            const int y0 = hg * p.R, rows = min(p.R, p.H - y0);
             const int wo = wt * 128 + m;
             const bool valid = wo < p.W;
-            // element offset of this lane's 32-channel segment of chunk c0 in the output / residual tensor
-            auto out_offset = [&](int c0) -> long {
+            // element offset of this lane's 32-channel segment of chunk c0 of output row ho in the output / residual tensor
+            auto out_offset = [&](int ho, int c0) -> long {
                 if (p.ps) {
                     const int qq = c0 / Cq, cc = c0 % Cq;
                     return (((long)n * 2 * p.H + 2 * ho + (qq >> 1)) * 2 * p.W + 2 * wo + (qq & 1)) * Cq + cc;
@@ -457,21 +494,24 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 8; ++j) rr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.residual && valid) {
-                const float4* rp = reinterpret_cast<const float4*>(p.residual + out_offset(0));
+                const float4* rp = reinterpret_cast<const float4*>(p.residual + out_offset(y0, 0));
 #pragma unroll
                 for (int j = 0; j < 8; ++j) rr[j] = __ldg(rp + j);
             }
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + (uint32_t)(acc * p.acc_stride) + ((uint32_t)(q * 32) << 16);
+          for (int t = 0; t < rows; ++t) {
+            const int ho = y0 + t;
+            const uint32_t t_row = tmem_base + (uint32_t)((acc * p.R + t) * p.acc_stride) + ((uint32_t)(q * 32) << 16);
             for (int c0 = 0; c0 < p.Cout; c0 += 32) {
                 float v[32];
                 tmem_ld32(t_row + c0, v);
                 float4 rn[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) rn[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.residual && valid && c0 + 32 < p.Cout) {          // prefetch the next chunk's skip values
-                    const float4* rp = reinterpret_cast<const float4*>(p.residual + out_offset(c0 + 32));
+                if (p.residual && valid && (c0 + 32 < p.Cout || t + 1 < rows)) {   // prefetch the next chunk's skip values
+                    const bool same_row = c0 + 32 < p.Cout;
+                    const float4* rp = reinterpret_cast<const float4*>(p.residual + out_offset(same_row ? ho : ho + 1, same_row ? c0 + 32 : 0));
 #pragma unroll
                     for (int j = 0; j < 8; ++j) rn[j] = __ldg(rp + j);
                 }
@@ -487,7 +527,18 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         out[j + e] = p.round_tf32 ? rna_tf32(t) : t;
                     }
                 }
-                if (p.tma_store) {
+                if (p.dbg & 4) {
+                    if (out[0] == 123.456f) p.y[0] = out[1];          // keep the values alive, store nothing
+                } else if (p.planar_out) {
+                    // last conv of a FastDVDnet DenBlock: the 3 real channels leave as planar frames, residual form
+                    // in1 - net (models.py:196) applied here; lanes are consecutive pixels -> coalesced plane accesses
+                    if (valid && c0 == 0) {
+                        const long plane = (long)p.H * p.W;
+                        const long o = (long)n * 3 * plane + (long)ho * p.W + wo;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) p.planar_out[o + c * plane] = __ldg(p.planar_in1 + o + c * plane) - out[c];
+                    }
+                } else if (p.tma_store) {
                     // coalesced path: the warp's 32 pixels x 32 channels go through a 128B-swizzled 4 KB staging tile and
                     // leave as ONE TMA store (box {32 ch, 32 px}; PixelShuffle = element stride 2 on the pixel axis of a map
                     // over the up-sampled tensor); out-of-image pixels are clipped by TMA
@@ -513,7 +564,7 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
                     ++st_cnt;
                 } else if (valid) {
-                    float* yp = p.y + out_offset(c0);
+                    float* yp = p.y + out_offset(ho, c0);
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
                         *reinterpret_cast<float4*>(yp + j) = make_float4(out[j], out[j + 1], out[j + 2], out[j + 3]);
@@ -521,6 +572,7 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 8; ++j) rr[j] = rn[j];
             }
+          }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -646,6 +698,7 @@ int env_int(const char* name, int dflt) {
 }
 
 bool fwd2_eligible(const sci_conv_desc* d) {
+    if (d->planar_out) return true;                      // fused planar output exists in the v2 kernel only
     return d->stride == 1 && d->Cout % 32 == 0 && d->Cout <= 128 && !d->w_split && !d->emit_lo &&
            env_int("SCI_CONV_V2", 1) != 0;
 }
@@ -658,11 +711,13 @@ int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream) {
     p.scale = d->scale; p.shift = d->shift; p.residual = d->residual; p.y = d->y;
     p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;
     p.relu = d->relu; p.ps = d->pixel_shuffle; p.round_tf32 = d->round_tf32;
+    p.planar_in1 = d->planar_in1; p.planar_out = d->planar_out;
+    if (p.planar_out && (!p.planar_in1 || p.ps || p.Cout != 32 || d->residual))
+        return sci_fail(SCI_EINVAL, "conv tc v2: planar output needs planar_in1, Cout == 32, no pixel_shuffle / residual");
     p.tiles_w = (p.W + 127) / 128;
-    p.num_tiles = p.tiles_w * p.H * p.N;
     p.k_chunks = p.Cin / KCH;
     const int b_bytes = p.Cout * KCH * 4;
-    p.tma_store = env_int("SCI_CONV_TMA_STORE", 1) ? 1 : 0;
+    p.tma_store = (env_int("SCI_CONV_TMA_STORE", 1) && !p.planar_out) ? 1 : 0;
     const int w_bytes = 9 * p.k_chunks * b_bytes;
     // shared-memory plan: [resident weights] [pipeline stages] [store staging: 4 warps x out_bufs x 4 KB]
     const int total_budget = 214 * 1024;
@@ -682,8 +737,20 @@ int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream) {
     p.stages = min(MAX_STAGES, (budget - (p.resident ? w_bytes : 0)) / stage_bytes);
     if (p.stages < 2) return sci_fail(SCI_EUNSUPPORTED, "conv tc v2: pipeline does not fit");
     p.acc_stride = p.Cout;
-    p.tmem_cols = next_pow2_cols(2 * p.acc_stride);
+    // super-tiles of R output rows: the R+2 input rows are loaded once and feed up to three output rows each, which
+    // cuts the shared-memory fill traffic per output row from 3 rows to (R+2)/R.  Measured (tools/bench_conv.py): the
+    // resident-weight layers are bound by ring_bytes / load round-trip latency, i.e. by bytes per output tile.
+    // R accumulators x 2 buffers must fit the 512 TMEM columns; streamed weights keep R = 1 (their B tiles are per filter row).
+    p.R = 1;
+    if (p.resident) {
+        const int rmax = env_int("SCI_CONV_ROWS", 8);
+        while (p.R * 2 <= rmax && 2 * (p.R * 2) * p.acc_stride <= 512 && p.R * 2 <= p.H) p.R *= 2;
+    }
+    p.tiles_h = (p.H + p.R - 1) / p.R;
+    p.num_tiles = p.tiles_w * p.tiles_h * p.N;
+    p.tmem_cols = next_pow2_cols(2 * p.R * p.acc_stride);
     p.desc_mode = env_int("SCI_CONV_DESC_MODE", 0);
+    p.dbg = env_int("SCI_CONV_DBG", 0);
     CUtensorMap tmA, tmB;
     // activation map with a {32 ch, 130 px, 1 row, 1 image} box
     {
@@ -1103,7 +1170,8 @@ int conv_wgrad2_tc_launch(const sci_wgrad_desc* d, void* stream) {
 }
 
 int check_conv_desc(const sci_conv_desc* d) {
-    SCI_REQUIRE(d && d->x && d->w && d->y, "conv: null pointer");
+    SCI_REQUIRE(d && d->x && d->w && (d->y || d->planar_out), "conv: null pointer");
+    SCI_REQUIRE(!d->planar_out || (d->stride == 1 && !d->w_split && !d->emit_lo), "conv: planar output options");
     SCI_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "conv: shape");
     SCI_REQUIRE(d->Cin % 8 == 0 && d->Cout % 4 == 0, "conv: Cin % 8, Cout % 4");
     SCI_REQUIRE(d->stride == 1 || d->stride == 2, "conv: stride");
@@ -1119,7 +1187,7 @@ extern "C" int sci_conv3x3_fwd(const sci_conv_desc* d, int impl, void* stream) {
     int rc = check_conv_desc(d);
     if (rc) return rc;
     if (impl == SCI_CONV_REF) {
-        SCI_REQUIRE(!d->w_split && !d->emit_lo, "conv ref: w_split / emit_lo are tensor-core (TF32) options");
+        SCI_REQUIRE(!d->w_split && !d->emit_lo && !d->planar_out, "conv ref: w_split / emit_lo / planar_out are tensor-core options");
         return sci_conv3x3_ref_launch(d, stream);
     }
     if (impl == SCI_CONV_TC) return fwd2_eligible(d) ? conv_fwd2_tc_launch(d, stream) : conv_fwd_tc_launch(d, stream);

@@ -50,6 +50,33 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restri
     packed[idx] = v;
 }
 
+// Data gradient of a STRIDE-2 convolution as a sub-pixel convolution at the LOW resolution (no zero-dilated tensor):
+//   z[i,j] = sum_{kh,kw} w[kh,kw] x[2i+kh-1, 2j+kw-1]   =>   dx[2i'+a, 2j'+b] = sum over the taps whose parity matches:
+//   a = 0: kh = 1 (from dz[i']);   a = 1: kh = 2 (from dz[i']) and kh = 0 (from dz[i'+1]);   same for b / kw.
+// Written as a 3x3 correlation over dz with 4*Ci_pad output columns (sub-pixel q = a*2+b, column q*Ci_pad + ci) whose
+// result the conv kernels scatter with their PixelShuffle epilogue.  packed[tap][col][co], tap = (dh+1)*3 + (dw+1).
+__device__ __forceinline__ int s2t_src_tap(int par, int d) {      // kernel index feeding output parity `par` from offset d
+    if (par == 0) return d == 0 ? 1 : -1;
+    return d == 0 ? 2 : (d == 1 ? 0 : -1);
+}
+__global__ void pack_weights_s2t_kernel(const float* __restrict__ w, float* __restrict__ packed, int Co, int Ci, int Co_pad,
+                                        int Ci_pad, const float* __restrict__ oscale, int round_tf32) {
+    const long total = (long)9 * 4 * Ci_pad * Co_pad;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int co = (int)(idx % Co_pad);
+    const int col = (int)((idx / Co_pad) % (4 * Ci_pad));
+    const int tap = (int)(idx / ((long)Co_pad * 4 * Ci_pad));
+    const int q = col / Ci_pad, ci = col % Ci_pad;
+    const int kh = s2t_src_tap(q >> 1, tap / 3 - 1), kw = s2t_src_tap(q & 1, tap % 3 - 1);
+    float v = 0.f;
+    if (co < Co && ci < Ci && kh >= 0 && kw >= 0) {
+        v = w[((long)co * Ci + ci) * 9 + kh * 3 + kw];
+        if (oscale) v = v * oscale[co];
+    }
+    packed[idx] = round_tf32 ? rna_tf32(v) : v;
+}
+
 __global__ void unpack_wgrad_kernel(const float* __restrict__ packed, float* __restrict__ dw, int Co, int Ci, int groups,
                                     int Co_pad, int Ci_pad, int ps, int ci_dup) {
     const int cig = Ci / groups, cog = Co / groups;
@@ -337,6 +364,15 @@ extern "C" int sci_conv_pack_weights(const float* w, float* packed, int Co, int 
     pack_weights_kernel<<<grid1d(total), 256, 0, sci_stream(stream)>>>(w, packed, Co, Ci, groups, Co_pad, Ci_pad, ps, oscale,
                                                                        transpose_flip, round_tf32, ci_dup);
     SCI_CHECK_LAUNCH("pack_weights");
+    return SCI_OK;
+}
+
+extern "C" int sci_conv_pack_weights_s2t(const float* w, float* packed, int Co, int Ci, int Co_pad, int Ci_pad,
+                                         const float* oscale, int round_tf32, void* stream) {
+    SCI_REQUIRE(w && packed && Co > 0 && Ci > 0 && Co_pad >= Co && Ci_pad >= Ci, "pack_weights_s2t");
+    const long total = (long)9 * 4 * Ci_pad * Co_pad;
+    pack_weights_s2t_kernel<<<grid1d(total), 256, 0, sci_stream(stream)>>>(w, packed, Co, Ci, Co_pad, Ci_pad, oscale, round_tf32);
+    SCI_CHECK_LAUNCH("pack_weights_s2t");
     return SCI_OK;
 }
 

@@ -33,7 +33,8 @@ class ConvDesc(ctypes.Structure):
     _fields_ = [("x", _f32p), ("w", _f32p), ("scale", _f32p), ("shift", _f32p), ("residual", _f32p), ("y", _f32p),
                 ("N", ctypes.c_int), ("H", ctypes.c_int), ("W", ctypes.c_int), ("Cin", ctypes.c_int),
                 ("Cout", ctypes.c_int), ("stride", ctypes.c_int), ("relu", ctypes.c_int),
-                ("pixel_shuffle", ctypes.c_int), ("round_tf32", ctypes.c_int), ("w_split", ctypes.c_int), ("emit_lo", ctypes.c_int)]
+                ("pixel_shuffle", ctypes.c_int), ("round_tf32", ctypes.c_int), ("w_split", ctypes.c_int), ("emit_lo", ctypes.c_int),
+                ("planar_in1", _f32p), ("planar_out", _f32p)]
 
 
 class WgradDesc(ctypes.Structure):
@@ -155,6 +156,15 @@ class ConvLayer:
             self.wpk_t = torch.empty(9 * self.Co_pad * self.Ci_pad, dtype=torch.float32, device=self.wpk.device)
             self.s1 = torch.zeros(self.Co_pad, dtype=torch.float32, device=self.wpk.device)
             self.s2 = torch.zeros(self.Co_pad, dtype=torch.float32, device=self.wpk.device)
+        if self.stride == 2 and self.groups == 1 and not self.ps and self.ci_dup == 0:
+            # stride-2 layers: data gradient as a sub-pixel convolution over dz at the low resolution
+            if self.wpk_t.numel() != 36 * self.Co_pad * self.Ci_pad:
+                self.wpk_t = torch.empty(36 * self.Co_pad * self.Ci_pad, dtype=torch.float32, device=self.wpk.device)
+            call("sci_conv_pack_weights_s2t", ptr(self.conv.weight.data), ptr(self.wpk_t), self.Co, self.Ci, self.Co_pad,
+                 self.Ci_pad, ptr(self.scale), int(tf32), stream())
+            self.s2t = True
+            return
+        self.s2t = False
         call("sci_conv_pack_weights", ptr(self.conv.weight.data), ptr(self.wpk_t), self.Co, self.Ci, self.groups,
              self.Co_pad, self.Ci_pad, int(self.ps), ptr(self.scale), 1, int(tf32), self.ci_dup, stream())
 
@@ -223,10 +233,11 @@ class _EngineBase:
                 off += n
 
     # ---- kernel wrappers ------------------------------------------------------------------------------
-    def conv(self, L, x, N, H, W, y, residual=None, round_out=True, emit_lo=False):
+    def conv(self, L, x, N, H, W, y, residual=None, round_out=True, emit_lo=False, planar=None):
+        """planar = (in1, out) planar [N,3,H,W] tensors: tensor-core path only, fused `out = in1 - conv` (y unused)."""
         d = ConvDesc(_dp(x), _dp(L.wpk), _dp(L.scale), _dp(L.shift), _dp(residual), _dp(y), N, H, W, L.Ci_pad, L.Co_pad,
                      L.stride, int(L.relu), int(L.ps), int(self.tf32 and round_out), int(self.tf32 and L.wsplit),
-                     int(emit_lo))
+                     int(emit_lo), _dp(planar[0]) if planar else None, _dp(planar[1]) if planar else None)
         if self.profile is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
@@ -236,6 +247,13 @@ class _EngineBase:
             Ho, Wo = (H - 1) // L.stride + 1, (W - 1) // L.stride + 1
             self.profile.append((ev0, ev1, 2.0 * N * Ho * Wo * 9 * (L.Ci // L.groups) * L.Co,
                                  "fwd %dx%d %d->%d s%d" % (H, W, L.Ci, L.Co, L.stride)))
+        self.n_launch += 1
+
+    def dgrad_s2(self, L, dz, N, Ho, Wo, dx, residual=None):
+        """Stride-2 layer: dx[N,2Ho,2Wo,Ci_pad] = PixelShuffle(conv(dz[N,Ho,Wo,Co_pad], sub-pixel weights)) [+ residual]."""
+        d = ConvDesc(_dp(dz), _dp(L.wpk_t), None, None, _dp(residual), _dp(dx), N, Ho, Wo, L.Co_pad, 4 * L.Ci_pad, 1, 0, 1,
+                     int(self.tf32), 0, 0)
+        call("sci_conv3x3_dgrad", ctypes.byref(d), self.impl, stream())
         self.n_launch += 1
 
     def dgrad(self, L, dz, N, Ho, Wo, dx, residual=None):
@@ -414,8 +432,12 @@ class FastDVDnetEngine(_EngineBase):
         u1b = g(keep("u1b"), (B, h2, w2, 64), dev);        self.conv(L[12], u1a, B, h2, w2, u1b)
         s0 = g(keep("s0"), (B, H, W, 32), dev);            self.conv(L[13], u1b, B, h2, w2, s0, residual=x0)
         o0 = g(keep("o0"), (B, H, W, 32), dev);            self.conv(L[14], s0, B, H, W, o0)
-        xo = g(keep("xo"), (B, H, W, L[15].Co_pad), dev);  self.conv(L[15], o0, B, H, W, xo, round_out=False)
-        call("sci_fastdvd_output", ptr(frames), ptr(xo), ptr(out), B, H, W, L[15].Co_pad, stream())
+        if self.impl == IMPL_TC and L[15].Co_pad == 32:
+            xo = None                                       # fused epilogue: out = frames - conv, planar, no NHWC tensor
+            self.conv(L[15], o0, B, H, W, None, round_out=False, planar=(frames, out))
+        else:
+            xo = g(keep("xo"), (B, H, W, L[15].Co_pad), dev);  self.conv(L[15], o0, B, H, W, xo, round_out=False)
+            call("sci_fastdvd_output", ptr(frames), ptr(xo), ptr(out), B, H, W, L[15].Co_pad, stream())
         if train:
             return dict(a_in=a_in, a0=a0, x0=x0, d0a=d0a, d0b=d0b, x1=x1, d1a=d1a, d1b=d1b, x2=x2, u2a=u2a, u2b=u2b,
                         s1=s1, u1a=u1a, u1b=u1b, s0=s0, o0=o0, xo=xo)
@@ -454,7 +476,9 @@ class FastDVDnetEngine(_EngineBase):
             dx = None
             if want_dx:
                 dx = g(dx_name, dx_shape, dev)
-                if Li.stride == 2:
+                if Li.stride == 2 and getattr(Li, "s2t", False):
+                    self.dgrad_s2(Li, dz, N, Hin // 2, Win // 2, dx, residual)
+                elif Li.stride == 2:
                     dil = g("g_dil", (N, Hin, Win, Li.Co_pad), dev)
                     call("sci_nhwc_dilate2", ptr(dz), ptr(dil), N, Hin // 2, Win // 2, Li.Co_pad, stream())
                     self.dgrad(Li, dil, N, Hin, Win, dx, residual)

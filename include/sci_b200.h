@@ -177,6 +177,10 @@ typedef struct sci_conv_desc {
                                multiplied, which removes the weight-rounding error of the TF32 path */
     int emit_lo;            /* TC only. 1: y has 2*Cout channels per pixel: [tf32(v) | tf32(v - tf32(v))]; the next
                                layer is packed with ci_dup = Cout so it multiplies both ("3xTF32": ~fp32 accuracy) */
+    const float* planar_in1; /* TC only, with planar_out: [N][3][H][W] frames                                   */
+    float* planar_out;      /* TC only. non-NULL: the layer is the last conv of a FastDVDnet DenBlock (Cout == 32, 3 real
+                               channels): instead of y the kernel writes out[n][c][h][w] = planar_in1[n][c][h][w] - conv[c]
+                               (packages/fastdvdnet/models.py:196) as planar frames; y may be NULL */
 } sci_conv_desc;
 
 /* 1 if this build contains the tcgen05 tensor-core convolution kernels. */
@@ -207,6 +211,12 @@ int sci_conv3x3_wgrad(const sci_wgrad_desc* d, int impl, void* stream);
  * anyway); sci_conv_unpack_wgrad then sums the two gradient blocks. */
 int sci_conv_pack_weights(const float* w, float* packed, int Co, int Ci, int groups, int Co_pad, int Ci_pad,
                           int ps, const float* oscale, int transpose_flip, int round_tf32, int ci_dup, void* stream);
+/* Data-gradient weights of a STRIDE-2 layer (groups = 1) as a sub-pixel convolution over dz at the low resolution:
+ * packed [9][4*Ci_pad][Co_pad]; run sci_conv3x3_dgrad with x = dz [N][Ho][Wo][Co_pad], Cin = Co_pad, Cout = 4*Ci_pad,
+ * stride 1, pixel_shuffle = 1 -> dx [N][2Ho][2Wo][Ci_pad].  Replaces "zero-dilate dz, then convolve at full resolution"
+ * (4x less operand traffic, no dilated tensor).  oscale (may be NULL) scales by the folded BatchNorm scale of column co. */
+int sci_conv_pack_weights_s2t(const float* w, float* packed, int Co, int Ci, int Co_pad, int Ci_pad, const float* oscale,
+                              int round_tf32, void* stream);
 /* inverse of the forward packing for gradients: dw_torch[Co][Ci/groups][3][3] = packed_dw (assign) */
 int sci_conv_unpack_wgrad(const float* packed_dw, float* dw, int Co, int Ci, int groups, int Co_pad, int Ci_pad,
                           int ps, int ci_dup, void* stream);

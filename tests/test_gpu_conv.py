@@ -44,6 +44,7 @@ CASES = [
     (96, 12, 1, 1, False, False, False, True, False, 16, 24, 1),     # FFDNet tail
     (12, 90, 3, 1, False, True, True, False, False, 16, 16, 2),      # FastDVDnet grouped input conv
     (32, 64, 1, 2, False, True, True, False, False, 24, 32, 2),      # DownBlock stride 2
+    (64, 128, 1, 2, False, True, True, False, False, 16, 24, 2),     # DownBlock stride 2 (sub-pixel dgrad with 256 columns)
     (128, 256, 1, 1, True, False, False, False, True, 8, 12, 2),     # UpBlock conv + PixelShuffle + skip add
     (32, 3, 1, 1, False, False, False, False, False, 18, 20, 1),     # DenBlock output conv
 ]
@@ -124,9 +125,20 @@ def test_conv_layer_fwd_bwd(cuda, impl, case):
     eng.wgrad(L, xd, dz, N, H, W)
     dx = torch.empty(N, H, W, L.Ci_pad, device=cuda)
     if stride == 2:
+        assert L.s2t                                   # stride-2 layers: sub-pixel data gradient at the low resolution
+        eng.dgrad_s2(L, dz, N, Ho, Wo, dx)
+        # the older formulation (zero-dilated dz convolved at full resolution) must agree with it
+        wt = torch.empty(9 * L.Co_pad * L.Ci_pad, device=cuda)
+        call("sci_conv_pack_weights", ptr(cconv.weight.data), ptr(wt), L.Co, L.Ci, 1, L.Co_pad, L.Ci_pad, 0, ptr(L.scale), 1,
+             int(eng.tf32), 0, stream())
         dil = torch.empty(N, H, W, L.Co_pad, device=cuda)
         call("sci_nhwc_dilate2", ptr(dz), ptr(dil), N, Ho, Wo, L.Co_pad, stream())
-        eng.dgrad(L, dil, N, H, W, dx)
+        dx_old = torch.empty_like(dx)
+        d = engine.ConvDesc(dil.data_ptr(), wt.data_ptr(), None, None, None, dx_old.data_ptr(), N, H, W, L.Co_pad, L.Ci_pad, 1, 0,
+                            0, int(eng.tf32), 0, 0)
+        call("sci_conv3x3_dgrad", ctypes.byref(d), eng.impl, stream())
+        e_form = _rel(dx.cpu(), dx_old.cpu())
+        assert e_form < {"ref": 1e-5, "tc": 1e-3}[impl], "sub-pixel vs dilated dgrad (outputs are TF32-rounded): %g" % e_form
     else:
         eng.dgrad(L, dz, N, Ho, Wo, dx)
     eng.param_grads(L)
