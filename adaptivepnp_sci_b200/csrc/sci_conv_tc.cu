@@ -318,6 +318,7 @@ struct Fwd2Params {
     int N, H, W, Cin, Cout, relu, ps, round_tf32;
     int tiles_w, num_tiles, k_chunks, stages, acc_stride, tmem_cols, resident, desc_mode, tma_store, out_bufs;
     const float* planar_in1; float* planar_out;   // fused network output: out[n][c][h][w] = in1[n][c][h][w] - conv[c], c < 3
+    int stack;        // filter rows stacked along N (see the MMA issuer); needs resident weights, R >= 2, 3*Cout <= 256
     int R, tiles_h;   // rows per super-tile (R output rows share their R+2 input rows), super-tiles per image column strip
     int dbg;   // SCI_CONV_DBG timing experiments (results invalid): 1 = no MMAs, 2 = no activation loads, 4 = no stores
 };
@@ -378,8 +379,13 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (elect_one()) {
                 mbar_arrive_expect_tx(&w_bar, w_bytes);
                 for (int tap = 0; tap < 9; ++tap)
-                    for (int kc = 0; kc < p.k_chunks; ++kc)
-                        tma_load_3d(smem_base + (uint32_t)(tap * p.k_chunks + kc) * b_bytes, &tmB, &w_bar, kc * KCH, 0, tap);
+                    for (int kc = 0; kc < p.k_chunks; ++kc) {
+                        // default: tiles ordered [tap][kc]; stacked: [s][kc][r] so that the three filter rows of a
+                        // horizontal tap form ONE K-major B matrix of 3*Cout rows
+                        const uint32_t slot = p.stack ? (uint32_t)(((tap % 3) * p.k_chunks + kc) * 3 + tap / 3)
+                                                      : (uint32_t)(tap * p.k_chunks + kc);
+                        tma_load_3d(smem_base + slot * b_bytes, &tmB, &w_bar, kc * KCH, 0, tap);
+                    }
             }
             __syncwarp();
         }
@@ -434,6 +440,48 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                 const uint64_t ad = desc_hi | (uint64_t)(((a_addr + s * 128 + k * 32) & 0x3FFFFu) >> 4);
                                 const uint64_t bd = desc_hi | (uint64_t)(((b_base + s * b_step + k * 32) & 0x3FFFFu) >> 4);
                                 if (!(p.dbg & 1)) tc_mma_tf32_elect(d_base, ad, bd, idesc, (uint32_t)((r | kc | s | k) != 0));
+                            }
+                        }
+                        tc_commit_elect(&empty_bar[stage]);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            } else if (p.stack) {
+                // Filter rows stacked along N.  Input row j (relative to y0 - 1) is filter row r of output row t = j - r; the
+                // accumulators of the super-tile sit in REVERSE row order (row t at column (R-1-t)*Cout), so ONE MMA with
+                // B = [W(r_lo) | .. | W(r_hi)] (N = nr*Cout) adds the row's contribution to all output rows it touches.
+                // The A operand (128 px x 8 ch, the shared-memory-bandwidth cost of a TF32 MMA) is then read once per
+                // horizontal tap instead of once per (tap, filter row): ~1.5-1.8x fewer tensor-pipe cycles for Cout = 32/64.
+                for (int j = 0; j < rows + 2; ++j) {
+                    const int r_lo = max(0, j - (rows - 1)), r_hi = min(2, j);
+                    const int nr = r_hi - r_lo + 1;
+                    const uint32_t d_col = d_base + (uint32_t)((p.R - 1 - (j - r_lo)) * p.acc_stride);
+                    const uint32_t idesc_n = (idesc & ~(0x3Fu << 17)) | ((uint32_t)((nr * p.Cout) >> 3) << 17);
+                    const uint32_t idesc_1 = idesc;                                               // N = Cout
+                    const uint32_t idesc_m = (idesc & ~(0x3Fu << 17)) | ((uint32_t)(((nr - 1) * p.Cout) >> 3) << 17);
+                    for (int kc = 0; kc < p.k_chunks; ++kc) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a_addr = ring_base + (uint32_t)stage * stage_bytes;
+#pragma unroll
+                        for (int s = 0; s < 3; ++s) {
+                            const uint32_t b_tile = smem_base + (uint32_t)((s * p.k_chunks + kc) * 3) * b_bytes;
+#pragma unroll
+                            for (int k = 0; k < KCH / 8; ++k) {
+                                const uint64_t ad = desc_hi | (uint64_t)(((a_addr + s * 128 + k * 32) & 0x3FFFFu) >> 4);
+                                if (p.dbg & 1) continue;
+                                if (r_lo == 0 && (kc | s | k) == 0) {
+                                    // this row opens the accumulator of output row t = j (r = 0): that slice must overwrite
+                                    const uint64_t b0 = desc_hi | (uint64_t)(((b_tile + k * 32) & 0x3FFFFu) >> 4);
+                                    tc_mma_tf32_elect(d_col, ad, b0, idesc_1, 0u);
+                                    if (nr > 1) {
+                                        const uint64_t b1 = desc_hi | (uint64_t)(((b_tile + b_bytes + k * 32) & 0x3FFFFu) >> 4);
+                                        tc_mma_tf32_elect(d_col + (uint32_t)p.acc_stride, ad, b1, idesc_m, 1u);
+                                    }
+                                } else {
+                                    const uint64_t bd = desc_hi | (uint64_t)(((b_tile + (uint32_t)r_lo * b_bytes + k * 32) & 0x3FFFFu) >> 4);
+                                    tc_mma_tf32_elect(d_col, ad, bd, idesc_n, 1u);
+                                }
                             }
                         }
                         tc_commit_elect(&empty_bar[stage]);
@@ -502,7 +550,7 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tc_fence_after();
           for (int t = 0; t < rows; ++t) {
             const int ho = y0 + t;
-            const uint32_t t_row = tmem_base + (uint32_t)((acc * p.R + t) * p.acc_stride) + ((uint32_t)(q * 32) << 16);
+            const uint32_t t_row = tmem_base + (uint32_t)((acc * p.R + (p.stack ? p.R - 1 - t : t)) * p.acc_stride) + ((uint32_t)(q * 32) << 16);
             for (int c0 = 0; c0 < p.Cout; c0 += 32) {
                 float v[32];
                 tmem_ld32(t_row + c0, v);
@@ -746,6 +794,7 @@ int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream) {
         const int rmax = env_int("SCI_CONV_ROWS", 8);
         while (p.R * 2 <= rmax && 2 * (p.R * 2) * p.acc_stride <= 512 && p.R * 2 <= p.H) p.R *= 2;
     }
+    p.stack = (p.resident && p.R >= 2 && 3 * p.Cout <= 256 && env_int("SCI_CONV_STACK", 1)) ? 1 : 0;
     p.tiles_h = (p.H + p.R - 1) / p.R;
     p.num_tiles = p.tiles_w * p.tiles_h * p.N;
     p.tmem_cols = next_pow2_cols(2 * p.R * p.acc_stride);

@@ -139,16 +139,23 @@ __global__ void bn_param_grad_kernel(const float* __restrict__ s1, const float* 
     dgamma[c] = (g != 0.f) ? (s2[c] - beta[c] * s1[c]) / g : 0.f;
 }
 
-__global__ void pixel_unshuffle_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int H, int W, int C) {
-    // in [N][2H][2W][C] -> out [N][H][W][4C], column q*C + c, q = dy*2+dx
-    const long total = (long)N * H * W * 4 * C;
-    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int col = (int)(idx % (4 * C));
-    const long p = idx / (4 * C);
-    const int w = (int)(p % W), h = (int)((p / W) % H), n = (int)(p / ((long)W * H));
-    const int q = col / C, c = col % C;
-    out[idx] = in[(((long)n * 2 * H + 2 * h + (q >> 1)) * 2 * W + 2 * w + (q & 1)) * C + c];
+// in [N][2H][2W][C] -> out [N][H][W][4C], column q*C + c, q = dy*2+dx.  One thread moves VEC consecutive channels
+// (float4 when C % 4 == 0), grid-stride so that every SM keeps several 16-byte loads in flight.
+template <int VEC>
+__global__ void __launch_bounds__(256) pixel_unshuffle_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int H,
+                                                                int W, int C) {
+    const int cv = C / VEC;
+    const long total = (long)N * H * W * 4 * cv;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int col = (int)(idx % (4 * cv));
+        const long p = idx / (4 * cv);
+        const int w = (int)(p % W), h = (int)((p / W) % H), n = (int)(p / ((long)W * H));
+        const int q = col / cv, c = (col % cv) * VEC;
+        const float* src = in + (((long)n * 2 * H + 2 * h + (q >> 1)) * 2 * W + 2 * w + (q & 1)) * C + c;
+        float* dst = out + p * 4 * C + (long)q * C + c;
+        if (VEC == 4) *reinterpret_cast<float4*>(dst) = ldg_stream4(src);
+        else *dst = *src;
+    }
 }
 
 __global__ void dilate2_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int H, int W, int C) {
@@ -418,7 +425,11 @@ extern "C" int sci_bn_param_grad(const float* s1, const float* s2, const float* 
 
 extern "C" int sci_nhwc_pixel_unshuffle(const float* in, float* out, int N, int H, int W, int C, void* stream) {
     SCI_REQUIRE(in && out && N > 0 && H > 0 && W > 0 && C > 0, "pixel_unshuffle");
-    pixel_unshuffle_kernel<<<grid1d((long)N * H * W * 4 * C), 256, 0, sci_stream(stream)>>>(in, out, N, H, W, C);
+    const bool v4 = C % 4 == 0 && (((uintptr_t)in | (uintptr_t)out) & 15) == 0;
+    const long work = (long)N * H * W * 4 * (v4 ? C / 4 : C);
+    const int grid = (int)min((long)SCI_NUM_SMS * 16, (work + 255) / 256);
+    if (v4) pixel_unshuffle_kernel<4><<<grid, 256, 0, sci_stream(stream)>>>(in, out, N, H, W, C);
+    else    pixel_unshuffle_kernel<1><<<grid, 256, 0, sci_stream(stream)>>>(in, out, N, H, W, C);
     SCI_CHECK_LAUNCH("pixel_unshuffle");
     return SCI_OK;
 }
