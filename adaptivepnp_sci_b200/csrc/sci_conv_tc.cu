@@ -318,6 +318,7 @@ struct Fwd2Params {
     int N, H, W, Cin, Cout, relu, ps, round_tf32;
     int tiles_w, num_tiles, k_chunks, stages, acc_stride, tmem_cols, resident, desc_mode, tma_store, out_bufs;
     const float* planar_in1; float* planar_out;   // fused network output: out[n][c][h][w] = in1[n][c][h][w] - conv[c], c < 3
+    int col0, Ctot;   // this launch computes GEMM columns [col0, col0 + Cout) of a layer with Ctot columns (Cout = 256 layers run as two halves)
     int stack;        // filter rows stacked along N (see the MMA issuer); needs resident weights, R >= 2, 3*Cout <= 256
     int R, tiles_h;   // rows per super-tile (R output rows share their R+2 input rows), super-tiles per image column strip
     int dbg;   // SCI_CONV_DBG timing experiments (results invalid): 1 = no MMAs, 2 = no activation loads, 4 = no stores
@@ -350,8 +351,8 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t stage_out_base = ring_base + (uint32_t)p.stages * stage_bytes;   // 4 warps x 2 x 4 KB store staging
 
     for (int i = threadIdx.x; i < p.Cout; i += TC_THREADS) {
-        s_scale[i] = p.scale ? p.scale[i] : 1.f;
-        s_shift[i] = p.shift ? p.shift[i] : 0.f;
+        s_scale[i] = p.scale ? p.scale[p.col0 + i] : 1.f;
+        s_shift[i] = p.shift ? p.shift[p.col0 + i] : 0.f;
     }
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -384,7 +385,7 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         // horizontal tap form ONE K-major B matrix of 3*Cout rows
                         const uint32_t slot = p.stack ? (uint32_t)(((tap % 3) * p.k_chunks + kc) * 3 + tap / 3)
                                                       : (uint32_t)(tap * p.k_chunks + kc);
-                        tma_load_3d(smem_base + slot * b_bytes, &tmB, &w_bar, kc * KCH, 0, tap);
+                        tma_load_3d(smem_base + slot * b_bytes, &tmB, &w_bar, kc * KCH, p.col0, tap);
                     }
             }
             __syncwarp();
@@ -404,7 +405,7 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         if (!skip_a) tma_load_4d(a_dst, &tmA, &full_bar[stage], kc * KCH, wt * 128 - 1, y0 + j - 1, n);
                         if (!p.resident) {       // streamed weights: R == 1, j is the filter row
                             for (int s = 0; s < 3; ++s)
-                                tma_load_3d(a_dst + A2_STAGE + (uint32_t)s * b_bytes, &tmB, &full_bar[stage], kc * KCH, 0, j * 3 + s);
+                                tma_load_3d(a_dst + A2_STAGE + (uint32_t)s * b_bytes, &tmB, &full_bar[stage], kc * KCH, p.col0, j * 3 + s);
                         }
                     }
                     __syncwarp();
@@ -521,7 +522,7 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // ===== epilogue: TMEM -> registers -> (scale/shift, ReLU, skip-add, TF32 round) -> swizzled staging -> TMA store
         const int q = warp & 3;
         const int m = q * 32 + lane;
-        const int Cq = p.Cout >> 2;
+        const int Cq = p.Ctot >> 2;
         int acc = 0; uint32_t acc_phase = 0;
         uint32_t st_cnt = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -531,11 +532,12 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const bool valid = wo < p.W;
             // element offset of this lane's 32-channel segment of chunk c0 of output row ho in the output / residual tensor
             auto out_offset = [&](int ho, int c0) -> long {
+                const int cg = p.col0 + c0;                           // column of the whole layer
                 if (p.ps) {
-                    const int qq = c0 / Cq, cc = c0 % Cq;
+                    const int qq = cg / Cq, cc = cg % Cq;
                     return (((long)n * 2 * p.H + 2 * ho + (qq >> 1)) * 2 * p.W + 2 * wo + (qq & 1)) * Cq + cc;
                 }
-                return (((long)n * p.H + ho) * p.W + wo) * p.Cout + c0;
+                return (((long)n * p.H + ho) * p.W + wo) * p.Ctot + cg;
             };
             // the skip tensor of the first chunk is fetched while the MMAs of this tile are still running
             float4 rr[8];
@@ -604,8 +606,9 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) {
-                        int cx = c0, cw = wt * 128 + q * 32, chh = ho;
-                        if (p.ps) { const int qq = c0 / Cq; cx = c0 % Cq; cw = 2 * cw + (qq & 1); chh = 2 * ho + (qq >> 1); }
+                        const int cg = p.col0 + c0;
+                        int cx = cg, cw = wt * 128 + q * 32, chh = ho;
+                        if (p.ps) { const int qq = cg / Cq; cx = cg % Cq; cw = 2 * cw + (qq & 1); chh = 2 * ho + (qq >> 1); }
                         asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                                      ::"l"(&tmY), "r"(sbuf), "r"(cx), "r"(cw), "r"(chh), "r"(n) : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -675,12 +678,12 @@ int make_act_map(CUtensorMap* tm, const float* x, int N, int H, int W, int C, in
 }
 
 // packed weights [taps][Cout][Cin] (taps = 9, or 18 with the hi/remainder split), box = {32 ch, Cout, 1}
-int make_weight_map(CUtensorMap* tm, const float* w, int Cout, int Cin, int taps) {
+int make_weight_map(CUtensorMap* tm, const float* w, int Cout, int Cin, int taps, int box_rows = 0) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return sci_fail(SCI_ELAUNCH, "cuTensorMapEncodeTiled entry point not available");
     const cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)taps};
     const cuuint64_t strides[2] = {(cuuint64_t)Cin * 4, (cuuint64_t)Cout * Cin * 4};
-    const cuuint32_t box[3] = {KCH, (cuuint32_t)Cout, 1};
+    const cuuint32_t box[3] = {KCH, (cuuint32_t)(box_rows ? box_rows : Cout), 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(w), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -747,17 +750,18 @@ int env_int(const char* name, int dflt) {
 
 bool fwd2_eligible(const sci_conv_desc* d) {
     if (d->planar_out) return true;                      // fused planar output exists in the v2 kernel only
-    return d->stride == 1 && d->Cout % 32 == 0 && d->Cout <= 128 && !d->w_split && !d->emit_lo &&
+    return d->stride == 1 && d->Cout % 32 == 0 && (d->Cout <= 128 || d->Cout == 256) && !d->w_split && !d->emit_lo &&
            env_int("SCI_CONV_V2", 1) != 0;
 }
 
-int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream) {
+// columns [col0, col0 + ncols) of the layer
+int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream, int col0, int ncols) {
     if (d->Cin % KCH != 0) return sci_fail(SCI_EUNSUPPORTED, "conv tc v2: Cin % 32");
     if (((uintptr_t)d->x | (uintptr_t)d->w | (uintptr_t)d->y | (uintptr_t)d->residual) & 15)
         return sci_fail(SCI_EINVAL, "conv tc: pointers must be 16-byte aligned");
     Fwd2Params p;
     p.scale = d->scale; p.shift = d->shift; p.residual = d->residual; p.y = d->y;
-    p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;
+    p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = ncols; p.col0 = col0; p.Ctot = d->Cout;
     p.relu = d->relu; p.ps = d->pixel_shuffle; p.round_tf32 = d->round_tf32;
     p.planar_in1 = d->planar_in1; p.planar_out = d->planar_out;
     if (p.planar_out && (!p.planar_in1 || p.ps || p.Cout != 32 || d->residual))
@@ -814,7 +818,7 @@ int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream) {
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return sci_fail(SCI_ELAUNCH, "cuTensorMapEncodeTiled(row box) failed");
     }
-    int rc = make_weight_map(&tmB, d->w, d->Cout, d->Cin, 9);
+    int rc = make_weight_map(&tmB, d->w, d->Cout, d->Cin, 9, ncols);
     if (rc) return rc;
     CUtensorMap tmY = tmA;
     if (p.tma_store) {
@@ -1239,7 +1243,14 @@ extern "C" int sci_conv3x3_fwd(const sci_conv_desc* d, int impl, void* stream) {
         SCI_REQUIRE(!d->w_split && !d->emit_lo && !d->planar_out, "conv ref: w_split / emit_lo / planar_out are tensor-core options");
         return sci_conv3x3_ref_launch(d, stream);
     }
-    if (impl == SCI_CONV_TC) return fwd2_eligible(d) ? conv_fwd2_tc_launch(d, stream) : conv_fwd_tc_launch(d, stream);
+    if (impl == SCI_CONV_TC) {
+        if (!fwd2_eligible(d)) return conv_fwd_tc_launch(d, stream);
+        if (d->Cout <= 128) return conv_fwd2_tc_launch(d, stream, 0, d->Cout);
+        // 256 columns: two passes of 128 (PixelShuffle layers: the two output-row parities); the activation rows are
+        // fetched twice, the tensor-core work is unchanged
+        rc = conv_fwd2_tc_launch(d, stream, 0, 128);
+        return rc ? rc : conv_fwd2_tc_launch(d, stream, 128, 128);
+    }
     return sci_fail(SCI_EINVAL, "conv: unknown impl");
 }
 
