@@ -1222,6 +1222,190 @@ int conv_wgrad2_tc_launch(const sci_wgrad_desc* d, void* stream) {
     return SCI_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// weight-gradient kernel, version 3 ("rs-stack"): all nine taps in ONE CTA, one pass over the data
+//   dW[r,s][co][ci] = sum_p dz[p][co] * x[p + (r-1) rows + (s-1) cols][ci]
+//   Version 2 ran one filter row per CTA group: dz and x were read three times, and with 32-channel layers only a quarter
+//   of the MMA rows did useful work (full-resolution layers: 0.47-0.86 ms each, 60 % of the weight-gradient time).
+//   Here the operand with FEWER channels (P) goes on the M side as the stack of its three ROW-shifted views - one
+//   {32 ch, 8 px, 10 rows} box per 32-channel chunk; a row shift is 1024 bytes, the swizzle period, so the views are plain
+//   descriptor offsets and the stack has a uniform leading-dimension stride of 1024 bytes - and the other operand (Q) on
+//   the N side as the stack of its three COLUMN-shifted 8x8 boxes.  One MMA per 8 pixels then yields the 3x3 block of
+//   taps for 32 P-channels x all Q-channels:  D[(r, p-ch)][(s, q-ch)].
+//     case A (P = dz, Q = x):  sum over q of dz[q - (r-1) rows] * x[q + (s-1) cols]   -> P view r starts at box row 2-r
+//     case B (P = x, Q = dz):  sum over q of x[q + (r-1) rows] * dz[q - (s-1) cols]   -> P view r starts at box row r
+//   TMA zero fill supplies both the conv padding (x) and the out-of-image output pixels (dz).
+// ---------------------------------------------------------------------------------------------------
+constexpr int WG3_P_BYTES = 10 * 1024;           // P chunk box: 10 rows x 8 px x 128 B
+struct Wgrad3Params {
+    const float* oscale; float* dw;
+    int N, H, W, Cin, Cout;
+    int tiles_w, tiles_h, num_tiles;
+    int p_is_dz, p_chunks, q_chunks, q_slots, n_tot, tmem_cols, stages;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_wgrad3_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ, const Wgrad3Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], done_bar;
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t p_bytes = (uint32_t)p.p_chunks * WG3_P_BYTES, q_bytes = (uint32_t)p.q_slots * WG_CHUNK_BYTES;
+    const uint32_t stage_bytes = p_bytes + q_bytes;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmP) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&done_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_slot, 0);
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, n = tile / (p.tiles_w * p.tiles_h);
+            const int ow0 = tw * WG_TILE, oh0 = th * WG_TILE;
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            if (elect_one()) {
+                mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+                const uint32_t pb = smem_base + (uint32_t)stage * stage_bytes, qb = pb + p_bytes;
+                for (int c = 0; c < p.p_chunks; ++c)
+                    tma_load_4d(pb + (uint32_t)c * WG3_P_BYTES, &tmP, &full_bar[stage], c * KCH, ow0, oh0 - 1, n);
+                for (int s = 0; s < 3; ++s)
+                    for (int c = 0; c < p.q_chunks; ++c)
+                        tma_load_4d(qb + (uint32_t)(s * p.q_chunks + c) * WG_CHUNK_BYTES, &tmQ, &full_bar[stage], c * KCH,
+                                    ow0 + (p.p_is_dz ? s - 1 : 1 - s), oh0, n);
+            }
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: both operands MN-major (SWIZZLE_128B_BASE32B), M = 128 (rows 96..127 unused), K = 8 pixels =====
+        const uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((128u >> 4) << 24);
+        const uint64_t pdesc_hi = umma_desc(0, 1024, 512, 1);              // stack of row-shifted views: stride 1024 B
+        const uint64_t qdesc_hi = umma_desc(0, WG_CHUNK_BYTES, 512, 1);    // stack of boxes: stride 8192 B
+        int stage = 0; uint32_t phase = 0; uint32_t first = 1;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t pb = smem_base + (uint32_t)stage * stage_bytes, qb = pb + p_bytes;
+            for (int c = 0; c < p.p_chunks; ++c) {
+                for (int g0 = 0; g0 < p.q_slots; g0 += 8) {                 // N groups of <= 8 slots (256 columns)
+                    const int ns = min(8, p.q_slots - g0);
+                    const uint32_t idesc = idesc0 | ((uint32_t)((ns * 32) >> 3) << 17);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(c * p.n_tot + g0 * 32);
+                    const uint32_t a0 = pb + (uint32_t)c * WG3_P_BYTES, b0 = qb + (uint32_t)g0 * WG_CHUNK_BYTES;
+#pragma unroll
+                    for (int k8 = 0; k8 < WG_TILE; ++k8) {
+                        tc_mma_tf32_elect(d_tmem, pdesc_hi | (uint64_t)(((a0 + k8 * 1024) & 0x3FFFFu) >> 4),
+                                          qdesc_hi | (uint64_t)(((b0 + k8 * 1024) & 0x3FFFFu) >> 4), idesc,
+                                          (uint32_t)(!first || k8 != 0));
+                    }
+                }
+            }
+            tc_commit_elect(&empty_bar[stage]);
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            first = 0;
+        }
+        tc_commit_elect(&done_bar);
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> registers -> red.global.add into the packed gradient dw[tap][co][ci] =====
+        const int i = warp & 3;                        // stacked view index: TMEM lanes 32 i .. 32 i + 31
+        if (i < 3 && blockIdx.x < p.num_tiles) {
+            mbar_wait(&done_bar, 0);
+            tc_fence_after();
+            const int r = p.p_is_dz ? 2 - i : i;
+            for (int c = 0; c < p.p_chunks; ++c) {
+                const int pch = c * 32 + lane;
+                const uint32_t t_row = tmem_base + (uint32_t)(c * p.n_tot) + ((uint32_t)(i * 32) << 16);
+                for (int slot = 0; slot < p.q_slots; ++slot) {
+                    float v[32];
+                    tmem_ld32(t_row + slot * 32, v);
+                    const int s = slot / p.q_chunks, q0 = (slot % p.q_chunks) * 32;
+                    const int tap = r * 3 + s;
+                    if (p.p_is_dz) {                   // row = output channel, 32 consecutive input channels
+                        const float sc = p.oscale ? p.oscale[pch] : 1.f;
+                        float* dst = p.dw + ((long)tap * p.Cout + pch) * p.Cin + q0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v[j] * sc),
+                                         "f"(v[j + 1] * sc), "f"(v[j + 2] * sc), "f"(v[j + 3] * sc) : "memory");
+                    } else {                           // row = input channel (lanes consecutive -> coalesced), 32 output channels
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int co = q0 + j;
+                            const float sc = p.oscale ? __ldg(p.oscale + co) : 1.f;
+                            atomicAdd(p.dw + ((long)tap * p.Cout + co) * p.Cin + pch, v[j] * sc);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
+}
+
+bool wgrad3_eligible(const sci_wgrad_desc* d) {
+    const int cp = min(d->Cin, d->Cout), cq = max(d->Cin, d->Cout);
+    return d->stride == 1 && (cp == 32 || cp == 64) && cq <= 96 && (cp / 32) * 3 * cq <= 512 && env_int("SCI_WGRAD_V3", 1) != 0;
+}
+
+int conv_wgrad3_tc_launch(const sci_wgrad_desc* d, void* stream) {
+    Wgrad3Params p;
+    p.oscale = d->oscale; p.dw = d->dw;
+    p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;
+    p.tiles_w = (p.W + WG_TILE - 1) / WG_TILE; p.tiles_h = (p.H + WG_TILE - 1) / WG_TILE;
+    p.num_tiles = p.tiles_w * p.tiles_h * p.N;
+    p.p_is_dz = d->Cout <= d->Cin ? 1 : 0;
+    const int cp = p.p_is_dz ? d->Cout : d->Cin, cq = p.p_is_dz ? d->Cin : d->Cout;
+    p.p_chunks = cp / KCH; p.q_chunks = cq / KCH; p.q_slots = 3 * p.q_chunks; p.n_tot = 3 * cq;
+    p.tmem_cols = next_pow2_cols(p.p_chunks * p.n_tot);
+    const size_t stage_bytes = (size_t)p.p_chunks * WG3_P_BYTES + (size_t)p.q_slots * WG_CHUNK_BYTES;
+    // the 4th (unused) stacked view of the last k-step reads up to 1 KB past the P box: keep a guard after the ring
+    p.stages = (int)min((size_t)4, (size_t)(212 * 1024) / stage_bytes);
+    if (p.stages < 2) return sci_fail(SCI_EUNSUPPORTED, "wgrad tc v3: pipeline does not fit");
+    CUtensorMap tmP, tmQ;
+    const float* P = p.p_is_dz ? d->dz : d->x;
+    const float* Q = p.p_is_dz ? d->x : d->dz;
+    int rc = make_act_map(&tmP, P, d->N, d->H, d->W, cp, 1, WG_TILE, 10, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+    rc = make_act_map(&tmQ, Q, d->N, d->H, d->W, cq, 1, WG_TILE, WG_TILE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+    const size_t smem = p.stages * stage_bytes + 2048 + 1024;
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(conv_wgrad3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        if (e != cudaSuccess) return sci_fail(SCI_ELAUNCH, "wgrad tc v3: smem attribute", e);
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    const int gx = max(1, min(p.num_tiles, SCI_NUM_SMS));
+    conv_wgrad3_tc_kernel<<<gx, TC_THREADS, smem, sci_stream(stream)>>>(tmP, tmQ, p);
+    SCI_CHECK_LAUNCH("conv tc wgrad v3");
+    return SCI_OK;
+}
+
 int check_conv_desc(const sci_conv_desc* d) {
     SCI_REQUIRE(d && d->x && d->w && (d->y || d->planar_out), "conv: null pointer");
     SCI_REQUIRE(!d->planar_out || (d->stride == 1 && !d->w_split && !d->emit_lo), "conv: planar output options");
@@ -1267,6 +1451,7 @@ extern "C" int sci_conv3x3_wgrad(const sci_wgrad_desc* d, int impl, void* stream
     if (impl == SCI_CONV_TC) {
         if (d->Cin % 32 != 0 || d->Cout % 32 != 0 || d->Cin > 128 || d->Cout > 256)
             return sci_fail(SCI_EUNSUPPORTED, "wgrad tc: needs Cin % 32 == 0 (<= 128), Cout % 32 == 0 (<= 256)");
+        if (wgrad3_eligible(d)) return conv_wgrad3_tc_launch(d, stream);
         return env_int("SCI_WGRAD_V2", 1) ? conv_wgrad2_tc_launch(d, stream) : conv_wgrad_tc_launch(d, stream);
     }
     return sci_fail(SCI_EINVAL, "wgrad: unknown impl");
