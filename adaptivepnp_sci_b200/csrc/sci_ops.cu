@@ -465,6 +465,50 @@ extern "C" int sci_dual_update_rgb(const float* xhat, const float* x_rgb, float*
     return SCI_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Closed-form demosaic update of the `close_form_demosaic` branch (dvp:112-118, 175-182, 224-230), all frames:
+//   x_rgb[c] = (rho * x3[c] + b3[c] + tau * xhat[c] + w[c]) / (rho * m[c] + tau)   [clip to [0,1] on the FFDNet branch]
+//   u[c]     = x_rgb[c] - inv_tau * w[c]
+// where x3 / b3 are the sparse 3-channel images of the Bayer-domain x / b (value at the pixel's CFA channel, 0 elsewhere)
+// and m the RGGB mask.  Same operation order as the reference's tensor expression; compiled with --fmad=false.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) closed_form_demosaic_kernel(const float* __restrict__ x, const float* __restrict__ b,
+                                                                    const float* __restrict__ xhat, const float* __restrict__ w,
+                                                                    float rho, float tau, float inv_tau, int clip,
+                                                                    float* __restrict__ x_rgb, float* __restrict__ u, int H, int W) {
+    const int t = blockIdx.z;
+    const long plane = (long)H * W;
+    const int col = blockIdx.x * blockDim.x + threadIdx.x, row = blockIdx.y;
+    if (col >= W) return;
+    const long p = (long)row * W + col;
+    const int cfa = (row & 1) + (col & 1);                 // RGGB: 0 = R, 1 = G, 2 = B
+    const float xv = x[(long)t * plane + p], bv = b[(long)t * plane + p];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const long o = ((long)t * 3 + c) * plane + p;
+        const float m = (c == cfa) ? 1.f : 0.f;
+        const float ww = w[o];
+        float num = rho * (m * xv);
+        num = num + m * bv;
+        num = num + tau * xhat[o];
+        num = num + ww;
+        float v = num / (rho * m + tau);
+        if (clip) v = fminf(fmaxf(v, 0.f), 1.f);
+        x_rgb[o] = v;
+        u[o] = v - inv_tau * ww;
+    }
+}
+
+extern "C" int sci_closed_form_demosaic(const float* x, const float* b, const float* xhat, const float* w, float rho, float tau,
+                                        float inv_tau, int clip, float* x_rgb, float* u, int H, int W, int B, void* stream) {
+    SCI_REQUIRE(x && b && xhat && w && x_rgb && u, "closed_form_demosaic: null pointer");
+    SCI_REQUIRE(H > 0 && W > 0 && B > 0 && H <= 65535 && B <= 65535, "closed_form_demosaic: shape");
+    closed_form_demosaic_kernel<<<dim3(sci_ceil_div(W, 256), H, B), 256, 0, sci_stream(stream)>>>(x, b, xhat, w, rho, tau, inv_tau,
+                                                                                                  clip, x_rgb, u, H, W);
+    SCI_CHECK_LAUNCH("closed_form_demosaic");
+    return SCI_OK;
+}
+
 // Gray-scale variant of the stage-2 bookkeeping (derived FFDNet-gray config): no Bayer sampling,
 // theta = clip(xhat); b += x - theta; w += x_pre - xhat; optional PSNR.  One thread = 4 pixels.
 __global__ void __launch_bounds__(256) dual_update_gray_kernel(const float* __restrict__ xhat, const float* __restrict__ x_pre,

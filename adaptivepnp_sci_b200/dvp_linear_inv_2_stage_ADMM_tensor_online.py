@@ -220,8 +220,6 @@ def twoStageAdmm_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, gamma=0.01,
     name = denoiser if denoiser == 'tv' else str(denoiser).lower()
     if name not in ('tv', 'ffdnet_color', 'fastdvd_color'):
         raise ValueError('Unsupported denoiser {}!'.format(denoiser))
-    if close_form_demosaic:
-        raise NotImplementedError("the closed-form demosaic branch is not built yet (SURVEY §8(f) row 3)")
     sigma, iter_max = _as_list(sigma, iter_max)
     pb = _Problem(y_bayer, Phi_bayer, x0_bayer, X_orig)
     dev = pb.y.device
@@ -237,6 +235,8 @@ def twoStageAdmm_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, gamma=0.01,
     alpha = 0.01 if name == 'tv' else 1                                  # :101-104
     rou = 0.55 if name == 'fastdvd_color' else 1                         # :106-109
     tau = 100                                                            # :110
+    if close_form_demosaic:                                              # :112-118
+        tau, rou = 10, 0.55
     inv_rou = float(np.float32(1 / rou))
     n_total = int(sum(iter_max))
     want_iqa = bool(show_iqa and X_orig is not None)
@@ -280,7 +280,14 @@ def twoStageAdmm_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, gamma=0.01,
                     do_update = do_update and (update_i < update_times or update_times < 0)   # :247
                     update_i += int(do_update)
                 adapter = ffdnet_adapter if name == 'ffdnet_color' else fastdvdnet_adapter
-                if model_demosaic is not None:
+                if close_form_demosaic and k > 0:
+                    # x_rgb = (rho*x3 + b3 + tau*xhat + w) / (rho*mask + tau) [clip for FFDNet] ; u = x_rgb - w/tau   (:175-182)
+                    if tile is not None:
+                        raise NotImplementedError("tiled mode does not cover the closed-form demosaic branch")
+                    ops.closed_form_demosaic(x, b, xhat, w, rou, tau, name == 'ffdnet_color', x_rgb, u)
+                    xhat = adapter.denoise_planar(u, pb, nsig, model_denoise, lr_, do_update, update_per_iter,
+                                                  grad_sync=grad_sync)
+                elif model_demosaic is not None:
                     # deep demosaicking: x_rgb = DDnet(merge(x + b/rho)) ; u = x_rgb - w/tau          (:192-198, :241-246)
                     if tile is not None:
                         raise NotImplementedError("tiled mode uses the Malvar demosaic (DDnet would need its own halo)")

@@ -99,6 +99,16 @@ def dual_update_rgb(xhat, x_rgb, w, x, b, theta, first_iter, orig=None, sse=None
          H, W, B, ptr(orig), ptr(sse), stream())
 
 
+def closed_form_demosaic(x, b, xhat, w, rho, tau, clip, x_rgb_out, u_out):
+    """x_rgb = (rho*x3 + b3 + tau*xhat + w) / (rho*mask + tau) [clip]; u = x_rgb - w/tau  (dvp:175-182, 198)."""
+    require_cuda_f32(x, b, xhat, w, x_rgb_out, u_out)
+    B, H, W = x.shape
+    import numpy as np
+    call("sci_closed_form_demosaic", ptr(x), ptr(b), ptr(xhat), ptr(w), float(rho), float(tau), float(np.float32(1 / tau)),
+         int(bool(clip)), ptr(x_rgb_out), ptr(u_out), H, W, B, stream())
+    return x_rgb_out, u_out
+
+
 def rgb_to_bayer(rgb):
     require_cuda_f32(rgb)
     B, _, H, W = rgb.shape

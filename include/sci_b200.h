@@ -125,6 +125,13 @@ int sci_dual_update_rgb(const float* xhat, const float* x_rgb, float* w, const f
                         float* b, float* theta, int first_iter, int H, int W, int B,
                         const float* orig, double* sse, void* stream);
 
+/* Closed-form demosaic update of the `close_form_demosaic` branch (dvp_linear_inv_2_stage_ADMM_tensor_online.py:112-118,
+ * 175-182, 224-230), all frames in one launch:
+ *   x_rgb[c] = (rho*x3[c] + b3[c] + tau*xhat[c] + w[c]) / (rho*m[c] + tau), optionally clipped to [0,1] (:182, FFDNet branch);
+ *   u[c] = x_rgb[c] - inv_tau*w[c] (:198).  x, b [B][H][W] Bayer-domain; xhat, w, x_rgb, u [B][3][H][W]; x3/b3/m are the
+ *   sparse 3-channel forms (fourCh2ThreeCh, utils_image.py:162-171) and the RGGB mask. */
+int sci_closed_form_demosaic(const float* x, const float* b, const float* xhat, const float* w, float rho, float tau,
+                             float inv_tau, int clip, float* x_rgb, float* u, int H, int W, int B, void* stream);
 /* ---- K5: RGB cube -> Bayer samples / sparse 3-channel mosaic --------------
  * sci_rgb_to_bayer: dvp...online.py:206-209, packages/fastdvdnet/utils.py:69-78
  *   rgb [B][3][H][W] -> mosaic [B][H][W].

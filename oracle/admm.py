@@ -17,8 +17,8 @@ from . import BAYER
 from .adapters import fastdvdnet_denoiser_full_tensor_v2, ffdnet_rgb_denoise_full_tensor, test_ddnet
 from .demosaic import malvar2004_tensor
 from .iqa import compare_psnr, compare_ssim
-from .sci_ops import (bayer_merge, bayer_split_init, masks_CFA_Bayer_tensor, oneCh2ThreeCh, project_stage1,
-                      project_stage2)
+from .sci_ops import (bayer_merge, bayer_split_init, fourCh2ThreeCh, masks_CFA_Bayer_tensor, oneCh2ThreeCh,
+                      project_stage1, project_stage2)
 from .tv_chambolle import denoise_tv_chambolle
 
 
@@ -88,8 +88,6 @@ def twoStageAdmm_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, gamma=0.01, denois
                                args=None, trace=None):
     """Stage 2.  'tv' -> 4-tuple; deep denoisers -> (xbgr3_np[H,W,3,B], x_bayer_np, psnr_, ssim_,
     psnr_all, model_denoise, model_demosaic)."""
-    if close_form_demosaic:
-        raise NotImplementedError('oracle: closed-form demosaic is a SURVEY §8(f) "next" row')
     y_bayer = torch.from_numpy(np.ascontiguousarray(y_bayer))
     Phi_bayer = torch.from_numpy(np.ascontiguousarray(Phi_bayer))
     sigma, iter_max = _listify(sigma, iter_max)
@@ -103,6 +101,11 @@ def twoStageAdmm_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, gamma=0.01, denois
     alpha = 0.01 if denoiser == 'tv' else 1                          # :101-104
     rou = 0.55 if denoiser == 'fastdvd_color' else 1                 # :106-109
     tau = 100
+    if close_form_demosaic:                                          # :112-118
+        tau = 10
+        rou = 0.55
+        bayer_mask = torch.stack([R_m, G_m, B_m], dim=2)             # gen_bayer_mask, utils_image.py:115-118 (bool [H,W,3])
+        inv_3ch = torch.repeat_interleave((rou * bayer_mask + tau).unsqueeze(3), nmask, dim=3)
     psnr_all = []
     k = 0
     update_i = 0
@@ -117,7 +120,11 @@ def twoStageAdmm_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, gamma=0.01, denois
                 TV = False
                 x_rgb = torch.zeros([nrow, ncol, 3, nmask])
                 x_bayer = bayer_merge(xall + (1 / rou) * ball)                                   # :169-172
-                if model_demosaic is not None:                                                   # :192-194, :241-243
+                if close_form_demosaic and k > 0:                                                # :175-182, :224-230
+                    x_rgb = (rou * fourCh2ThreeCh(xall) + fourCh2ThreeCh(ball) + tau * xbgr3 + w) / inv_3ch
+                    if denoiser.lower() == 'ffdnet_color':
+                        x_rgb = x_rgb.clip(0, 1)                                                 # :182 (FFDNet branch only)
+                elif model_demosaic is not None:                                                 # :192-194, :241-243
                     x_rgb = test_ddnet(oneCh2ThreeCh(x_bayer), yall, Phiall, model_demosaic)
                 elif demosaic_method == 'malvar2004':                                            # :185-191 (App. D.2)
                     for t in range(nmask):

@@ -111,6 +111,17 @@ def oneCh2ThreeCh(oneCh):
     return RGB
 
 
+def fourCh2ThreeCh(RGGB):
+    """utils/utils_image.py:162-171 — [h,w,B,4] Bayer planes -> sparse 3-channel mosaic [H,W,3,B]."""
+    h, w, B, _ = RGGB.shape
+    RGB = torch.zeros(2 * h, 2 * w, 3, B)
+    RGB[0::2, 0::2, 0, :] = RGGB[:, :, :, 0]
+    RGB[0::2, 1::2, 1, :] = RGGB[:, :, :, 1]
+    RGB[1::2, 0::2, 1, :] = RGGB[:, :, :, 2]
+    RGB[1::2, 1::2, 2, :] = RGGB[:, :, :, 3]
+    return RGB
+
+
 def rgb_to_bayer4(xrgb):
     """dvp...online.py:206-209 / test_ffdnet_ipol.py:275-278 — RGGB samples of an
     RGB cube [H,W,3,B] -> [h,w,B,4].  Nothing is averaged."""

@@ -242,6 +242,49 @@ def ddnet_(ns):
     np.savez_compressed(os.path.join(HERE, "ddnet.npz"), **out)
 
 
+def closed_form(ns):
+    """``close_form_demosaic=True`` branch of stage 2 (dvp:112-118, 175-182, 224-230): tau = 10, rho = 0.55 and the
+    closed-form x_rgb update from k = 1 on (k = 0 demosaics with Malvar)."""
+    print("closed-form demosaic branch")
+    out = {}
+    meas, mask, orig = synthetic.make_case(64, 64, 8, 3000, bayer=True)
+    warm = np.load(os.path.join(HERE, "loops.npz"))["s2_warm"]
+    kw = dict(show_iqa=True, demosaic_method='malvar2004', lr_=2e-6, interval_iter=3, update_=True, update_per_iter=2,
+              close_form_demosaic=True)
+    ns.utilspy.worker_init_fn(0)
+    r = ns.dvp.twoStageAdmm_denoise_bayer(meas, mask, 1, 0.01, 'ffdnet_color', [4, 3], False, [25 / 255, 12 / 255],
+                                          x0_bayer=torch.from_numpy(warm), X_orig=orig, model_denoise=_ref_ffdnet(ns),
+                                          model_demosaic=None, logf=io.StringIO(), **kw)
+    ns.utilspy.worker_init_fn(0)
+    o = admm.twoStageAdmm_denoise_bayer(meas, mask, 1, 0.01, 'ffdnet_color', [4, 3], False, [25 / 255, 12 / 255],
+                                        x0_bayer=torch.from_numpy(warm), X_orig=orig, model_denoise=_orc_ffdnet(), **kw)
+    _eq(r[0], o[0], "closed-form ffdnet xbgr3")
+    _eq(r[1], o[1], "closed-form ffdnet x_bayer")
+    _eq(np.array(r[4]), np.array(o[4]), "closed-form ffdnet psnr_all")
+    print("   psnr_all:", np.round(np.array(r[4]), 2))
+    out.update(ffd_rgb=r[0], ffd_x=r[1], ffd_psnr_all=np.array(r[4]))
+    kw = dict(kw, update_times=-1)
+    ns.utilspy.worker_init_fn(0)
+    r = ns.dvp.twoStageAdmm_denoise_bayer(meas, mask, 1, 0.01, 'fastdvd_color', [5, 2], False, [12 / 255, 6 / 255],
+                                          x0_bayer=torch.from_numpy(warm), X_orig=orig, model_denoise=_ref_fastdvd(ns),
+                                          model_demosaic=None, logf=io.StringIO(), **kw)
+    ns.utilspy.worker_init_fn(0)
+    o = admm.twoStageAdmm_denoise_bayer(meas, mask, 1, 0.01, 'fastdvd_color', [5, 2], False, [12 / 255, 6 / 255],
+                                        x0_bayer=torch.from_numpy(warm), X_orig=orig, model_denoise=_orc_fastdvd(), **kw)
+    _eq(r[0], o[0], "closed-form fastdvd xbgr3")
+    _eq(r[1], o[1], "closed-form fastdvd x_bayer")
+    _eq(np.array(r[4]), np.array(o[4]), "closed-form fastdvd psnr_all")
+    print("   psnr_all:", np.round(np.array(r[4]), 2))
+    out.update(fdvd_rgb=r[0], fdvd_x=r[1], fdvd_psnr_all=np.array(r[4]))
+    r = ns.dvp.twoStageAdmm_denoise_bayer(meas, mask, 1, 0.01, 'tv', [6], False, [0], x0_bayer=torch.from_numpy(warm),
+                                          X_orig=orig, show_iqa=True, logf=io.StringIO(), close_form_demosaic=True)
+    o = admm.twoStageAdmm_denoise_bayer(meas, mask, 1, 0.01, 'tv', [6], False, [0], x0_bayer=torch.from_numpy(warm),
+                                        X_orig=orig, close_form_demosaic=True)
+    _eq(r[0], o[0], "closed-form flag with tv (rho = 0.55)")
+    out.update(tv_x=r[0], tv_psnr_all=np.array(r[3]))
+    np.savez_compressed(os.path.join(HERE, "closed_form.npz"), **out)
+
+
 def nets(ns):
     print("networks")
     g = torch.Generator().manual_seed(11)
@@ -379,6 +422,10 @@ if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "ddnet":
     ddnet_(ref_harness.load())        # regenerate only tests/golden/ddnet.npz (needs loops.npz)
     sys.exit(0)
 
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "closed_form":
+    closed_form(ref_harness.load())
+    sys.exit(0)
+
 if __name__ == "__main__":
     if not ref_harness.available():
         sys.exit("reference tree not present: golden vectors can only be regenerated in the build container")
@@ -389,4 +436,5 @@ if __name__ == "__main__":
     adapters_(ns)
     loops(ns)
     ddnet_(ns)
+    closed_form(ns)
     print("golden vectors written to", HERE)

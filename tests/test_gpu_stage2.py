@@ -87,3 +87,28 @@ def test_stage2_ffdnet_gray_vs_derived_oracle(cuda, impl):
     # the warm start itself (stage 1 on a gray cube = 4 interleaved sub-problems) is the reference's own function
     w_gpu = admm_denoise_bayer_demosaic_pre(meas, mask, 1, 0.01, 'tv', [40], False, [0], X_orig=orig, show_iqa=False)[0]
     assert np.max(np.abs(w_gpu - warm)) < 2e-5
+
+
+def test_stage2_closed_form_demosaic(cuda, impl):
+    """close_form_demosaic=True branch: tau = 10, rho = 0.55, closed-form x_rgb update from k = 1 on."""
+    from adaptivepnp_sci_b200.dvp_linear_inv_2_stage_ADMM_tensor_online import np2tch_cuda, twoStageAdmm_denoise_bayer
+    from adaptivepnp_sci_b200.utilspy import worker_init_fn
+    from oracle import synthetic
+    d = np.load(os.path.join(G, "closed_form.npz"))
+    warm = np.load(os.path.join(G, "loops.npz"))["s2_warm"]
+    meas, mask, orig = synthetic.make_case(64, 64, 8, 3000, bayer=True)
+    kw = dict(show_iqa=True, demosaic_method='malvar2004', lr_=2e-6, interval_iter=3, update_=True, update_per_iter=2,
+              logf=io.StringIO(), close_form_demosaic=True)
+    tol = {"ref": 2e-4, "tc": 1e-3}[impl]
+    r = twoStageAdmm_denoise_bayer(meas, mask, 1, 0.01, 'ffdnet_color', [4, 3], False, [25 / 255, 12 / 255],
+                                   x0_bayer=np2tch_cuda(warm), X_orig=orig, model_denoise=_ffdnet(cuda), **kw)
+    assert np.max(np.abs(r[0] - d["ffd_rgb"])) < tol and np.max(np.abs(r[1] - d["ffd_x"])) < tol
+    assert np.max(np.abs(np.array(r[4]) - d["ffd_psnr_all"])) < 0.05
+    worker_init_fn(0)
+    r = twoStageAdmm_denoise_bayer(meas, mask, 1, 0.01, 'fastdvd_color', [5, 2], False, [12 / 255, 6 / 255],
+                                   x0_bayer=np2tch_cuda(warm), X_orig=orig, model_denoise=_fastdvd(cuda), update_times=-1, **kw)
+    assert np.max(np.abs(r[0] - d["fdvd_rgb"])) < tol and np.max(np.abs(r[1] - d["fdvd_x"])) < tol
+    assert np.max(np.abs(np.array(r[4]) - d["fdvd_psnr_all"])) < 0.05
+    r = twoStageAdmm_denoise_bayer(meas, mask, 1, 0.01, 'tv', [6], False, [0], x0_bayer=np2tch_cuda(warm), X_orig=orig,
+                                   show_iqa=True, logf=io.StringIO(), close_form_demosaic=True)
+    assert np.max(np.abs(r[0] - d["tv_x"])) < 2e-5 and np.max(np.abs(np.array(r[3]) - d["tv_psnr_all"])) < 1e-3
