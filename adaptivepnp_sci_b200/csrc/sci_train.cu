@@ -305,6 +305,27 @@ __global__ void fastdvd_output_kernel(const float* __restrict__ frames, const fl
     }
 }
 
+// dy[f][p][c] = -dout[f][c][p] for c < 3, 0 for the padded columns.  One thread reads the three plane values of its pixel
+// (coalesced), the block writes the [256 px][Cpad] rows through shared memory (fully coalesced NHWC write).
+__global__ void __launch_bounds__(FPACK_PIX) fastdvd_output_grad_kernel(const float* __restrict__ dout, float* __restrict__ dy,
+                                                                          int H, int W, int Cpad) {
+    extern __shared__ float srow[];                   // [FPACK_PIX][Cpad + 1]
+    const long plane = (long)H * W;
+    const int f = blockIdx.y;
+    const long p0 = (long)blockIdx.x * FPACK_PIX, p = p0 + threadIdx.x;
+    const int CS = Cpad + 1;
+    float* row = srow + threadIdx.x * CS;
+    for (int k = 0; k < Cpad; ++k) row[k] = 0.f;
+    if (p < plane) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) row[c] = -dout[((long)f * 3 + c) * plane + p];
+    }
+    __syncthreads();
+    const int npx = (int)min((long)FPACK_PIX, plane - p0);
+    float* dst = dy + ((long)f * plane + p0) * Cpad;
+    for (int i = threadIdx.x; i < npx * Cpad; i += FPACK_PIX) dst[i] = srow[(i / Cpad) * CS + (i % Cpad)];
+}
+
 __global__ void noisy_input_kernel(const float* __restrict__ v, const double* __restrict__ noise, float* __restrict__ vplus,
                                    long n) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -500,7 +521,10 @@ extern "C" int sci_fastdvd_output(const float* frames, const float* y, float* ou
 
 extern "C" int sci_fastdvd_output_grad(const float* dout, float* dy, int B, int H, int W, int Cpad, void* stream) {
     SCI_REQUIRE(dout && dy && B > 0 && H > 0 && W > 0 && Cpad >= 3, "fastdvd_output_grad");
-    fastdvd_output_kernel<<<grid1d((long)B * H * W * Cpad), 256, 0, sci_stream(stream)>>>(dout, nullptr, dy, B, H, W, Cpad, 1);
+    SCI_REQUIRE(Cpad <= 64, "fastdvd_output_grad: Cpad");
+    const long plane = (long)H * W;
+    fastdvd_output_grad_kernel<<<dim3(grid1d(plane, FPACK_PIX), B), FPACK_PIX, (size_t)FPACK_PIX * (Cpad + 1) * sizeof(float),
+                                 sci_stream(stream)>>>(dout, dy, H, W, Cpad);
     SCI_CHECK_LAUNCH("fastdvd_output_grad");
     return SCI_OK;
 }
