@@ -122,11 +122,11 @@ def run_reference(args):
     cores = torch.get_num_threads()
     v = args.steps / t
     sample = "1 inference ADMM iteration (projection + Malvar + FastDVDnet as executed by the reference + dual updates) of the 512x512x8 workload per step"
-    print(json.dumps({"impl": "reference", "metric": "admm_iters_per_sec", "value": v, "unit": "iters/s", "n_gpus": args.gpus,
+    _emit({"impl": "reference", "metric": "admm_iters_per_sec", "value": v, "unit": "iters/s", "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
                       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG,
                       "cpu_baseline": {"value": v, "unit": "iters/s", "cores": cores, "kind": "port", "sample": sample},
-                      "e2e": {"value": v, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                      "e2e": {"value": v, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
 
 def main():
@@ -276,10 +276,19 @@ def main():
             "e2e": {"value": e2e_value, "unit": "iters/s", "sec_per_recon": ms_e2e * 1e-3 / args.steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
+
+def _emit(line):
+    """The ONE JSON line of the contract goes to the real stdout; everything else this process (or NCCL, which logs
+    its version banner to stdout when NCCL_DEBUG is set) prints is routed to stderr."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
 
 if __name__ == "__main__":
     main()
