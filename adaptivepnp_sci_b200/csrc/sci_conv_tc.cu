@@ -548,6 +548,14 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 8; ++j) rr[j] = __ldg(rp + j);
             }
+            // fused planar output: the three in1 values of this lane's pixel are fetched ahead as well
+            float pin[3] = {0.f, 0.f, 0.f};
+            const long pl_plane = (long)p.H * p.W;
+            if (p.planar_out && valid) {
+                const long o = (long)n * 3 * pl_plane + (long)y0 * p.W + wo;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) pin[c] = __ldg(p.planar_in1 + o + c * pl_plane);
+            }
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
           for (int t = 0; t < rows; ++t) {
@@ -583,10 +591,14 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     // last conv of a FastDVDnet DenBlock: the 3 real channels leave as planar frames, residual form
                     // in1 - net (models.py:196) applied here; lanes are consecutive pixels -> coalesced plane accesses
                     if (valid && c0 == 0) {
-                        const long plane = (long)p.H * p.W;
-                        const long o = (long)n * 3 * plane + (long)ho * p.W + wo;
+                        const long o = (long)n * 3 * pl_plane + (long)ho * p.W + wo;
+                        float nxt[3] = {0.f, 0.f, 0.f};
+                        if (t + 1 < rows) {
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) p.planar_out[o + c * plane] = __ldg(p.planar_in1 + o + c * plane) - out[c];
+                            for (int c = 0; c < 3; ++c) nxt[c] = __ldg(p.planar_in1 + o + p.W + c * pl_plane);
+                        }
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) { p.planar_out[o + c * pl_plane] = pin[c] - out[c]; pin[c] = nxt[c]; }
                     }
                 } else if (p.tma_store) {
                     // coalesced path: the warp's 32 pixels x 32 channels go through a 128B-swizzled 4 KB staging tile and
