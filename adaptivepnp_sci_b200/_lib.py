@@ -75,6 +75,12 @@ PROTOTYPES = {
     "sci_ddnet_stage2_input": [_p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _p],
     "sci_ddnet_upsample4": [_p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _p],
     "sci_ddnet_output": [_p, _p, _p, _i, _p, _p, _i, _i, _i, _p],
+    "sci_ddnet_loss_fwd_bwd": [_p, _p, _p, _p, _i, _i, _i, _p],
+    "sci_ddnet_output_bwd": [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "sci_ddnet_stage2_input_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "sci_ddnet_pack_input1_bwd": [_p, _p, _p, _i, _i, _i, _p],
+    "sci_ddnet_pack_input4_bwd": [_p, _p, _p, _i, _i, _i, _i, _p],
+    "sci_ddnet_upsample4_bwd": [_p, _p, _i, _i, _i, _p],
     "sci_host_legacy_normal": [_p, _p, _p, _p, _d, _d, _p, _l, _i],
     "sci_meas_loss_fwd_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _l, _p],
     "sci_axpy": [_p, _f, _p, _p, _l, _p],

@@ -6,8 +6,10 @@ and return convention.  The solvers call it as ``test_ddnet(oneCh2ThreeCh(x_baye
 native solver uses ``demosaic_planar`` on the frame-planar mosaic directly (the sum over the three sparse colour planes
 that DDnet forms first, network_demosaicking.py:411-416, IS the mosaic).
 
-The optional self-supervised update (``args.dm_update``, DDnet_test.py:231-276), reachable only by calling
-``test_ddnet`` directly with an ``args`` object, is not built: it raises ``NotImplementedError``.
+The optional self-supervised update (``args.dm_update``, DDnet_test.py:231-276; reachable only by calling ``test_ddnet``
+directly with an ``args`` object) runs on the same engine: per step one training forward, the re-mosaicking loss
+``MSE(vnoisy, sites(out))`` (:208-216, :268), the full backward (all convolutions and the three mixing tensors), and one
+Adam step with a FRESH optimizer state (the reference constructs ``torch.optim.Adam`` inside the loop, :270).
 """
 import torch
 
@@ -16,6 +18,7 @@ from ._lib import SciError, call, ptr, stream
 from .network_demosaicking import DDnet
 
 NUM_IN_FR_EXT = 5          # DDnet_test.py:16
+last_losses = []
 
 
 def _unwrap(model):
@@ -46,16 +49,40 @@ def ddnet_seqdenoise(seq, windsize, model):
     return demosaic_planar(rgb_sum(seq), model).clone()
 
 
+def update_and_demosaic(planar, model, lr, update_per_iter):
+    """planar [B,3,H,W] sparse-RGB input.  ``update_per_iter`` self-supervised steps, then the demosaicked sequence."""
+    eng = _unwrap(model).engine()
+    B, _, H, W = planar.shape
+    mosaic = rgb_sum(planar)
+    loss = torch.zeros(update_per_iter, dtype=torch.float64, device=planar.device)
+    dout = eng.ws.get("dd_dout", (B, 3, H, W), planar.device)
+    for it in range(update_per_iter):
+        out = eng.forward(mosaic, train=True)                                         # :259-261
+        call("sci_ddnet_loss_fwd_bwd", ptr(planar), ptr(out), ptr(dout), ptr(loss[it:it + 1]), B, H, W, stream())   # :266-268
+        eng.backward(dout)                                                            # :272
+        eng.bucket.new_optimizer()                                                    # :270 a fresh Adam every step
+        eng.bucket.adam_step(lr)                                                      # :273
+        eng.after_step()
+    last_losses[:] = [loss]
+    return eng.forward(mosaic, train=False)                                           # :279-282
+
+
 def test_ddnet(vnoisy, yall, Phiall, model=None, useGPU=True, args=None, gray=False):
-    """vnoisy [H,W,3,B] (sparse RGB mosaic, pixel-last as in the reference) -> demosaicked [H,W,3,B]."""
+    """vnoisy [H,W,3,B] (sparse RGB mosaic, pixel-last as in the reference) -> demosaicked [H,W,3,B]
+    (``(out, model)`` when ``args.dm_update``)."""
     if not useGPU:
         raise SciError("the B200 path has no CPU mode")
     if gray:
         raise NotImplementedError("DDnet demosaics Bayer mosaics; gray=True is not a path of the reference solvers")
-    if args is not None and getattr(args, "dm_update", False):
-        raise NotImplementedError("online update of the demosaicker (args.dm_update) is not built; the solvers never "
-                                  "enable it (dvp_linear_inv_2_stage_ADMM_tensor_online.py:193,243 pass no args)")
+    updata_ = bool(args is not None and args.dm_update)
     H, W, C, B = vnoisy.shape
     planar = ops.pixlast_to_planar(vnoisy.contiguous().float(), C, B).view(B, C, H, W)
-    out = demosaic_planar(rgb_sum(planar), model)
-    return ops.planar_to_pixlast(out, 3, B).view(H, W, 3, B)
+    if updata_:
+        out = update_and_demosaic(planar, model, args.dm_lr, args.dm_update_per_iter)
+        for val in last_losses[0].cpu().numpy():
+            print('ddn loss:', end=' ')
+            print('tensor(%.4e)' % val)
+    else:
+        out = demosaic_planar(rgb_sum(planar), model)
+    outv = ops.planar_to_pixlast(out, 3, B).view(H, W, 3, B)
+    return (outv, model) if updata_ else outv

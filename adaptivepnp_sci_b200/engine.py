@@ -560,17 +560,20 @@ class DDnetEngine(_EngineBase):
                     for i, (c, r, st, ps) in enumerate(module.temp11.fusion_specs())]
         super().__init__(module, self.t1 + self.t11 + self.fus + self.t2)
 
-    def _body(self, L, a_in, N, H, W):
-        """The 16-conv U-shaped body shared by all DenBlock variants (:232-241): returns the last conv's output."""
+    def _body(self, L, a_in, N, H, W, keep=None):
+        """The 16-conv U-shaped body shared by all DenBlock variants (:232-241): returns the last conv's output.
+        ``keep`` (a tag): every activation gets its own buffer and the dict of them is returned too (training)."""
         dev = a_in.device
         g = self.ws.get
         h2, w2, h4, w4 = H // 2, W // 2, H // 4, W // 4
+        S = {"a_in": a_in}
 
         def run(i, x, n_h, n_w, name, residual=None, round_out=True):
             Li = L[i]
             ho, wo = (n_h // 2, n_w // 2) if Li.stride == 2 else ((n_h * 2, n_w * 2) if Li.ps else (n_h, n_w))
-            y = g("dd_" + name, (N, ho, wo, Li.out_ch), dev)
+            y = g(("dd_%s_%s" % (keep, name)) if keep else ("dd_" + name), (N, ho, wo, Li.out_ch), dev)
             self.conv(Li, x, N, n_h, n_w, y, residual=residual, round_out=round_out)
+            S[name] = y
             return y
         a0 = run(0, a_in, H, W, "a0")
         x0 = run(1, a0, H, W, "x0")
@@ -587,46 +590,133 @@ class DDnetEngine(_EngineBase):
         u1b = run(12, u1a, h2, w2, "u1b")
         s0 = run(13, u1b, h2, w2, "s0", residual=x0)
         o0 = run(14, s0, H, W, "o0")
-        return run(15, o0, H, W, "xo", round_out=False)
+        xo = run(15, o0, H, W, "xo", round_out=False)
+        return (xo, S) if keep else xo
 
-    def forward(self, mosaic):
-        """mosaic [B,H,W] planar (whole circular sequence) -> demosaicked [B,3,H,W]."""
+    def _layer_bwd(self, Li, dy, y, x_in, N, Hin, Win, dx_name, residual=None, want_dx=True):
+        """Backward of one conv layer given dy w.r.t. its stored output y: weight gradient, then dx (w.r.t. its input)."""
+        dev = dy.device
+        Ho, Wo = (Hin // 2, Win // 2) if Li.stride == 2 else (Hin, Win)
+        dz = self.act_bwd(Li, dy, y, N * Ho * Wo, Li.Co_pad)
+        self.wgrad(Li, x_in, dz, N, Hin, Win)
+        dx = None
+        if want_dx:
+            dx = self.ws.get(dx_name, (N, Hin, Win, Li.Ci_pad), dev)
+            if Li.stride == 2:
+                self.dgrad_s2(Li, dz, N, Ho, Wo, dx, residual)
+            else:
+                self.dgrad(Li, dz, N, Ho, Wo, dx, residual)
+        self.param_grads(Li)
+        return dx
+
+    def _body_backward(self, L, S, d_xo, N, H, W, want_dx, tag):
+        """Adjoint of _body: parameter gradients of its 16 convs; returns d loss / d a_in (or None)."""
+        dev = d_xo.device
+        g = self.ws.get
+        h2, w2, h4, w4 = H // 2, W // 2, H // 4, W // 4
+        nm = lambda n: "ddg_%s_%s" % (tag, n)
+        bw = self._layer_bwd
+        d_o0 = bw(L[15], d_xo, None, S["o0"], N, H, W, nm("f_a"))
+        d_s0 = bw(L[14], d_o0, S["o0"], S["s0"], N, H, W, nm("f_b"))
+        # s0 = x0 + PixelShuffle(conv13(u1b)): the gradient of the GEMM output is the pixel-unshuffle of d_s0
+        d_c13 = g(nm("c13"), (N, h2, w2, L[13].Co_pad), dev)
+        call("sci_nhwc_pixel_unshuffle", ptr(d_s0), ptr(d_c13), N, h2, w2, L[13].out_ch, stream())
+        d_u1b = bw(L[13], d_c13, None, S["u1b"], N, h2, w2, nm("h_a"))
+        d_u1a = bw(L[12], d_u1b, S["u1b"], S["u1a"], N, h2, w2, nm("h_b"))
+        d_s1 = bw(L[11], d_u1a, S["u1a"], S["s1"], N, h2, w2, nm("h_a"))
+        d_c10 = g(nm("c10"), (N, h4, w4, L[10].Co_pad), dev)
+        call("sci_nhwc_pixel_unshuffle", ptr(d_s1), ptr(d_c10), N, h4, w4, L[10].out_ch, stream())
+        d_u2b = bw(L[10], d_c10, None, S["u2b"], N, h4, w4, nm("q_a"))
+        d_u2a = bw(L[9], d_u2b, S["u2b"], S["u2a"], N, h4, w4, nm("q_b"))
+        d_x2 = bw(L[8], d_u2a, S["u2a"], S["x2"], N, h4, w4, nm("q_a"))
+        d_d1b = bw(L[7], d_x2, S["x2"], S["d1b"], N, h4, w4, nm("q_b"))
+        d_d1a = bw(L[6], d_d1b, S["d1b"], S["d1a"], N, h4, w4, nm("q_a"))
+        d_x1 = bw(L[5], d_d1a, S["d1a"], S["x1"], N, h2, w2, nm("h_b"), residual=d_s1)     # x1 also feeds the skip into s1
+        d_d0b = bw(L[4], d_x1, S["x1"], S["d0b"], N, h2, w2, nm("h_a"))
+        d_d0a = bw(L[3], d_d0b, S["d0b"], S["d0a"], N, h2, w2, nm("h_b"))
+        d_x0 = bw(L[2], d_d0a, S["d0a"], S["x0"], N, H, W, nm("f_a"), residual=d_s0)
+        d_a0 = bw(L[1], d_x0, S["x0"], S["a0"], N, H, W, nm("f_w"))
+        return bw(L[0], d_a0, S["a0"], S["a_in"], N, H, W, nm("f_in"), want_dx=want_dx)
+
+    def forward(self, mosaic, train=False):
+        """mosaic [B,H,W] planar (whole circular sequence) -> demosaicked [B,3,H,W].  train=True keeps the activations."""
         B, H, W = mosaic.shape
         if H % 8 or W % 8:
             raise NotImplementedError("native DDnet engine needs H, W multiples of 8 (half-resolution path with two "
                                       "stride-2 levels; the reference reflect-pads to 4, DDnet_test.py:180-187, and "
                                       "would itself fail on sizes that are not multiples of 8)")
-        self.prepare(training=False)
+        self.prepare(training=train)
         dev = mosaic.device
         m = self.module
         a, a2, a3 = m.weight_tensor_in.data, m.weight_tensor_in2.data, m.weight_tensor_out.data
         sp = int(self.tf32)
         g = self.ws.get
-        t2in = g("dd_t2in", (2 * B, H, W, 32), dev)
-        res1, res2 = g("dd_res1", (B, 3, H, W), dev), g("dd_res2", (B, 3, H, W), dev)
+        t = "tr_" if train else ""
+        t2in = g("dd_%st2in" % t, (2 * B, H, W, 32), dev)
+        res1, res2 = g("dd_%sres1" % t, (B, 3, H, W), dev), g("dd_%sres2" % t, (B, 3, H, W), dev)
         # path 1: full-resolution single-channel triples
-        in1 = g("dd_in1", (3 * B, H, W, 32), dev)
+        in1 = g("dd_%sin1" % t, (3 * B, H, W, 32), dev)
         call("sci_ddnet_pack_input1", ptr(mosaic), ptr(a), ptr(in1), B, H, W, 32, sp, stream())
-        xo1 = self._body(self.t1, in1, 3 * B, H, W)
+        r1 = self._body(self.t1, in1, 3 * B, H, W, keep="t1" if train else None)
+        xo1, S1 = r1 if train else (r1, None)
         call("sci_ddnet_stage2_input", ptr(mosaic), ptr(a), ptr(xo1), xo1.shape[-1], ptr(t2in), ptr(res1), B, H, W, 32, sp,
              stream())
         # path 2: half-resolution RGGB planes, residual, bilinear x2, fusion convs
-        in4 = g("dd_in4", (3 * B, H // 2, W // 2, 32), dev)
+        in4 = g("dd_%sin4" % t, (3 * B, H // 2, W // 2, 32), dev)
         call("sci_ddnet_pack_input4", ptr(mosaic), ptr(a2), ptr(in4), B, H, W, 32, sp, stream())
-        xo4 = self._body(self.t11, in4, 3 * B, H // 2, W // 2)
-        up = g("dd_up", (3 * B, H, W, 32), dev)
+        r4 = self._body(self.t11, in4, 3 * B, H // 2, W // 2, keep="t11" if train else None)
+        xo4, S4 = r4 if train else (r4, None)
+        up = g("dd_%sup" % t, (3 * B, H, W, 32), dev)
         call("sci_ddnet_upsample4", ptr(mosaic), ptr(a2), ptr(xo4), xo4.shape[-1], ptr(up), B, H, W, 32, sp, stream())
-        f0 = g("dd_f0", (3 * B, H, W, self.fus[0].out_ch), dev)
+        f0 = g("dd_%sf0" % t, (3 * B, H, W, self.fus[0].out_ch), dev)
         self.conv(self.fus[0], up, 3 * B, H, W, f0)
-        xf = g("dd_xf", (3 * B, H, W, self.fus[1].out_ch), dev)
+        xf = g("dd_%sxf" % t, (3 * B, H, W, self.fus[1].out_ch), dev)
         self.conv(self.fus[1], f0, 3 * B, H, W, xf, round_out=False)
         call("sci_ddnet_stage2_input", None, None, ptr(xf), xf.shape[-1], ptr(t2in[B:]), ptr(res2), B, H, W, 32, sp, stream())
         # temp2 on both paths (one batch of 2B), then the learnable output mix
-        xo2 = self._body(self.t2, t2in, 2 * B, H, W)
-        out = g("dd_out", (B, 3, H, W), dev)
+        r2 = self._body(self.t2, t2in, 2 * B, H, W, keep="t2" if train else None)
+        xo2, S2 = r2 if train else (r2, None)
+        out = g("dd_%sout" % t, (B, 3, H, W), dev)
         call("sci_ddnet_output", ptr(res1), ptr(res2), ptr(xo2), xo2.shape[-1], ptr(a3), ptr(out), B, H, W, stream())
         self.n_launch += 6
+        if train:
+            self._saved = dict(mosaic=mosaic, B=B, H=H, W=W, S1=S1, S4=S4, S2=S2, up=up, f0=f0, xf=xf, res1=res1, res2=res2, xo2=xo2)
         return out
+
+    def backward(self, dout):
+        """Gradients of ALL trained parameters (convs of temp1 / temp11 / fusion / temp2 and the three mixing tensors) into
+        the flat grad bucket, given d loss / d output [B,3,H,W]."""
+        sv = self._saved
+        mosaic, B, H, W = sv["mosaic"], sv["B"], sv["H"], sv["W"]
+        dev = dout.device
+        m = self.module
+        g = self.ws.get
+        gv = self.bucket.grad_view
+        da, da2, da3 = gv(m.weight_tensor_in), gv(m.weight_tensor_in2), gv(m.weight_tensor_out)
+        da.zero_(); da2.zero_(); da3.zero_()
+        self.dw_flat.zero_()
+        # output mix and the two residual adds of temp2
+        d_xo2 = g("ddg_xo2", (2 * B, H, W, 32), dev)
+        d_res1, d_res2 = g("ddg_res1", (B, 3, H, W), dev), g("ddg_res2", (B, 3, H, W), dev)
+        call("sci_ddnet_output_bwd", ptr(dout), ptr(sv["res1"]), ptr(sv["res2"]), ptr(sv["xo2"]), sv["xo2"].shape[-1],
+             ptr(m.weight_tensor_out.data), ptr(d_xo2), ptr(d_res1), ptr(d_res2), ptr(da3), B, H, W, stream())
+        d_t2in = self._body_backward(self.t2, sv["S2"], d_xo2, 2 * B, H, W, True, "t2")
+        # path 1
+        d_xo1 = g("ddg_xo1", (3 * B, H, W, 32), dev)
+        call("sci_ddnet_stage2_input_bwd", ptr(d_t2in), ptr(d_res1), ptr(mosaic), ptr(d_xo1), ptr(da), B, H, W, stream())
+        d_in1 = self._body_backward(self.t1, sv["S1"], d_xo1, 3 * B, H, W, True, "t1")
+        call("sci_ddnet_pack_input1_bwd", ptr(d_in1), ptr(mosaic), ptr(da), B, H, W, stream())
+        # path 2: fusion convs, bilinear up-sampling, residual, temp11
+        d_xf = g("ddg_xf", (3 * B, H, W, 32), dev)
+        call("sci_ddnet_stage2_input_bwd", ptr(d_t2in[B:]), ptr(d_res2), None, ptr(d_xf), None, B, H, W, stream())
+        d_f0 = self._layer_bwd(self.fus[1], d_xf, None, sv["f0"], 3 * B, H, W, "ddg_f0")
+        d_up = self._layer_bwd(self.fus[0], d_f0, sv["f0"], sv["up"], 3 * B, H, W, "ddg_up")
+        d_y4 = g("ddg_y4", (3 * B, H // 2, W // 2, 32), dev, zero=True)
+        call("sci_ddnet_upsample4_bwd", ptr(d_up), ptr(d_y4), B, H, W, stream())
+        call("sci_ddnet_pack_input4_bwd", ptr(d_y4), ptr(mosaic), ptr(da2), B, H, W, 1, stream())
+        d_in4 = self._body_backward(self.t11, sv["S4"], d_y4, 3 * B, H // 2, W // 2, True, "t11")
+        call("sci_ddnet_pack_input4_bwd", ptr(d_in4), ptr(mosaic), ptr(da2), B, H, W, 0, stream())
+        self.n_launch += 8
 
     def forward_window(self, x):
         """Reference call convention model(x[1,15,H,W]) for ONE 5-frame window (network_demosaicking.py:406-463);

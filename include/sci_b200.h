@@ -292,6 +292,23 @@ int sci_ddnet_upsample4(const float* mosaic, const float* a2, const float* xo4, 
                         int W, int Cpad, int split_tf32, void* stream);
 int sci_ddnet_output(const float* res1, const float* res2, const float* xo2, int xo_cpad, const float* a3, float* out,
                      int B, int H, int W, void* stream);
+/* Backward of the DDnet boundary (self-supervised demosaicker update, DDnet_test.py:231-276).
+ *   loss_fwd_bwd     : loss += mean over [B][3][H][W] of (v - site(out))^2, site() keeps the RGGB site of each channel
+ *                      (DDnet_test.py:208-216, :268); dout (may be NULL) = d loss / d out
+ *   output_bwd       : adjoint of sci_ddnet_output: d_xo2 [2B][H][W][32], d_res1/d_res2 [B][3][H][W], da3[6] += ...
+ *   stage2_input_bwd : adjoint of sci_ddnet_stage2_input for one path: d_xo [3B][H][W][32]; path 1 also da[3j+1] += ...
+ *   pack_input1_bwd  : da[3j+k] += <d_in1[jB+f][.][k], mosaic[(f-2+j+k) mod B]>
+ *   pack_input4_bwd  : da2[(3j+k)*4+ib] += ...; centre_only = 1 treats d4 as the gradient of y4 = in1 + xo4 (slot k = 1)
+ *   upsample4_bwd    : adjoint of the bilinear x2 up-sampling, scattered (atomics) into the ZEROED d_y4 [3B][H/2][W/2][32]
+ * The scalar-gradient slots (da, da2, da3) are accumulated with atomics and must be zeroed by the caller. */
+int sci_ddnet_loss_fwd_bwd(const float* v, const float* out, float* dout, double* loss, int B, int H, int W, void* stream);
+int sci_ddnet_output_bwd(const float* dout, const float* res1, const float* res2, const float* xo2, int xo_cpad, const float* a3,
+                         float* d_xo2, float* d_res1, float* d_res2, float* da3, int B, int H, int W, void* stream);
+int sci_ddnet_stage2_input_bwd(const float* d_t2in, const float* d_res, const float* mosaic, float* d_xo, float* da, int B, int H,
+                               int W, void* stream);
+int sci_ddnet_pack_input1_bwd(const float* d_in1, const float* mosaic, float* da, int B, int H, int W, void* stream);
+int sci_ddnet_pack_input4_bwd(const float* d4, const float* mosaic, float* da2, int B, int H, int W, int centre_only, void* stream);
+int sci_ddnet_upsample4_bwd(const float* d_up, float* d_y4, int B, int H, int W, void* stream);
 /* training input of the FastDVDnet fine-tune (test_fastdvdnet.py:359 with utils_image.py:183-192):
  * vplus = v + float32(float64(v) + noise), noise float64 from the host RNG. */
 int sci_fastdvd_noisy_input(const float* v, const double* noise, float* vplus, long n, void* stream);

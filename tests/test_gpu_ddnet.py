@@ -55,10 +55,35 @@ def test_ddnet_adapter(cuda, impl):
     assert out.shape == (32, 48, 3, 8)
     assert np.max(np.abs(out.cpu().numpy() - d["ad_inf"])) < TOL[impl]
 
+
+
+def test_ddnet_self_supervised_update(cuda, impl):
+    """args.dm_update (DDnet_test.py:231-276): two update steps (fresh Adam each), losses, updated weights incl. the mixing
+    tensors, and the output after the update, against the reference's values."""
+    from adaptivepnp_sci_b200 import ddnet_adapter
+    from adaptivepnp_sci_b200.utils_image import oneCh2ThreeCh
+    d = np.load(os.path.join(G, "ddnet.npz"))
+    v = oneCh2ThreeCh(torch.from_numpy(d["ad_mosaic"]).cuda())
+    lr = 1e-5
+
     class Args:
-        dm_lr, dm_update_per_iter, dm_update = 1e-5, 2, True
-    with pytest.raises(NotImplementedError):
-        ddnet_plugin(v, None, None, _ddnet(cuda), True, Args)
+        dm_lr, dm_update_per_iter, dm_update = lr, 2, True
+    m = _ddnet(cuda)
+    before = {k: t.clone() for k, t in m.state_dict().items()}
+    out, m2 = ddnet_adapter.test_ddnet(v, None, None, m, True, Args)
+    assert m2 is m and out.shape == (32, 48, 3, 8)
+    tol = {"ref": 5e-5, "tc": 1e-3}[impl]
+    assert np.max(np.abs(out.cpu().numpy() - d["ad_upd"])) < tol
+    losses = ddnet_adapter.last_losses[0].cpu().numpy()
+    assert np.allclose(losses, d["ad_losses"], rtol={"ref": 1e-5, "tc": 2e-3}[impl])
+    for key, gold in (("module.temp1.inc_1.convblock.0.weight", d["ad_w_first_after"]),
+                      ("module.weight_tensor_in2", d["ad_mix_after"])):
+        w = m.state_dict()[key].cpu().numpy()
+        assert np.max(np.abs(w - gold)) <= 2 * 2 * lr * 1.01           # 2 Adam steps of at most ~lr each, either sign
+        assert np.mean(np.abs(w - gold)) < 0.15 * lr
+        assert float((m.state_dict()[key] - before[key]).abs().max()) > 0.5 * lr        # it did train
+    # the never-executed noise-map input blocks keep their weights (torch skips parameters without gradient)
+    assert torch.equal(m.state_dict()["module.temp1.inc.convblock.0.weight"], before["module.temp1.inc.convblock.0.weight"])
 
 
 def test_stage2_with_deep_demosaic(cuda, impl):
