@@ -48,6 +48,7 @@ PROTOTYPES = {
     "sci_bayer4_to_mosaic": [_p, _p, _i, _i, _i, _p],
     "sci_mosaic_to_bayer4": [_p, _p, _i, _i, _i, _p],
     "sci_psnr_accum": [_p, _p, _l, _i, _p, _p],
+    "sci_ssim_accum": [_p, _p, _i, _i, _i, _d, _p, _p],
     "sci_conv_tc_available": [],
     "sci_conv3x3_fwd": [_p, _i, _p],
     "sci_conv3x3_dgrad": [_p, _i, _p],

@@ -633,3 +633,49 @@ extern "C" int sci_psnr_accum(const float* a, const float* orig, long npix, int 
     SCI_CHECK_LAUNCH("psnr_accum");
     return SCI_OK;
 }
+
+
+// ---------------------------------------------------------------------------
+// On-device SSIM for the final per-frame report (dvp:321; skimage.metrics.structural_similarity defaults restated in
+// oracle/iqa.py: 7x7 uniform window, sample covariance, K1 = .01, K2 = .03, float64, mean over the image cropped by 3).
+// Each thread evaluates S at one pixel of the crop from the 49-tap window sums in fp64 (the crop never touches the
+// image border, so the filter's border mode is irrelevant); per-frame sums are block-reduced and added atomically.
+// ssim_sum[t] += sum of S over the crop of frame t;  the caller divides by (H-6)*(W-6).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ssim_kernel(const float* __restrict__ a, const float* __restrict__ ref, int H, int W,
+                                                    double C1, double C2, double* __restrict__ ssim_sum) {
+    __shared__ double red[32];
+    const int t = blockIdx.z;
+    const long plane = (long)H * W;
+    const int col = blockIdx.x * 32 + (threadIdx.x & 31) + 3, row = blockIdx.y * 8 + (threadIdx.x >> 5) + 3;
+    double S = 0.0;
+    if (col < W - 3 && row < H - 3) {
+        const float* pa = a + t * plane + (long)(row - 3) * W + (col - 3);
+        const float* pr = ref + t * plane + (long)(row - 3) * W + (col - 3);
+        double sx = 0.0, sy = 0.0, sxx = 0.0, syy = 0.0, sxy = 0.0;
+        for (int dy = 0; dy < 7; ++dy) {
+#pragma unroll
+            for (int dx = 0; dx < 7; ++dx) {
+                const double x = (double)pr[dy * W + dx], y = (double)pa[dy * W + dx];     // X = reference image, Y = result
+                sx += x; sy += y; sxx += x * x; syy += y * y; sxy += x * y;
+            }
+        }
+        const double inv = 1.0 / 49.0, cov_norm = 49.0 / 48.0;
+        const double ux = sx * inv, uy = sy * inv;
+        const double vx = cov_norm * (sxx * inv - ux * ux), vy = cov_norm * (syy * inv - uy * uy);
+        const double vxy = cov_norm * (sxy * inv - ux * uy);
+        S = ((2.0 * ux * uy + C1) * (2.0 * vxy + C2)) / ((ux * ux + uy * uy + C1) * (vx + vy + C2));
+    }
+    const double sblk = block_sum(S, red);
+    if (threadIdx.x == 0) atomicAdd(ssim_sum + t, sblk);
+}
+
+extern "C" int sci_ssim_accum(const float* a, const float* ref, int H, int W, int B, double data_range, double* ssim_sum,
+                              void* stream) {
+    SCI_REQUIRE(a && ref && ssim_sum && H >= 7 && W >= 7 && B > 0 && B <= 65535, "ssim_accum");
+    const double C1 = (0.01 * data_range) * (0.01 * data_range), C2 = (0.03 * data_range) * (0.03 * data_range);
+    ssim_kernel<<<dim3(sci_ceil_div(W - 6, 32), sci_ceil_div(H - 6, 8), B), 256, 0, sci_stream(stream)>>>(a, ref, H, W, C1, C2,
+                                                                                                          ssim_sum);
+    SCI_CHECK_LAUNCH("ssim_accum");
+    return SCI_OK;
+}

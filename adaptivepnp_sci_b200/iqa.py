@@ -1,11 +1,12 @@
-"""Image-quality reporting used by the solvers (PSNR from device-side SSE, host SSIM).
+"""Image-quality reporting used by the solvers (PSNR from device-side SSE, SSIM on the device).
 
 The reference obtains both from scikit-image on the host after a D2H copy in
 every iteration (dvp_linear_inv_2_stage_ADMM_tensor_online.py:274-281,:318-321).
 Here the squared-error sums are accumulated on the device (``sci_psnr_accum`` and
 the fused kernels) and only scalars cross PCIe; SSIM (7x7 uniform window, sample
-covariance, K1=.01, K2=.03, float64) is evaluated once per reconstruction on the
-host for reporting — an on-device SSIM is SURVEY §8(f).4 (next).
+covariance, K1=.01, K2=.03, float64) is evaluated once per reconstruction by
+``sci_ssim_accum`` on the device.  ``ssim`` below is the host
+restatement kept for the tiled multi-GPU gather path and for cross-checks.
 """
 import numpy as np
 from scipy.ndimage import uniform_filter

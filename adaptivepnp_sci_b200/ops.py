@@ -133,6 +133,15 @@ def psnr_accum(a, orig, sse_per_frame):
     call("sci_psnr_accum", ptr(a), ptr(orig), npix, B, ptr(sse_per_frame), stream())
 
 
+def ssim_frames(a, orig):
+    """Per-frame SSIM (skimage defaults, float64) of a [B,H,W] against orig [B,H,W], computed on the device -> [B] float64."""
+    require_cuda_f32(a, orig)
+    B, H, W = a.shape
+    acc = torch.zeros(B, dtype=torch.float64, device=a.device)
+    call("sci_ssim_accum", ptr(a), ptr(orig), H, W, B, 1.0, ptr(acc), stream())
+    return acc / float((H - 6) * (W - 6))
+
+
 def axpy(x, a, y, out=None):
     """out = x + a*y (elementwise, fp32)."""
     require_cuda_f32(x, y, out)

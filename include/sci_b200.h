@@ -149,6 +149,11 @@ int sci_mosaic_to_bayer4(const float* mosaic, float* stack, int h, int w, int B,
  * fp32 difference and square, fp64 accumulation (skimage PSNR restated). */
 int sci_psnr_accum(const float* a, const float* orig, long npix, int B, double* sse_per_frame,
                    void* stream);
+/* Per-frame SSIM of the final report (dvp...online.py:321; skimage structural_similarity defaults: 7x7 uniform window,
+ * sample covariance, K1 = .01, K2 = .03, float64, mean over the image cropped by 3 pixels), evaluated on the device:
+ * ssim_sum[t] += sum of the SSIM map over the crop of frame t (divide by (H-6)*(W-6)).  a, ref [B][H][W]. */
+int sci_ssim_accum(const float* a, const float* ref, int H, int W, int B, double data_range, double* ssim_sum,
+                   void* stream);
 
 
 /* =========================================================================

@@ -216,3 +216,17 @@ def test_psnr_accum(cuda):
     for t in range(5):
         assert abs(got[t] - oiqa.compare_psnr(o[t].numpy(), a[t].numpy(), 1.)) < 1e-9
     assert abs(iqa.ssim(a[0].numpy(), o[0].numpy()) - oiqa.compare_ssim(a[0].numpy(), o[0].numpy())) < 1e-12
+
+
+def test_ssim_on_device_matches_oracle(cuda):
+    """sci_ssim_accum against the oracle's restatement of skimage's structural_similarity (float64)."""
+    from adaptivepnp_sci_b200 import ops
+    from oracle import iqa, synthetic
+    _, _, orig = synthetic.make_case(64, 96, 4, 11, bayer=True)
+    rng = np.random.default_rng(3)
+    rec = np.clip(orig + 0.05 * rng.standard_normal(orig.shape), 0, 1).astype(np.float32)
+    a = torch.from_numpy(rec).permute(2, 0, 1).contiguous().cuda()
+    o = torch.from_numpy(orig).permute(2, 0, 1).contiguous().cuda()
+    got = ops.ssim_frames(a, o).cpu().numpy()
+    want = np.array([iqa.compare_ssim(orig[:, :, t], rec[:, :, t], data_range=1.) for t in range(4)])
+    assert np.max(np.abs(got - want)) < 1e-10
