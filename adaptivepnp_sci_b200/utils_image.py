@@ -20,8 +20,14 @@ def np2tch_cuda(a):
 
 
 def cuda2np(a):
-    """utils_image.py:95."""
-    return a.cpu().detach().numpy()
+    """utils_image.py:95.  Large results are read back through a pinned staging tensor (one DMA at PCIe speed instead of
+    the staged pageable path); the returned numpy array owns that buffer."""
+    a = a.detach()
+    if a.is_cuda and a.numel() * a.element_size() >= (1 << 20):
+        host = torch.empty(a.shape, dtype=a.dtype, pin_memory=True)
+        host.copy_(a, non_blocking=False)
+        return host.numpy()
+    return a.cpu().numpy()
 
 
 def masks_CFA_Bayer_tensor(shape, pattern='RGGB'):

@@ -194,10 +194,18 @@ def main():
         return twoStageAdmm_denoise_bayer(d_meas, d_mask, 1, 0.01, 'fastdvd_color', ITERS, False, SIGMA, x0_bayer=d_warm,
                                           X_orig=None, show_iqa=False, return_device=True, **kw)
 
+    # end-to-end arm: the step's inputs start in PINNED host memory (numpy views of pinned tensors) and go through the
+    # public call, which uploads them, and whose results come back as host arrays
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.float32, pin_memory=True)
+        t.copy_(torch.from_numpy(a))
+        return t
+    p_meas, p_mask, p_warm = pinned(meas), pinned(mask), pinned(warm)
+
     def step_e2e():
         reset_model()
-        return twoStageAdmm_denoise_bayer(meas, mask, 1, 0.01, 'fastdvd_color', ITERS, False, SIGMA,
-                                          x0_bayer=torch.from_numpy(warm).cuda(), X_orig=None, show_iqa=False, logf=None, **kw)
+        return twoStageAdmm_denoise_bayer(p_meas.numpy(), p_mask.numpy(), 1, 0.01, 'fastdvd_color', ITERS, False, SIGMA,
+                                          x0_bayer=p_warm.to(dev, non_blocking=True), X_orig=None, show_iqa=False, logf=None, **kw)
 
     def barrier():
         if world > 1:
