@@ -30,6 +30,10 @@ constexpr int TV_NPIX = TV_RW * TV_RH;     // 3840
 constexpr int TV_ROWGROUPS = 4;            // 80 columns x 4 row groups
 constexpr int TV_THREADS = TV_RW * TV_ROWGROUPS;   // 320
 constexpr int TV_MAX_UPD = 4;              // out_1..out_4 are the candidate results
+#ifndef TV_UNROLL
+#define TV_UNROLL 4                        // row-loop unrolling: independent pixels in flight hide the sqrt / divide latency
+#endif
+constexpr int TV_UNROLL_N = TV_UNROLL;
 
 // workspace: double epart[B][4 iters][2 kinds][4 phases][nblk], then int nstop[B*4]
 __host__ __device__ inline size_t tv_epart_count(int B, int nblk) { return (size_t)B * 4 * 2 * 4 * nblk; }
@@ -95,6 +99,7 @@ __global__ void __launch_bounds__(TV_THREADS) tv_chambolle_kernel(
         // ---- phase A: d = -div p, out = f + d (it > 0); write the result of the channels stopping here
         if (it > 0) {
             if (t_active) {
+#pragma unroll TV_UNROLL_N
                 for (int rr = ry; rr < TV_RH; rr += TV_ROWGROUPS) {
                     const int gr = gr0 + rr, i = rr * TV_RW + cx;
                     float d = -(sp0[i] + sp1[i]);
@@ -124,6 +129,7 @@ __global__ void __launch_bounds__(TV_THREADS) tv_chambolle_kernel(
         if (it == TV_MAX_UPD || it == last_iter) break;   // the last dual update never shapes the result
         // ---- phase B: forward differences, energy, dual update
         if (t_active) {
+#pragma unroll TV_UNROLL_N
             for (int rr = ry; rr < TV_RH; rr += TV_ROWGROUPS) {
                 const int gr = gr0 + rr, i = rr * TV_RW + cx;
                 const bool in_img = col_in && gr >= 0 && gr < H;
