@@ -80,7 +80,8 @@ def _host_buffer(n):
     """float64 host array for the noise.  On a GPU box it lives in PINNED memory (torch's caching host allocator), so the
     upload in ``finetune_and_denoise`` is one asynchronous DMA instead of a staged, blocking pageable copy (2 x 50 MB per
     reconstruction at 512x512x8); the numpy view keeps the owning tensor alive."""
-    if torch.cuda.is_available() and os.environ.get("SCI_NOISE_PINNED", "1") != "0":
+    # (whole-frame draws of the tiled mode are gigabytes per rank: page-locking those costs more than it saves)
+    if n <= (1 << 25) and torch.cuda.is_available() and os.environ.get("SCI_NOISE_PINNED", "1") != "0":
         try:
             return torch.empty(n, dtype=torch.float64, pin_memory=True).numpy()
         except RuntimeError:
