@@ -306,8 +306,12 @@ class FFDNetEngine(_EngineBase):
         for i, c in enumerate(convs):
             last = i == len(convs) - 1
             # FFDNet returns the denoised image itself (no residual), so weight-rounding error reaches the output
-            # undamped: on the TF32 path its weights are kept as tf32 hi + remainder (north_star 1e-3 max-abs bound)
-            layers.append(ConvLayer(c, None, relu=not last, first=(i == 0), wsplit=(default_impl() == IMPL_TC)))
+            # undamped: on the TF32 path its weights are kept as tf32 hi + remainder (north_star 1e-3 max-abs bound).
+            # This also holds for the TRAINING forward: with plain TF32 weights there (1.75 ms instead of 3.5 ms per pass at
+            # 8x512x512, tools/time_ffdnet_train.py) the Adam-normalised updates change enough to move the final
+            # reconstruction by 5e-3 on the golden online loop (3.4e-4 with the split), so the split stays on.
+            layers.append(ConvLayer(c, None, relu=not last, first=(i == 0), wsplit=(default_impl() == IMPL_TC)
+                                    and os.environ.get("SCI_FFDNET_TRAIN_WSPLIT", "1") != "0"))
         super().__init__(module, layers)
         # inference on the TF32 path uses "3xTF32": every activation is stored as tf32 hi + remainder and every weight
         # as tf32 hi + remainder, which brings the conv stack to ~fp32 accuracy (FFDNet has no residual connection, so
