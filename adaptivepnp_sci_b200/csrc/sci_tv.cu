@@ -18,6 +18,8 @@
 // rewrites the few channels that did.  No host involvement, 3 launches.
 //
 // Compiled with --fmad=false: the fp32 arithmetic mirrors numpy's separate ops.
+#include <stdlib.h>
+
 #include "sci_common.cuh"
 
 namespace {
@@ -181,6 +183,179 @@ __global__ void __launch_bounds__(TV_THREADS) tv_chambolle_kernel(
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Version 2 of the tile kernel (same maths, same interface, bit-identical interior results).  ncu on version 1
+// (profiles/ncu_r1_prof_tv_chambolle.csv): issue slots 65 % busy, DRAM 2 % — instruction-bound, and most instructions were
+// boundary predicates and address arithmetic.  Here
+//   * the four shared-memory arrays carry a 2-pixel zero border, so tile-edge neighbours need no predicate (halo pixels
+//     may then hold garbage one ring deeper per iteration, which the 8-pixel halo already budgets for);
+//   * image borders are handled by per-row / per-thread select masks (dual variables outside the image stay exactly 0);
+//   * a thread owns a PAIR of adjacent columns (the two column phases) of rows ry, ry+8, ..: every shared-memory access is
+//     one 64-bit load/store for two pixels and the address arithmetic is shared.
+// ---------------------------------------------------------------------------------------------------
+constexpr int TV2_P = TV_RW + 4;                   // padded row pitch (84, even: float2 aligned)
+constexpr int TV2_ROWS = TV_RH + 4;                // 52
+constexpr int TV2_N = TV2_P * TV2_ROWS;            // 4368 floats per array
+constexpr int TV2_PAIRS = TV_RW / 2;               // 40 column pairs
+constexpr int TV2_RG = TV_THREADS / TV2_PAIRS;     // 8 row groups
+constexpr int TV2_RPT = TV_RH / TV2_RG;            // 6 rows per thread
+
+__global__ void __launch_bounds__(TV_THREADS, 3) tv_chambolle2_kernel(
+    const float* __restrict__ x, const float* __restrict__ b, float c_b, float* __restrict__ theta,
+    float* __restrict__ b_out, float s_b, int clip, int H, int W, float tau, float tw, int last_iter,
+    double* __restrict__ epart, const int* __restrict__ nstop, int is_fix) {
+    extern __shared__ float smem[];
+    float* sf = smem;
+    float* so = sf + TV2_N;
+    float* sp0 = so + TV2_N;
+    float* sp1 = sp0 + TV2_N;
+    __shared__ int s_stop[4];
+
+    const int t = blockIdx.z;
+    const int nblk = gridDim.x * gridDim.y, blk = blockIdx.y * gridDim.x + blockIdx.x;
+    if (threadIdx.x < 4) s_stop[threadIdx.x] = is_fix ? nstop[t * 4 + threadIdx.x] : last_iter;
+    __syncthreads();
+    if (is_fix && s_stop[0] >= last_iter && s_stop[1] >= last_iter && s_stop[2] >= last_iter && s_stop[3] >= last_iter)
+        return;
+
+    const long plane = (long)H * W;
+    const float* xp = x + t * plane;
+    const float* bp = b ? b + t * plane : nullptr;
+    const int gr0 = blockIdx.y * TV_TH - TV_HALO, gc0 = blockIdx.x * TV_TW - TV_HALO;    // both even
+
+    // zero everything once (borders stay zero for the whole kernel)
+    {
+        float4* z = reinterpret_cast<float4*>(smem);
+        for (int i = threadIdx.x; i < 4 * TV2_N / 4; i += TV_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+
+    const int cx = (threadIdx.x % TV2_PAIRS) * 2, ry = threadIdx.x / TV2_PAIRS;
+    const int gc = gc0 + cx;                                  // even; the pair is (gc, gc+1) = column phases 0, 1
+    const bool col_in = gc >= 0 && gc < W;                    // W even: both columns in or both out
+    const bool col_right = col_in && gc + 2 < W;              // forward neighbour (c+2) exists in the image, for both
+    const bool col_interior = cx >= TV_HALO && cx < TV_HALO + TV_TW && gc < W;
+    const int rpar = ry & 1;                                  // gr0 even, rows advance by 8: fixed row parity per thread
+    const int base = (ry + 2) * TV2_P + cx + 2;               // smem index of (rr = ry, cx)
+
+    // ---- load f = x + c_b*b
+#pragma unroll
+    for (int k = 0; k < TV2_RPT; ++k) {
+        const int gr = gr0 + ry + k * TV2_RG, i = base + k * TV2_RG * TV2_P;
+        float2 v = make_float2(0.f, 0.f);
+        if (col_in && gr >= 0 && gr < H) {
+            v = *reinterpret_cast<const float2*>(xp + (long)gr * W + gc);
+            if (bp) {
+                const float2 bb = *reinterpret_cast<const float2*>(bp + (long)gr * W + gc);
+                v.x = v.x + c_b * bb.x; v.y = v.y + c_b * bb.y;
+            }
+        }
+        *reinterpret_cast<float2*>(sf + i) = v;
+        *reinterpret_cast<float2*>(so + i) = v;
+    }
+    __syncthreads();
+
+    double e_d[TV_MAX_UPD][2], e_n[TV_MAX_UPD][2];            // [iteration][column phase]
+#pragma unroll
+    for (int k = 0; k < TV_MAX_UPD; ++k) { e_d[k][0] = e_d[k][1] = e_n[k][0] = e_n[k][1] = 0.0; }
+    const int stop0 = s_stop[rpar * 2 + 0], stop1 = s_stop[rpar * 2 + 1];
+
+#pragma unroll
+    for (int it = 0; it <= TV_MAX_UPD; ++it) {
+        if (it > last_iter) break;
+        if (it > 0) {
+            // ---- phase A: d = -div p, out = f + d; write the result of the channels stopping here
+#pragma unroll 2
+            for (int k = 0; k < TV2_RPT; ++k) {
+                const int rr = ry + k * TV2_RG, gr = gr0 + rr, i = base + k * TV2_RG * TV2_P;
+                const float2 p0 = *reinterpret_cast<const float2*>(sp0 + i), p1 = *reinterpret_cast<const float2*>(sp1 + i);
+                const float2 pu = *reinterpret_cast<const float2*>(sp0 + i - 2 * TV2_P);
+                const float2 pl = *reinterpret_cast<const float2*>(sp1 + i - 2);
+                const float2 f = *reinterpret_cast<const float2*>(sf + i);
+                float dx = -(p0.x + p1.x), dy = -(p0.y + p1.y);
+                dx += pu.x; dy += pu.y;
+                dx += pl.x; dy += pl.y;
+                const float ox = f.x + dx, oy = f.y + dy;
+                *reinterpret_cast<float2*>(so + i) = make_float2(ox, oy);
+                if (col_interior && rr >= TV_HALO && rr < TV_HALO + TV_TH && gr < H) {
+                    if (it < TV_MAX_UPD && !is_fix) {
+                        e_d[it][0] += (double)(dx * dx);
+                        e_d[it][1] += (double)(dy * dy);
+                    }
+                    const long g = (long)gr * W + gc;
+                    const bool w0 = it == stop0 && (!is_fix || stop0 < last_iter);
+                    const bool w1 = it == stop1 && (!is_fix || stop1 < last_iter);
+                    if (w0 || w1) {
+                        float t0 = ox, t1 = oy;
+                        if (clip) { t0 = fminf(fmaxf(t0, 0.f), 1.f); t1 = fminf(fmaxf(t1, 0.f), 1.f); }
+                        if (w0 && w1) {
+                            *reinterpret_cast<float2*>(theta + t * plane + g) = make_float2(t0, t1);
+                            if (bp) {
+                                const float2 bb = *reinterpret_cast<const float2*>(bp + g), xx = *reinterpret_cast<const float2*>(xp + g);
+                                *reinterpret_cast<float2*>(b_out + t * plane + g) =
+                                    make_float2(bb.x + s_b * (xx.x - t0), bb.y + s_b * (xx.y - t1));
+                            }
+                        } else {
+                            const int j = w0 ? 0 : 1;
+                            const float th = w0 ? t0 : t1;
+                            theta[t * plane + g + j] = th;
+                            if (bp) b_out[t * plane + g + j] = bp[g + j] + s_b * (xp[g + j] - th);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (it == TV_MAX_UPD || it == last_iter) break;       // the last dual update never shapes the result
+        // ---- phase B: forward differences, energy, dual update
+#pragma unroll 2
+        for (int k = 0; k < TV2_RPT; ++k) {
+            const int rr = ry + k * TV2_RG, gr = gr0 + rr, i = base + k * TV2_RG * TV2_P;
+            const bool in_img = col_in && gr >= 0 && gr < H;
+            const bool has_dn = in_img && gr + 2 < H, has_rt = in_img && col_right;
+            const float2 o = *reinterpret_cast<const float2*>(so + i);
+            const float2 od = *reinterpret_cast<const float2*>(so + i + 2 * TV2_P);
+            const float2 orr = *reinterpret_cast<const float2*>(so + i + 2);
+            const float g0x = has_dn ? od.x - o.x : 0.f, g0y = has_dn ? od.y - o.y : 0.f;
+            const float g1x = has_rt ? orr.x - o.x : 0.f, g1y = has_rt ? orr.y - o.y : 0.f;
+            const float nx = sqrtf(g0x * g0x + g1x * g1x), ny = sqrtf(g0y * g0y + g1y * g1y);
+            if (col_interior && rr >= TV_HALO && rr < TV_HALO + TV_TH && gr < H && !is_fix) {
+                e_n[it][0] += (double)nx;
+                e_n[it][1] += (double)ny;
+            }
+            const float ix = 1.0f / (nx * tw + 1.0f), iy = 1.0f / (ny * tw + 1.0f);
+            const float2 p0 = *reinterpret_cast<const float2*>(sp0 + i), p1 = *reinterpret_cast<const float2*>(sp1 + i);
+            *reinterpret_cast<float2*>(sp0 + i) = in_img ? make_float2((p0.x - tau * g0x) * ix, (p0.y - tau * g0y) * iy)
+                                                         : make_float2(0.f, 0.f);
+            *reinterpret_cast<float2*>(sp1 + i) = in_img ? make_float2((p1.x - tau * g1x) * ix, (p1.y - tau * g1y) * iy)
+                                                         : make_float2(0.f, 0.f);
+        }
+        __syncthreads();
+    }
+
+    if (is_fix) return;
+    // ---- deterministic per-block energy partials: every thread parks its 16 sums in shared memory (the image arrays
+    //      are dead now), 32 threads add them up in a fixed order
+    __syncthreads();
+    double* sd = reinterpret_cast<double*>(smem);             // [TV_THREADS][16]
+#pragma unroll
+    for (int k = 0; k < TV_MAX_UPD; ++k) {
+        sd[threadIdx.x * 16 + k * 4 + 0] = e_d[k][0];
+        sd[threadIdx.x * 16 + k * 4 + 1] = e_d[k][1];
+        sd[threadIdx.x * 16 + k * 4 + 2] = e_n[k][0];
+        sd[threadIdx.x * 16 + k * 4 + 3] = e_n[k][1];
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        // thread -> (k, kind, row parity rp, column phase cp)
+        const int cp = threadIdx.x & 1, rp = (threadIdx.x >> 1) & 1, kind = (threadIdx.x >> 2) & 1, k = threadIdx.x >> 3;
+        double s = 0.0;
+        for (int g = rp; g < TV2_RG; g += 2)                  // row groups with this row parity
+            for (int c = 0; c < TV2_PAIRS; ++c) s += sd[(g * TV2_PAIRS + c) * 16 + k * 4 + kind * 2 + cp];
+        epart[((((size_t)t * 4 + k) * 2 + kind) * 4 + (rp * 2 + cp)) * nblk + blk] = s;
+    }
+}
+
 // One block per channel: fixed-order (deterministic) reduction of the per-block partials, then the
 // reference's stopping rule  |E_prev - E_i| < eps * E_init  (i >= 1).
 constexpr int TV_DEC_THREADS = 128;
@@ -246,14 +421,17 @@ extern "C" int sci_tv_chambolle2d(const float* x, const float* b, float c_b, flo
     const int nblk = grid.x * grid.y;
     double* epart = reinterpret_cast<double*>(workspace);
     int* nstop = reinterpret_cast<int*>(epart + tv_epart_count(B, nblk));
-    const size_t smem = (size_t)4 * TV_NPIX * sizeof(float);
-    static bool attr_set[64] = {};
+    const char* v2env = getenv("SCI_TV_V2");
+    const bool v2 = !(v2env && v2env[0] == '0');
+    auto kern = v2 ? tv_chambolle2_kernel : tv_chambolle_kernel;
+    const size_t smem = v2 ? (size_t)4 * TV2_N * sizeof(float) : (size_t)4 * TV_NPIX * sizeof(float);
+    static bool attr_set[64][2] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(tv_chambolle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (dev < 0 || dev >= 64 || !attr_set[dev][v2]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return sci_fail(SCI_ELAUNCH, "tv: smem attribute", e);
-        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+        if (dev >= 0 && dev < 64) attr_set[dev][v2] = true;
     }
     const int last_iter = n_iter_max - 1;              // index of the last iterate (4 for n_iter_max=5)
     const float tau = 0.25f;                            // 1/(2*ndim), ndim = 2
@@ -262,15 +440,13 @@ extern "C" int sci_tv_chambolle2d(const float* x, const float* b, float c_b, flo
         // n_iter_max = 1 returns the input unchanged
         return sci_fail(SCI_EUNSUPPORTED, "tv: n_iter_max = 1 is the identity; not routed through the kernel");
     }
-    tv_chambolle_kernel<<<grid, TV_THREADS, smem, st>>>(x, b, c_b, theta, b_out, s_b, clip, H, W, tau, tw, last_iter,
-                                                        epart, nullptr, 0);
+    kern<<<grid, TV_THREADS, smem, st>>>(x, b, c_b, theta, b_out, s_b, clip, H, W, tau, tw, last_iter, epart, nullptr, 0);
     SCI_CHECK_LAUNCH("tv main pass");
     const int nch = B * 4;
     tv_decide_kernel<<<nch, TV_DEC_THREADS, 0, st>>>(epart, nblk, (double)weight, (double)eps,
                                                      (double)(H / 2) * (double)(W / 2), last_iter, nstop, nstop_out);
     SCI_CHECK_LAUNCH("tv decide");
-    tv_chambolle_kernel<<<grid, TV_THREADS, smem, st>>>(x, b, c_b, theta, b_out, s_b, clip, H, W, tau, tw, last_iter,
-                                                        epart, nstop, 1);
+    kern<<<grid, TV_THREADS, smem, st>>>(x, b, c_b, theta, b_out, s_b, clip, H, W, tau, tw, last_iter, epart, nstop, 1);
     SCI_CHECK_LAUNCH("tv fix-up pass");
     return SCI_OK;
 }
