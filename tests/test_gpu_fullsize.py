@@ -76,3 +76,33 @@ def test_ddnet_forward_512(cuda, monkeypatch):
         torch.cuda.empty_cache()
     assert outs["tc"].shape == (8, 3, 512, 512)
     assert float((outs["tc"] - outs["ref"]).abs().max()) < 1e-3
+
+
+@pytest.mark.parametrize("shape", [(5, 72, 104), (3, 36, 200)])
+def test_fastdvdnet_ragged_shapes_tc_vs_fp32(cuda, monkeypatch, shape):
+    """Shapes that do not fill the 128-pixel tiles / R-row super-tiles / 8x8 weight-gradient tiles evenly: the tensor-core
+    engine against the fp32 FFMA engine (forward, measurement loss, all parameter gradients)."""
+    from adaptivepnp_sci_b200.ffdnet_adapter import _tile_loss
+    monkeypatch.setenv("SCI_CONV_IMPL", "tc")
+    B, H, W = shape
+    g = torch.Generator().manual_seed(B * 100 + H)
+    u = torch.rand(B, 3, H, W, generator=g).cuda()
+    phi = (torch.rand(B, H, W, generator=g) > 0.5).float().cuda()
+    y = (torch.rand(H, W, generator=g) * B / 2).cuda()
+    res = {}
+    for impl in ("tc", "ref"):
+        m = _fastdvd(impl)
+        eng = m.module.engine()
+        out = eng.forward(u, 12 / 255, train=False).clone()
+        o_tr = eng.forward(u, 12 / 255, train=True)
+        loss = torch.zeros(1, dtype=torch.float64, device=u.device)
+        dout = _tile_loss(eng, o_tr, phi, y, "dout", loss, None, True)
+        eng.backward(dout)
+        res[impl] = (out.cpu(), eng.bucket.grad.clone().cpu(), float(loss))
+    (o_tc, g_tc, l_tc), (o_ref, g_ref, l_ref) = res["tc"], res["ref"]
+    assert float((o_tc - o_ref).abs().max()) < 1e-3
+    assert abs(l_tc - l_ref) < 1e-4 * abs(l_ref)
+    gmax = float(g_ref.abs().max())
+    assert gmax > 0 and float((g_tc - g_ref).abs().max()) < 3e-3 * gmax
+    cos = float((g_tc.double() * g_ref.double()).sum() / (g_tc.double().norm() * g_ref.double().norm()))
+    assert cos > 0.9999
