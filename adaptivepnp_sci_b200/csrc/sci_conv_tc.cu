@@ -318,6 +318,7 @@ struct Fwd2Params {
     int N, H, W, Cin, Cout, relu, ps, round_tf32;
     int tiles_w, num_tiles, k_chunks, stages, acc_stride, tmem_cols, resident, desc_mode, tma_store, out_bufs;
     const float* planar_in1; float* planar_out;   // fused network output: out[n][c][h][w] = in1[n][c][h][w] - conv[c], c < 3
+    int pdl;          // launched with programmatic stream serialization: see griddepcontrol below
     int col0, Ctot;   // this launch computes GEMM columns [col0, col0 + Cout) of a layer with Ctot columns (Cout = 256 layers run as two halves)
     int stack;        // filter rows stacked along N (see the MMA issuer); needs resident weights, R >= 2, 3*Cout <= 256
     int R, tiles_h;   // rows per super-tile (R output rows share their R+2 input rows), super-tiles per image column strip
@@ -373,6 +374,8 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_slot, 0);
+    // the next kernel of the stream may be scheduled as soon as SMs free up (it waits for our completion itself)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0) {
         // ===== TMA producer (warp-uniform loop, one elected lane issues) =====
@@ -390,6 +393,10 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             __syncwarp();
         }
+        // Programmatic dependent launch: everything above (barriers, TMEM, tensor maps, the resident WEIGHTS, which no
+        // kernel of the running chain writes) overlapped the tail of the previous kernel; its activations may only be
+        // read once it has completed and flushed
+        if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
         int stage = 0; uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             const int wt = tile % p.tiles_w, hg = (tile / p.tiles_w) % p.tiles_h, n = tile / (p.tiles_w * p.tiles_h);
@@ -525,6 +532,7 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int Cq = p.Ctot >> 2;
         int acc = 0; uint32_t acc_phase = 0;
         uint32_t st_cnt = 0;
+        if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");      // residual / in1 come from earlier kernels
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             const int wt = tile % p.tiles_w, hg = (tile / p.tiles_w) % p.tiles_h, n = tile / (p.tiles_w * p.tiles_h);
             const int y0 = hg * p.R, rows = min(p.R, p.H - y0);
@@ -858,6 +866,18 @@ int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream, int col0, int ncol
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     const int grid = min(p.num_tiles, SCI_NUM_SMS);
+    p.pdl = (d->pdl && env_int("SCI_CONV_PDL", 1)) ? 1 : 0;
+    if (p.pdl) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = sci_stream(stream);
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, conv_fwd2_tc_kernel, tmA, tmB, tmY, p);
+        if (e != cudaSuccess) return sci_fail(SCI_ELAUNCH, "conv tc fwd v2 (PDL launch)", e);
+        return SCI_OK;
+    }
     conv_fwd2_tc_kernel<<<grid, TC_THREADS, smem, sci_stream(stream)>>>(tmA, tmB, tmY, p);
     SCI_CHECK_LAUNCH("conv tc fwd v2");
     return SCI_OK;

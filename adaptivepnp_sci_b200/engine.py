@@ -34,7 +34,7 @@ class ConvDesc(ctypes.Structure):
                 ("N", ctypes.c_int), ("H", ctypes.c_int), ("W", ctypes.c_int), ("Cin", ctypes.c_int),
                 ("Cout", ctypes.c_int), ("stride", ctypes.c_int), ("relu", ctypes.c_int),
                 ("pixel_shuffle", ctypes.c_int), ("round_tf32", ctypes.c_int), ("w_split", ctypes.c_int), ("emit_lo", ctypes.c_int),
-                ("planar_in1", _f32p), ("planar_out", _f32p)]
+                ("planar_in1", _f32p), ("planar_out", _f32p), ("pdl", ctypes.c_int)]
 
 
 class WgradDesc(ctypes.Structure):
@@ -200,6 +200,7 @@ class _EngineBase:
         self._bwd_valid = False
         self.dirty = True
         self.n_launch = 0
+        self.pdl_chain = False   # True inside an inference chain: weights are packed, consecutive convs may overlap (PDL)
         self.profile = None      # set to a list to record (start_event, end_event, algorithmic_flops, tag) per conv launch
 
     # ---- parameter state ------------------------------------------------------------------------------
@@ -237,7 +238,8 @@ class _EngineBase:
         """planar = (in1, out) planar [N,3,H,W] tensors: tensor-core path only, fused `out = in1 - conv` (y unused)."""
         d = ConvDesc(_dp(x), _dp(L.wpk), _dp(L.scale), _dp(L.shift), _dp(residual), _dp(y), N, H, W, L.Ci_pad, L.Co_pad,
                      L.stride, int(L.relu), int(L.ps), int(self.tf32 and round_out), int(self.tf32 and L.wsplit),
-                     int(emit_lo), _dp(planar[0]) if planar else None, _dp(planar[1]) if planar else None)
+                     int(emit_lo), _dp(planar[0]) if planar else None, _dp(planar[1]) if planar else None,
+                     int(self.pdl_chain))
         if self.profile is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
@@ -457,8 +459,14 @@ class FastDVDnetEngine(_EngineBase):
         dev = frames.device
         t1_out = self.ws.get("t1_out_train" if train else "t1_out", (B, 3, H, W), dev)
         out = self.ws.get("out_train" if train else "out", (B, 3, H, W), dev)
-        s1 = self._block_forward("t1", self.t1, frames, sigma, t1_out, train)
-        s2 = self._block_forward("t2", self.t2, t1_out, sigma, out, train)
+        # inference: the packed weights are final before the first conv starts, so consecutive layers may overlap their
+        # prologue with the previous layer's tail (programmatic dependent launch); not while profiling per layer
+        self.pdl_chain = (not train) and self.profile is None and self.impl == IMPL_TC
+        try:
+            s1 = self._block_forward("t1", self.t1, frames, sigma, t1_out, train)
+            s2 = self._block_forward("t2", self.t2, t1_out, sigma, out, train)
+        finally:
+            self.pdl_chain = False
         if train:
             self._saved = (s1, s2, B, H, W)
         return out
@@ -650,6 +658,14 @@ class DDnetEngine(_EngineBase):
                                       "stride-2 levels; the reference reflect-pads to 4, DDnet_test.py:180-187, and "
                                       "would itself fail on sizes that are not multiples of 8)")
         self.prepare(training=train)
+        self.pdl_chain = (not train) and self.profile is None and self.impl == IMPL_TC      # see FastDVDnetEngine.forward
+        try:
+            return self._forward(mosaic, train)
+        finally:
+            self.pdl_chain = False
+
+    def _forward(self, mosaic, train):
+        B, H, W = mosaic.shape
         dev = mosaic.device
         m = self.module
         a, a2, a3 = m.weight_tensor_in.data, m.weight_tensor_in2.data, m.weight_tensor_out.data

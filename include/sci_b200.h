@@ -193,6 +193,10 @@ typedef struct sci_conv_desc {
     float* planar_out;      /* TC only. non-NULL: the layer is the last conv of a FastDVDnet DenBlock (Cout == 32, 3 real
                                channels): instead of y the kernel writes out[n][c][h][w] = planar_in1[n][c][h][w] - conv[c]
                                (packages/fastdvdnet/models.py:196) as planar frames; y may be NULL */
+    int pdl;                /* TC only. 1: programmatic dependent launch — the kernel may be scheduled while the previous kernel
+                               of the stream is still draining; it sets up barriers / TMEM / resident weights meanwhile and
+                               waits for that kernel's completion before touching x / residual / planar_in1.  Only valid when
+                               the previous kernel does not write w, scale or shift (engine: inference chains) */
 } sci_conv_desc;
 
 /* 1 if this build contains the tcgen05 tensor-core convolution kernels. */
