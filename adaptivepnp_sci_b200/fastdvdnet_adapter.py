@@ -69,11 +69,19 @@ def fast_legacy_normal(rs, loc, scale, shape, nthreads=None):
     c_pos, c_has, c_g = ctypes.c_int(int(pos)), ctypes.c_int(int(has_gauss)), ctypes.c_double(float(gauss))
     rc = lib.sci_host_legacy_normal(key.ctypes.data_as(ctypes.c_void_p), ctypes.byref(c_pos), ctypes.byref(c_has),
                                     ctypes.byref(c_g), float(loc), float(scale), out.ctypes.data_as(ctypes.c_void_p), n,
-                                    int(nthreads or min(16, os.cpu_count() or 1)))
+                                    int(nthreads or _default_rng_threads()))
     if rc != 0:
         raise SciError("sci_host_legacy_normal failed (%d)" % rc)
     rs.set_state((name, key, c_pos.value, c_has.value, c_g.value))
     return out.reshape(shape)
+
+
+def _default_rng_threads():
+    """Worker threads of the host noise generator: the box's cores are shared by all ranks of the node (torchrun sets
+    LOCAL_WORLD_SIZE), and the main thread of every rank must keep launching kernels while the helper draws ahead."""
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))
+    return max(1, min(16, cores // ranks - 1))
 
 
 def _host_buffer(n):
