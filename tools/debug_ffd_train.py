@@ -3,7 +3,7 @@ sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "t
 import numpy as np, torch
 from adaptivepnp_sci_b200.dvp_linear_inv_2_stage_ADMM_tensor_online import np2tch_cuda, twoStageAdmm_denoise_bayer
 from adaptivepnp_sci_b200.network_ffdnet import FFDNet
-from oracle import synthetic
+from adaptivepnp_sci_b200 import synthetic
 d = np.load("tests/golden/loops.npz")
 meas, mask, orig = synthetic.make_case(64, 64, 8, 3000, bayer=True)
 def mk():

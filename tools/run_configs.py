@@ -1,8 +1,8 @@
 """Per-config timing of BASELINE.json configs 1-3 on ONE GPU (configs 4 and 5 are bench.py and tools/run_config5.py).
 
 Device time with CUDA events around the public solver call with device-resident outputs where the API allows it
-(``return_device=True``), otherwise end to end (numpy in / numpy out).  ``--cpu`` also times the oracle port of the
-reference on the host for the configs where that takes seconds (config 1) so both numbers sit side by side."""
+(``return_device=True``), otherwise end to end (numpy in / numpy out).  (CPU timings of the reference's port come from
+``bench.py --impl reference`` / the ``cpu_baseline`` leg — nothing outside tests/, smoke() and bench.py touches oracle/.)"""
 import argparse, io, json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -28,9 +28,7 @@ def timed(fn, reps=3, warm=2):
 
 
 def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--cpu", action="store_true")
-    args = ap.parse_args()
+    argparse.ArgumentParser().parse_args()
     out = {}
     worker_init_fn(0)
     # config 1: TV warm start, 256x256x8 gray cube, 40 iterations (ADMM_TV_Warm_Start_save.py:36-37,132-135)
@@ -41,12 +39,6 @@ def main():
     r = run1()
     out["config1_tv_256x256x8"] = {"ms_per_recon_e2e": ms, "iters": 40, "iters_per_sec": 40e3 / ms, "psnr_db": float(np.mean(r[1]))}
     warm1 = r[0]
-    if args.cpu:
-        from oracle import admm
-        torch.set_num_threads(os.cpu_count() or 1)
-        t0 = time.time()
-        admm.admm_denoise_bayer_demosaic_pre(meas, mask, 1, 0.01, 'tv', [40], False, [0], X_orig=orig)
-        out["config1_tv_256x256x8"]["cpu_oracle_port_s"] = time.time() - t0
     # config 2: two-stage + online FFDNet-gray on the same cube (derived loop); sigma 25/12/6, iters 6/6/4
     sd = torch.load(os.path.join(ROOT, "model_zoo", "ffdnet_gray.pth"))
 
