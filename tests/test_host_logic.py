@@ -1,0 +1,48 @@
+"""CPU: small pieces of host logic around the hot path (no GPU, no compute calls into the library)."""
+import os
+
+import numpy as np
+
+
+def test_rng_helper_threads_share_the_node(monkeypatch):
+    """The host-noise helper leaves cores for the launch threads of all ranks of the node (8-GPU scaling fix)."""
+    from adaptivepnp_sci_b200 import fastdvdnet_adapter as fa
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    monkeypatch.delenv("LOCAL_WORLD_SIZE", raising=False)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    assert fa._default_rng_threads() == max(1, min(16, cores - 1))
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
+    assert fa._default_rng_threads() == max(1, min(16, cores // 8 - 1))
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", str(4 * cores))
+    assert fa._default_rng_threads() == 1
+
+
+def test_warm_start_handoff_roundtrip(tmp_path):
+    """Stage 1 -> stage 2 hand-off file (results/savedmat/_Admm_tv_<name>8.mat, key v_Admm_tv_denoise; reference
+    ADMM_TV_Warm_Start_save.py:174-178 <-> two_stage_ADMM_Online_FFD_Warm.py:171-176)."""
+    from adaptivepnp_sci_b200 import matio
+    v = np.random.default_rng(0).random((16, 24, 16)).astype(np.float32)
+    d = str(tmp_path) + "/"
+    p = matio.save_warm_start(d, "Beauty_bayer", 8, v, np.ones(16, np.float32), np.ones(16, np.float32))
+    assert os.path.basename(p) == "_Admm_tv_Beauty_bayer8.mat"
+    back = matio.load_warm_start(d, "Beauty_bayer", 8)
+    assert back.dtype == np.float32 and np.array_equal(back, v)
+
+
+def test_synthetic_dataset_fallback_shapes():
+    """Without dataset files the loaders fall back to the deterministic synthetic videos (scale 0..255 like the .mat data)."""
+    from adaptivepnp_sci_b200 import matio
+    meas, mask, orig = matio.load_video("/nonexistent", "Jockey_bayer", nmea=2, synthetic_shape=(32, 48, 8), force_synthetic=True)
+    assert meas.shape == (32, 48, 2) and mask.shape == (32, 48, 8) and orig.shape == (32, 48, 16)
+    assert meas.dtype == np.float32 and float(orig.max()) <= 255.0 and float(orig.max()) > 1.0
+    assert np.allclose(meas[:, :, 1], (orig[:, :, 8:] * mask).sum(2), rtol=1e-5)
+
+
+def test_script_schedules_cover_all_videos():
+    from adaptivepnp_sci_b200 import matio, stage2_script as s
+    for table in (s.FFD_TABLE, s.FASTDVD_TABLE, s.FFD_DEEP, s.FASTDVD_DEEP):
+        assert set(table) == set(matio.VIDEOS)
+    for name, (sig, iters, lr, upi, interval, times) in s.FASTDVD_TABLE.items():
+        assert len(sig) == len(iters) and lr in (2e-6, 2e-7) and upi in (1, 2)
+    for name, (sig, iters, interval) in s.FASTDVD_DEEP.items():
+        assert len(sig) == len(iters) and interval >= 1
