@@ -679,3 +679,44 @@ extern "C" int sci_ssim_accum(const float* a, const float* ref, int H, int W, in
     SCI_CHECK_LAUNCH("ssim_accum");
     return SCI_OK;
 }
+
+
+// ---------------------------------------------------------------------------
+// Right/bottom reflect padding (torch F.pad(..., mode='reflect'): no edge repeat) and the matching crop for the sequence
+// drivers, which pad every frame to a multiple of 4 before calling the network and cut the result back
+// (packages/fastdvdnet/fastdvdnet.py:119-141, packages/DDnet/DDnet_test.py:180-196).  planes = any number of [H][W] planes.
+// ---------------------------------------------------------------------------
+__global__ void reflect_pad_kernel(const float* __restrict__ in, float* __restrict__ out, long planes, int H, int W, int Ho, int Wo) {
+    const long total = planes * Ho * Wo;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = (int)(idx % Wo), r = (int)((idx / Wo) % Ho);
+    const long pl = idx / ((long)Wo * Ho);
+    const int rs = r < H ? r : 2 * (H - 1) - r, cs = c < W ? c : 2 * (W - 1) - c;      // Ho <= 2H-1, Wo <= 2W-1 for crop: rs = r
+    out[idx] = in[(pl * H + rs) * W + cs];
+}
+
+extern "C" int sci_reflect_pad2d(const float* in, float* out, long planes, int H, int W, int Ho, int Wo, void* stream) {
+    SCI_REQUIRE(in && out && planes > 0 && H > 0 && W > 0 && Ho >= H && Wo >= W && Ho < 2 * H && Wo < 2 * W, "reflect_pad2d");
+    const long total = planes * Ho * Wo;
+    reflect_pad_kernel<<<sci_ceil_div(total, 256), 256, 0, sci_stream(stream)>>>(in, out, planes, H, W, Ho, Wo);
+    SCI_CHECK_LAUNCH("reflect_pad2d");
+    return SCI_OK;
+}
+
+__global__ void crop_kernel(const float* __restrict__ in, float* __restrict__ out, long planes, int H, int W, int Hc, int Wc) {
+    const long total = planes * Hc * Wc;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = (int)(idx % Wc), r = (int)((idx / Wc) % Hc);
+    const long pl = idx / ((long)Wc * Hc);
+    out[idx] = in[(pl * H + r) * W + c];
+}
+
+extern "C" int sci_crop2d(const float* in, float* out, long planes, int H, int W, int Hc, int Wc, void* stream) {
+    SCI_REQUIRE(in && out && planes > 0 && Hc > 0 && Wc > 0 && Hc <= H && Wc <= W, "crop2d");
+    const long total = planes * Hc * Wc;
+    crop_kernel<<<sci_ceil_div(total, 256), 256, 0, sci_stream(stream)>>>(in, out, planes, H, W, Hc, Wc);
+    SCI_CHECK_LAUNCH("crop2d");
+    return SCI_OK;
+}

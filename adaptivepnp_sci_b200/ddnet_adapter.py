@@ -29,8 +29,12 @@ def _unwrap(model):
 
 
 def demosaic_planar(mosaic, model):
-    """mosaic [B,H,W] planar device tensor -> demosaicked [B,3,H,W] (engine-owned buffer, valid until the next call)."""
-    return _unwrap(model).engine().forward(mosaic)
+    """mosaic [B,H,W] planar device tensor -> demosaicked [B,3,H,W] (engine-owned buffer, valid until the next call).
+    Frames whose size is not a multiple of 4 are reflect-padded and the result cropped, as ddnet_seqdenoise does
+    (DDnet_test.py:180-196)."""
+    padded, H, W = ops.pad_to_multiple(mosaic, 4)
+    out = _unwrap(model).engine().forward(padded)
+    return ops.crop_to(out, H, W)
 
 
 def rgb_sum(rgb):

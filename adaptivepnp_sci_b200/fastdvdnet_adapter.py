@@ -252,7 +252,9 @@ def fastdvdnet_seqdenoise(seq, noise_std, windsize, model, train=None):
     """fastdvdnet.py:82-146 — seq [N,3,H,W] -> [N,3,H,W], circular 5-frame window."""
     if windsize != NUM_IN_FR_EXT:
         raise NotImplementedError("window size 5 only")
-    out = _unwrap(model).engine().forward(seq.contiguous().float(), float(noise_std.flatten()[0]), train=False).clone()
+    padded, H, W = ops.pad_to_multiple(seq.contiguous().float(), 4)                     # reflect pad to x4 (:119-127)
+    out = _unwrap(model).engine().forward(padded, float(noise_std.flatten()[0]), train=False)
+    out = ops.crop_to(out, H, W).clone()                                                # un-pad (:134-141)
     return (out, model) if train else out
 
 

@@ -142,6 +142,29 @@ def ssim_frames(a, orig):
     return acc / float((H - 6) * (W - 6))
 
 
+def pad_to_multiple(t, m):
+    """[..., H, W] -> reflect-padded (right / bottom, like F.pad(mode='reflect')) to multiples of m; returns (padded, H, W)."""
+    require_cuda_f32(t)
+    H, W = t.shape[-2:]
+    Ho, Wo = (H + m - 1) // m * m, (W + m - 1) // m * m
+    if (Ho, Wo) == (H, W):
+        return t, H, W
+    out = torch.empty(t.shape[:-2] + (Ho, Wo), dtype=torch.float32, device=t.device)
+    call("sci_reflect_pad2d", ptr(t.contiguous()), ptr(out), t.numel() // (H * W), H, W, Ho, Wo, stream())
+    return out, H, W
+
+
+def crop_to(t, Hc, Wc):
+    """[..., H, W] -> contiguous [..., Hc, Wc] (top-left crop)."""
+    require_cuda_f32(t)
+    H, W = t.shape[-2:]
+    if (Hc, Wc) == (H, W):
+        return t
+    out = torch.empty(t.shape[:-2] + (Hc, Wc), dtype=torch.float32, device=t.device)
+    call("sci_crop2d", ptr(t.contiguous()), ptr(out), t.numel() // (H * W), H, W, Hc, Wc, stream())
+    return out
+
+
 def axpy(x, a, y, out=None):
     """out = x + a*y (elementwise, fp32)."""
     require_cuda_f32(x, y, out)

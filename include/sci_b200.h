@@ -125,6 +125,11 @@ int sci_dual_update_rgb(const float* xhat, const float* x_rgb, float* w, const f
                         float* b, float* theta, int first_iter, int H, int W, int B,
                         const float* orig, double* sse, void* stream);
 
+/* Right/bottom reflect padding (torch F.pad mode='reflect') of `planes` [H][W] planes to [Ho][Wo] and the matching crop:
+ * the sequence drivers pad every frame to a multiple of 4 before the network and cut the result back
+ * (packages/fastdvdnet/fastdvdnet.py:119-141, packages/DDnet/DDnet_test.py:180-196). */
+int sci_reflect_pad2d(const float* in, float* out, long planes, int H, int W, int Ho, int Wo, void* stream);
+int sci_crop2d(const float* in, float* out, long planes, int H, int W, int Hc, int Wc, void* stream);
 /* Closed-form demosaic update of the `close_form_demosaic` branch (dvp_linear_inv_2_stage_ADMM_tensor_online.py:112-118,
  * 175-182, 224-230), all frames in one launch:
  *   x_rgb[c] = (rho*x3[c] + b3[c] + tau*xhat[c] + w[c]) / (rho*m[c] + tau), optionally clipped to [0,1] (:182, FFDNet branch);

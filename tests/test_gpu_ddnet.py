@@ -110,3 +110,27 @@ def test_stage2_with_deep_demosaic(cuda, impl):
                                    update_times=-1, **kw)
     assert np.max(np.abs(r[0] - d["s2f_rgb"])) < tol and np.max(np.abs(r[1] - d["s2f_x"])) < tol
     assert np.max(np.abs(np.array(r[4]) - d["s2f_psnr_all"])) < 0.05
+
+
+def test_sequence_drivers_reflect_pad_to_multiple_of_4(cuda, impl):
+    """Frames whose size is not a multiple of 4 are reflect-padded (right / bottom) before the network and cropped after it
+    (DDnet_test.py:180-196, fastdvdnet.py:119-141): DDnet against the reference's output for a 30x46 input, FastDVDnet
+    against the oracle's restatement of the sequence driver."""
+    from adaptivepnp_sci_b200 import fastdvdnet_adapter
+    from adaptivepnp_sci_b200.ddnet_adapter import test_ddnet as ddnet_plugin
+    from adaptivepnp_sci_b200.utils_image import oneCh2ThreeCh
+    from oracle import adapters, networks, synthetic
+    d = np.load(os.path.join(G, "ddnet.npz"))
+    v = oneCh2ThreeCh(torch.from_numpy(d["ad_mosaic"]).cuda())[:30, :46].contiguous()
+    out = ddnet_plugin(v, None, None, _ddnet(cuda))
+    assert out.shape == (30, 46, 3, 8)
+    assert np.max(np.abs(out.cpu().numpy() - d["ad_inf_odd"])) < TOL[impl]
+    g = torch.Generator().manual_seed(9)
+    seq = torch.rand(6, 3, 30, 46, generator=g)
+    om = networks.Wrapped(networks.FastDVDnet(num_input_frames=5))
+    om.load_state_dict({"module." + k: t for k, t in synthetic.fastdvdnet_synthetic_state_dict().items()}, strict=True)
+    with torch.no_grad():
+        want = adapters.fastdvdnet_seqdenoise(seq, torch.tensor([12 / 255]), 5, om.eval())
+    got = fastdvdnet_adapter.fastdvdnet_seqdenoise(seq.cuda(), torch.tensor([12 / 255]).cuda(), 5, _fastdvd(cuda))
+    assert got.shape == (6, 3, 30, 46)
+    assert float((got.cpu() - want).abs().max()) < TOL[impl] * 5
