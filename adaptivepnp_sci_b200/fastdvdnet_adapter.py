@@ -81,7 +81,7 @@ def _default_rng_threads():
     LOCAL_WORLD_SIZE), and the main thread of every rank must keep launching kernels while the helper draws ahead."""
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))
-    return max(1, min(16, cores // ranks - 1))
+    return max(1, min(8, cores // ranks - 1))       # the Mersenne-Twister word stream is serial: 4-8 workers already hide the rest
 
 
 def _host_buffer(n):

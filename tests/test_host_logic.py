@@ -10,9 +10,9 @@ def test_rng_helper_threads_share_the_node(monkeypatch):
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     monkeypatch.delenv("LOCAL_WORLD_SIZE", raising=False)
     monkeypatch.delenv("WORLD_SIZE", raising=False)
-    assert fa._default_rng_threads() == max(1, min(16, cores - 1))
+    assert fa._default_rng_threads() == max(1, min(8, cores - 1))
     monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
-    assert fa._default_rng_threads() == max(1, min(16, cores // 8 - 1))
+    assert fa._default_rng_threads() == max(1, min(8, cores // 8 - 1))
     monkeypatch.setenv("LOCAL_WORLD_SIZE", str(4 * cores))
     assert fa._default_rng_threads() == 1
 
