@@ -84,17 +84,56 @@ def _default_rng_threads():
     return max(1, min(8, cores // ranks - 1))       # the Mersenne-Twister word stream is serial: 4-8 workers already hide the rest
 
 
+_pool_lock = __import__("threading").Lock()
+_pool = {}       # element count -> free page-locked float64 tensors
+_owner = {}      # data pointer of a handed-out array -> the page-locked tensor that owns it
+
+
 def _host_buffer(n):
-    """float64 host array for the noise.  On a GPU box it lives in PINNED memory (torch's caching host allocator), so the
-    upload in ``finetune_and_denoise`` is one asynchronous DMA instead of a staged, blocking pageable copy (2 x 50 MB per
-    reconstruction at 512x512x8); the numpy view keeps the owning tensor alive."""
-    # (whole-frame draws of the tiled mode are gigabytes per rank: page-locking those costs more than it saves)
+    """float64 host array for the noise.  On a GPU box it lives in PINNED memory, so the upload in
+    ``finetune_and_denoise`` is one asynchronous DMA instead of a staged, blocking pageable copy (2 x 50 MB per
+    reconstruction at 512x512x8).  The buffers are pooled explicitly: page-locking 50 MB costs tens of milliseconds and
+    takes driver locks that stall kernel launches, so after ``prewarm_host_buffers`` no allocation happens in steady state.
+    (Whole-frame draws of the tiled mode are gigabytes per rank: page-locking those costs more than it saves.)"""
     if n <= (1 << 25) and torch.cuda.is_available() and os.environ.get("SCI_NOISE_PINNED", "1") != "0":
-        try:
-            return torch.empty(n, dtype=torch.float64, pin_memory=True).numpy()
-        except RuntimeError:
-            pass
+        with _pool_lock:
+            free = _pool.get(n)
+            t = free.pop() if free else None
+        if t is None:
+            try:
+                t = torch.empty(n, dtype=torch.float64, pin_memory=True)
+            except RuntimeError:
+                t = None
+        if t is not None:
+            a = t.numpy()
+            with _pool_lock:
+                _owner[a.ctypes.data] = t
+            return a
     return np.empty(n, dtype=np.float64)
+
+
+def _release_host_buffer(arr):
+    """Give a pooled buffer back once nothing reads it any more (no-op for ordinary numpy arrays)."""
+    with _pool_lock:
+        t = _owner.pop(arr.ctypes.data, None)
+        if t is not None:
+            _pool.setdefault(t.numel(), []).append(t)
+
+
+def prewarm_host_buffers(n, count):
+    """Page-lock ``count`` buffers of ``n`` doubles up front (first reconstruction), so later calls only recycle."""
+    if not (n <= (1 << 25) and torch.cuda.is_available() and os.environ.get("SCI_NOISE_PINNED", "1") != "0"):
+        return
+    with _pool_lock:
+        have = len(_pool.get(n, ()))
+    fresh = []
+    for _ in range(max(0, count - have)):
+        try:
+            fresh.append(torch.empty(n, dtype=torch.float64, pin_memory=True))
+        except RuntimeError:
+            break
+    with _pool_lock:
+        _pool.setdefault(n, []).extend(fresh)
 
 
 def _state_key(st):
@@ -147,7 +186,11 @@ class NoiseStream:
         """(Re)start the helper from the CURRENT global state; caller holds the lock."""
         import threading
         self.epoch += 1
+        for _, _, _, arr in self.queue:
+            _release_host_buffer(arr)
         self.queue = []
+        if tuple(shape) != self.shape:
+            prewarm_host_buffers(int(np.prod(shape)), self.depth + 3)
         self.shape = tuple(shape)
         self.rs = np.random.RandomState()
         self.rs.set_state(np.random.get_state())
@@ -205,17 +248,27 @@ def finetune_and_denoise(v, phi, y, sigma, model, lr, update_per_iter, grad_sync
         n_update_iter, lr_all = [update_per_iter], [lr]                                  # :344-349
     else:
         n_update_iter, lr_all = list(update_per_iter), list(lr)
+    full = None
     if noise is None:
         if tile is None:
             noise = noise_stream.get((B, 3, H, W))
         else:
-            noise = noise_stream.get((B, 3, tile.H_total, W))[:, :, tile.g0:tile.g0 + H]
+            full = noise_stream.get((B, 3, tile.H_total, W))
+            noise = full[:, :, tile.g0:tile.g0 + H]
     noise_h = np.ascontiguousarray(noise, dtype=np.float64)
+    if full is not None and noise_h.ctypes.data != full.ctypes.data:
+        _release_host_buffer(full)           # the strip was copied out: the whole-frame buffer is free again
     noise_d = torch.from_numpy(noise_h).to(dev, non_blocking=True)        # pinned source -> one asynchronous DMA
     # the host buffer must outlive the DMA (the host runs ahead of the stream): park it until its event has fired
     ev = torch.cuda.Event()
     ev.record()
-    _inflight[:] = [(e, a) for e, a in _inflight if not e.query()] + [(ev, noise_h)]
+    still = []
+    for e, a in _inflight:
+        if e.query():
+            _release_host_buffer(a)          # its upload has completed: the pinned buffer goes back to the pool
+        else:
+            still.append((e, a))
+    _inflight[:] = still + [(ev, noise_h)]
     vplus = eng.ws.get("vplus", (B, 3, H, W), dev)
     call("sci_fastdvd_noisy_input", ptr(v), ptr(noise_d), ptr(vplus), v.numel(), stream())    # :359
     eng.prepare(training=True)
