@@ -335,13 +335,25 @@ __device__ __forceinline__ uint64_t umma_desc_off(uint32_t saddr, int mode) {
     return d;
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// Epilogue organisation (round 2).  The ncu source view of the full-resolution layers showed the four epilogue warps
+// - one per SM sub-partition - busy >90 % of the time at IPC 0.25 (407 instructions per 32-channel chunk, every one
+// waiting for its predecessor) while the MMA warp sat on the tmem_empty barrier: the 12->90 layer was bound by its
+// epilogue, not by the tensor pipe, shared memory or HBM.  Hence
+//   * EPI_WG = 2 epilogue warpgroups (warps 4-7 and 8-11; a warp may only touch the TMEM lane quarter warp % 4, so the
+//     second group shares the quarters and takes every second (row, chunk) unit): two warps per scheduler hide each
+//     other's latencies;
+//   * MODE selects the epilogue at compile time (0 = TMA store, 1 = TMA store + skip-add, 2 = fused planar network
+//     output, 3 = direct stores) instead of run-time flags per element; scale / shift come from shared memory as float4;
+//   * the planar mode fetches the in1 values of ALL its rows before it waits for the accumulator (the per-row prefetch
+//     left the HBM latency of those loads exposed: 46 % of the epilogue's samples in the 32->3 layer).
+template <int EPI_WG, int MODE>
+__global__ void __launch_bounds__(128 + 128 * EPI_WG, 1)
 conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmY, const Fwd2Params p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2], w_bar;
     __shared__ uint32_t tmem_slot;
-    __shared__ float s_scale[128], s_shift[128];
+    __shared__ __align__(16) float s_scale[128], s_shift[128];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -349,9 +361,9 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t w_bytes = p.resident ? 9u * (uint32_t)p.k_chunks * b_bytes : 0u;
     const uint32_t stage_bytes = A2_STAGE + (p.resident ? 0u : 3u * b_bytes);
     const uint32_t ring_base = smem_base + w_bytes;
-    const uint32_t stage_out_base = ring_base + (uint32_t)p.stages * stage_bytes;   // 4 warps x 2 x 4 KB store staging
+    const uint32_t stage_out_base = ring_base + (uint32_t)p.stages * stage_bytes;   // 4 EPI_WG warps x out_bufs x 4 KB store staging
 
-    for (int i = threadIdx.x; i < p.Cout; i += TC_THREADS) {
+    for (int i = threadIdx.x; i < p.Cout; i += 128 + 128 * EPI_WG) {
         s_scale[i] = p.scale ? p.scale[p.col0 + i] : 1.f;
         s_shift[i] = p.shift ? p.shift[p.col0 + i] : 0.f;
     }
@@ -361,7 +373,7 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4 * EPI_WG); }
         mbar_init(&w_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -527,9 +539,15 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else if (warp >= 4) {
         // ===== epilogue: TMEM -> registers -> (scale/shift, ReLU, skip-add, TF32 round) -> swizzled staging -> TMA store
-        const int q = warp & 3;
+        const int q = warp & 3;                            // TMEM lane quarter this warp may access
+        const int g = (warp >> 2) - 1;                     // epilogue warpgroup: takes the units u = g (mod EPI_WG)
         const int m = q * 32 + lane;
         const int Cq = p.Ctot >> 2;
+        const int nch = p.Cout >> 5;                       // 32-column chunks per output row
+        const float lower = p.relu ? 0.f : -INFINITY;
+        const long pl_plane = (long)p.H * p.W;
+        constexpr int PIN_ROWS = (8 + EPI_WG - 1) / EPI_WG;   // planar mode: rows of a super-tile (R <= 8) per warpgroup
+        const uint32_t sbuf0 = stage_out_base + (uint32_t)((g * 4 + q) * p.out_bufs) * 4096u;
         int acc = 0; uint32_t acc_phase = 0;
         uint32_t st_cnt = 0;
         if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");      // residual / in1 come from earlier kernels
@@ -538,6 +556,7 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int y0 = hg * p.R, rows = min(p.R, p.H - y0);
             const int wo = wt * 128 + m;
             const bool valid = wo < p.W;
+            const int units = rows * nch;
             // element offset of this lane's 32-channel segment of chunk c0 of output row ho in the output / residual tensor
             auto out_offset = [&](int ho, int c0) -> long {
                 const int cg = p.col0 + c0;                           // column of the whole layer
@@ -547,103 +566,126 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
                 return (((long)n * p.H + ho) * p.W + wo) * p.Ctot + cg;
             };
-            // the skip tensor of the first chunk is fetched while the MMAs of this tile are still running
+            // operands from global memory are requested while the MMAs of this tile are still running
             float4 rr[8];
+            float pin[PIN_ROWS][3];
+            if (MODE == 1 || MODE == 3) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) rr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.residual && valid) {
-                const float4* rp = reinterpret_cast<const float4*>(p.residual + out_offset(y0, 0));
+                for (int j = 0; j < 8; ++j) rr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.residual && valid && g < units) {
+                    const float4* rp = reinterpret_cast<const float4*>(p.residual + out_offset(y0 + g / nch, (g % nch) << 5));
 #pragma unroll
-                for (int j = 0; j < 8; ++j) rr[j] = __ldg(rp + j);
+                    for (int j = 0; j < 8; ++j) rr[j] = __ldg(rp + j);
+                }
             }
-            // fused planar output: the three in1 values of this lane's pixel are fetched ahead as well
-            float pin[3] = {0.f, 0.f, 0.f};
-            const long pl_plane = (long)p.H * p.W;
-            if (p.planar_out && valid) {
-                const long o = (long)n * 3 * pl_plane + (long)y0 * p.W + wo;
+            if (MODE == 2) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) pin[c] = __ldg(p.planar_in1 + o + c * pl_plane);
+                for (int i = 0; i < PIN_ROWS; ++i) {
+                    const int t = g + i * EPI_WG;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) pin[i][c] = 0.f;
+                    if (valid && t < rows) {
+                        const long o = (long)n * 3 * pl_plane + (long)(y0 + t) * p.W + wo;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) pin[i][c] = __ldg(p.planar_in1 + o + c * pl_plane);
+                    }
+                }
             }
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-          for (int t = 0; t < rows; ++t) {
-            const int ho = y0 + t;
-            const uint32_t t_row = tmem_base + (uint32_t)((acc * p.R + (p.stack ? p.R - 1 - t : t)) * p.acc_stride) + ((uint32_t)(q * 32) << 16);
-            for (int c0 = 0; c0 < p.Cout; c0 += 32) {
-                float v[32];
+            // one unit = 32 channels of one output row for this lane's pixel
+            auto unit = [&](int t, int c0, float (&v)[32]) {
+                const uint32_t t_row = tmem_base + (uint32_t)((acc * p.R + (p.stack ? p.R - 1 - t : t)) * p.acc_stride) + ((uint32_t)(q * 32) << 16);
                 tmem_ld32(t_row + c0, v);
-                float4 rn[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) rn[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.residual && valid && (c0 + 32 < p.Cout || t + 1 < rows)) {   // prefetch the next chunk's skip values
-                    const bool same_row = c0 + 32 < p.Cout;
-                    const float4* rp = reinterpret_cast<const float4*>(p.residual + out_offset(same_row ? ho : ho + 1, same_row ? c0 + 32 : 0));
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) rn[j] = __ldg(rp + j);
-                }
-                float out[32];
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    const float radd[4] = {rr[j >> 2].x, rr[j >> 2].y, rr[j >> 2].z, rr[j >> 2].w};
+                    const float4 sc = *reinterpret_cast<const float4*>(&s_scale[c0 + j]);
+                    const float4 sh = *reinterpret_cast<const float4*>(&s_shift[c0 + j]);
+                    v[j]     = fmaxf(fmaf(v[j],     sc.x, sh.x), lower);
+                    v[j + 1] = fmaxf(fmaf(v[j + 1], sc.y, sh.y), lower);
+                    v[j + 2] = fmaxf(fmaf(v[j + 2], sc.z, sh.z), lower);
+                    v[j + 3] = fmaxf(fmaf(v[j + 3], sc.w, sh.w), lower);
+                }
+            };
+            if (MODE == 2) {
+                // last conv of a FastDVDnet DenBlock: the 3 real channels leave as planar frames, residual form
+                // in1 - net (models.py:196) applied here; lanes are consecutive pixels -> coalesced plane accesses
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float t = v[j + e] * s_scale[c0 + j + e] + s_shift[c0 + j + e];
-                        if (p.relu) t = fmaxf(t, 0.f);
-                        t += radd[e];
-                        out[j + e] = p.round_tf32 ? rna_tf32(t) : t;
+                for (int i = 0; i < PIN_ROWS; ++i) {
+                    const int t = g + i * EPI_WG;
+                    if (t < rows) {
+                        float v[32];
+                        unit(t, 0, v);
+                        if (valid) {
+                            const long o = (long)n * 3 * pl_plane + (long)(y0 + t) * p.W + wo;
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) p.planar_out[o + c * pl_plane] = pin[i][c] - v[c];
+                        }
                     }
                 }
-                if (p.dbg & 4) {
-                    if (out[0] == 123.456f) p.y[0] = out[1];          // keep the values alive, store nothing
-                } else if (p.planar_out) {
-                    // last conv of a FastDVDnet DenBlock: the 3 real channels leave as planar frames, residual form
-                    // in1 - net (models.py:196) applied here; lanes are consecutive pixels -> coalesced plane accesses
-                    if (valid && c0 == 0) {
-                        const long o = (long)n * 3 * pl_plane + (long)ho * p.W + wo;
-                        float nxt[3] = {0.f, 0.f, 0.f};
-                        if (t + 1 < rows) {
+            } else {
+                for (int u = g; u < units; u += EPI_WG) {
+                    const int t = u / nch, c0 = (u - t * nch) << 5;
+                    const int ho = y0 + t;
+                    float v[32];
+                    unit(t, c0, v);
+                    if (MODE == 1 || MODE == 3) {
+                        float4 rn[8];
 #pragma unroll
-                            for (int c = 0; c < 3; ++c) nxt[c] = __ldg(p.planar_in1 + o + p.W + c * pl_plane);
+                        for (int j = 0; j < 8; ++j) rn[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        const int un = u + EPI_WG;
+                        if (p.residual && valid && un < units) {          // prefetch the skip values of this warp's next unit
+                            const int tn = un / nch;
+                            const float4* rp = reinterpret_cast<const float4*>(p.residual + out_offset(y0 + tn, (un - tn * nch) << 5));
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) rn[j] = __ldg(rp + j);
                         }
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) { p.planar_out[o + c * pl_plane] = pin[c] - out[c]; pin[c] = nxt[c]; }
+                        for (int j = 0; j < 8; ++j) {
+                            v[4 * j] += rr[j].x; v[4 * j + 1] += rr[j].y; v[4 * j + 2] += rr[j].z; v[4 * j + 3] += rr[j].w;
+                            rr[j] = rn[j];
+                        }
                     }
-                } else if (p.tma_store) {
-                    // coalesced path: the warp's 32 pixels x 32 channels go through a 128B-swizzled 4 KB staging tile and
-                    // leave as ONE TMA store (box {32 ch, 32 px}; PixelShuffle = element stride 2 on the pixel axis of a map
-                    // over the up-sampled tensor); out-of-image pixels are clipped by TMA
-                    const uint32_t sbuf = stage_out_base + (uint32_t)(q * p.out_bufs + (p.out_bufs == 2 ? (st_cnt & 1) : 0)) * 4096u;
-                    if (lane == 0) {
-                        if (p.out_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                        else                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    }
-                    __syncwarp();
+                    if (p.round_tf32) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const uint32_t a = sbuf + (uint32_t)lane * 128u + (uint32_t)(((j >> 2) ^ (lane & 7)) << 4);
-                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(out[j]), "f"(out[j + 1]), "f"(out[j + 2]), "f"(out[j + 3]) : "memory");
+                        for (int j = 0; j < 32; ++j) v[j] = rna_tf32(v[j]);
                     }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) {
-                        const int cg = p.col0 + c0;
-                        int cx = cg, cw = wt * 128 + q * 32, chh = ho;
-                        if (p.ps) { const int qq = cg / Cq; cx = cg % Cq; cw = 2 * cw + (qq & 1); chh = 2 * ho + (qq >> 1); }
-                        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                                     ::"l"(&tmY), "r"(sbuf), "r"(cx), "r"(cw), "r"(chh), "r"(n) : "memory");
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    }
-                    ++st_cnt;
-                } else if (valid) {
-                    float* yp = p.y + out_offset(ho, c0);
+                    if (MODE == 3) {
+                        if (valid) {
+                            float* yp = p.y + out_offset(ho, c0);
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(yp + j) = make_float4(out[j], out[j + 1], out[j + 2], out[j + 3]);
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<float4*>(yp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        }
+                    } else {
+                        // coalesced path: the warp's 32 pixels x 32 channels go through a 128B-swizzled 4 KB staging tile and
+                        // leave as ONE TMA store (box {32 ch, 32 px}; PixelShuffle = element stride 2 on the pixel axis of a map
+                        // over the up-sampled tensor); out-of-image pixels are clipped by TMA
+                        const uint32_t sbuf = sbuf0 + (p.out_bufs == 2 ? (st_cnt & 1) * 4096u : 0u);
+                        if (lane == 0) {
+                            if (p.out_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                            else                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const uint32_t a = sbuf + (uint32_t)lane * 128u + (uint32_t)(((j >> 2) ^ (lane & 7)) << 4);
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) {
+                            const int cg = p.col0 + c0;
+                            int cx = cg, cw = wt * 128 + q * 32, chh = ho;
+                            if (p.ps) { const int qq = cg / Cq; cx = cg % Cq; cw = 2 * cw + (qq & 1); chh = 2 * ho + (qq >> 1); }
+                            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                                         ::"l"(&tmY), "r"(sbuf), "r"(cx), "r"(cw), "r"(chh), "r"(n) : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                        ++st_cnt;
+                    }
                 }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) rr[j] = rn[j];
             }
-          }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -790,19 +832,30 @@ int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream, int col0, int ncol
     p.k_chunks = p.Cin / KCH;
     const int b_bytes = p.Cout * KCH * 4;
     p.tma_store = (env_int("SCI_CONV_TMA_STORE", 1) && !p.planar_out) ? 1 : 0;
+    const int mode = p.planar_out ? 2 : (!p.tma_store ? 3 : (d->residual ? 1 : 0));
     const int w_bytes = 9 * p.k_chunks * b_bytes;
-    // shared-memory plan: [resident weights] [pipeline stages] [store staging: 4 warps x out_bufs x 4 KB]
+    // shared-memory plan: [resident weights] [pipeline stages] [store staging: 4 * epi_wg warps x out_bufs x 4 KB].
+    // Two epilogue warpgroups (see the kernel comment) unless their extra staging would cost the weights their residency.
     const int total_budget = 214 * 1024;
-    int out_stage = 0, budget = 0;
-    for (p.out_bufs = 2; p.out_bufs >= 1; --p.out_bufs) {
-        out_stage = p.tma_store ? 4 * p.out_bufs * 4096 : 0;
-        budget = total_budget - out_stage;
-        p.resident = (w_bytes + 3 * A2_STAGE <= budget) ? 1 : 0;
-        const int sb = A2_STAGE + (p.resident ? 0 : 3 * b_bytes);
-        const int st = (budget - (p.resident ? w_bytes : 0)) / sb;
-        const bool would_be_resident = w_bytes + 3 * A2_STAGE <= total_budget - 4 * 4096;
-        if ((p.resident || !would_be_resident) && st >= 3) break;
-        if (p.out_bufs == 1) break;
+    int out_stage = 0, budget = 0, epi_wg = 2;
+    const int epi_env = env_int("SCI_CONV_EPI_WG", 0);
+    // measured per layer (tools/pass_layers.py): the second warpgroup pays where the epilogue work per MMA is high (K <= 32:
+    // 12->90 0.270 -> 0.255 ms, or a skip-add: 64->128+PS 0.251 -> 0.178 ms) and costs where the MMA-issuing warp is the
+    // critical path and now shares its scheduler with two epilogue warps (128->128: 0.067 -> 0.078 ms)
+    const int epi_first = epi_env ? (epi_env == 1 ? 1 : 2) : ((d->Cin <= 32 || d->residual) ? 2 : 1);
+    for (epi_wg = epi_first; epi_wg >= 1; --epi_wg) {
+        for (p.out_bufs = (epi_wg == 2 ? 1 : 2); p.out_bufs >= 1; --p.out_bufs) {
+            out_stage = p.tma_store ? 4 * epi_wg * p.out_bufs * 4096 : 0;
+            budget = total_budget - out_stage;
+            p.resident = (w_bytes + 3 * A2_STAGE <= budget) ? 1 : 0;
+            const int sb = A2_STAGE + (p.resident ? 0 : 3 * b_bytes);
+            const int st = (budget - (p.resident ? w_bytes : 0)) / sb;
+            const bool would_be_resident = w_bytes + 3 * A2_STAGE <= total_budget - (p.tma_store ? 4 * epi_wg * 4096 : 0);
+            if ((p.resident || !would_be_resident) && st >= 3) break;
+            if (p.out_bufs == 1) break;
+        }
+        const bool resident_with_one = w_bytes + 3 * A2_STAGE <= total_budget - (p.tma_store ? 4 * 4096 : 0);
+        if (epi_wg == 1 || epi_env == 2 || p.resident || !resident_with_one) break;
     }
     if (env_int("SCI_CONV_RESIDENT", 1) == 0) p.resident = 0;
     const int stage_bytes = A2_STAGE + (p.resident ? 0 : 3 * b_bytes);
@@ -857,28 +910,34 @@ int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream, int col0, int ncol
     }
     const size_t smem = (size_t)(p.resident ? w_bytes : 0) + (size_t)p.stages * stage_bytes + out_stage + 1024;
     if (smem > 220 * 1024) return sci_fail(SCI_EUNSUPPORTED, "conv tc v2: shared memory budget exceeded");
-    static bool attr_set[64] = {};
+    typedef void (*Fwd2Kernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const Fwd2Params);
+    static const Fwd2Kernel kernels[2][4] = {
+        {conv_fwd2_tc_kernel<1, 0>, conv_fwd2_tc_kernel<1, 1>, conv_fwd2_tc_kernel<1, 2>, conv_fwd2_tc_kernel<1, 3>},
+        {conv_fwd2_tc_kernel<2, 0>, conv_fwd2_tc_kernel<2, 1>, conv_fwd2_tc_kernel<2, 2>, conv_fwd2_tc_kernel<2, 3>}};
+    const Fwd2Kernel kern = kernels[epi_wg - 1][mode];
+    static bool attr_set[64][2][4] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(conv_fwd2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (dev < 0 || dev >= 64 || !attr_set[dev][epi_wg - 1][mode]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         if (e != cudaSuccess) return sci_fail(SCI_ELAUNCH, "conv tc v2: smem attribute", e);
-        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+        if (dev >= 0 && dev < 64) attr_set[dev][epi_wg - 1][mode] = true;
     }
     const int grid = min(p.num_tiles, SCI_NUM_SMS);
+    const int threads = 128 + 128 * epi_wg;
     p.pdl = (d->pdl && env_int("SCI_CONV_PDL", 1)) ? 1 : 0;
     if (p.pdl) {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = sci_stream(stream);
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = sci_stream(stream);
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, conv_fwd2_tc_kernel, tmA, tmB, tmY, p);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmY, p);
         if (e != cudaSuccess) return sci_fail(SCI_ELAUNCH, "conv tc fwd v2 (PDL launch)", e);
         return SCI_OK;
     }
-    conv_fwd2_tc_kernel<<<grid, TC_THREADS, smem, sci_stream(stream)>>>(tmA, tmB, tmY, p);
+    kern<<<grid, threads, smem, sci_stream(stream)>>>(tmA, tmB, tmY, p);
     SCI_CHECK_LAUNCH("conv tc fwd v2");
     return SCI_OK;
 }
