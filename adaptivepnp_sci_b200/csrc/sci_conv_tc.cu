@@ -104,6 +104,19 @@ __device__ __forceinline__ void tc_mma_tf32_elect(uint32_t d_tmem, uint64_t ades
         "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
+// K-major SWIZZLE_128B descriptor split into its 32-bit halves: the low word carries the start address (>> 4) and
+// LBO = 16 B, the high word (SBO = 1024 B, version 1, layout SWIZZLE_128B) never changes.  Advancing an operand by whole
+// 16-byte units inside the tile is then ONE 32-bit add on the low word.
+constexpr uint32_t DESC_HI_K128 = 0x40004040u;
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | 0x10000u; }
+__device__ __forceinline__ void mma_tf32_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accum), "r"(DESC_HI_K128) : "memory");
+}
 __device__ __forceinline__ void tc_commit_elect(uint64_t* bar) {
     asm volatile(
         "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
@@ -433,11 +446,17 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (warp-uniform loop, one elected lane issues) =====
+        // ===== MMA issuer =====
+        // Round 2: the ncu source view showed this warp as the critical path of EVERY layer: ~15 SASS instructions per
+        // UTCHMMA (ELECT + VOTEU per instruction, 64-bit descriptor arithmetic in vector registers, four R2UR) at ~6 cycles
+        // each = ~100 cycles per MMA, against 40-64 cycles of shared-memory operand reads (N = 32..128).  Now: all lanes wait
+        // on the barriers (warp-uniform), ONE lane elected once issues a stage's MMAs in straight-line code; descriptors are
+        // a per-stage 32-bit low word plus compile-time increments, the high word is a constant.
+        const bool leader = elect_one();
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Cout >> 3) << 17) | ((128u >> 4) << 24);
-        const uint64_t desc_hi = umma_desc(0, 16, 1024);          // everything but the start-address field
         if (p.resident) { mbar_wait(&w_bar, 0); tc_fence_after(); }
         int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+        const uint32_t b_tile_lo = b_bytes >> 4;                  // one [Cout][32 ch] weight tile, in descriptor units
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
             tc_fence_after();
@@ -445,24 +464,28 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int rows = min(p.R, p.H - hg * p.R);
             const uint32_t d_base = tmem_base + (uint32_t)(acc * p.R * p.acc_stride);
             if (p.R == 1) {
-                // one output row per tile: straight-line issue (the issuing thread is the critical path of the wide layers)
+                // one output row per tile (streamed or resident weights)
                 for (int r = 0; r < 3; ++r) {
                     for (int kc = 0; kc < p.k_chunks; ++kc) {
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
-                        const uint32_t a_addr = ring_base + (uint32_t)stage * stage_bytes;
-                        const uint32_t b_base = p.resident ? smem_base + (uint32_t)(r * 3 * p.k_chunks + kc) * b_bytes : a_addr + A2_STAGE;
-                        const uint32_t b_step = p.resident ? (uint32_t)p.k_chunks * b_bytes : b_bytes;
+                        if (leader) {
+                            const uint32_t a_addr = ring_base + (uint32_t)stage * stage_bytes;
+                            const uint32_t a_lo = desc_lo(a_addr);
+                            const uint32_t b_lo = desc_lo(p.resident ? smem_base + (uint32_t)(r * 3 * p.k_chunks + kc) * b_bytes : a_addr + A2_STAGE);
+                            const uint32_t b_step = p.resident ? (uint32_t)p.k_chunks * b_tile_lo : b_tile_lo;
+                            const uint32_t first = (uint32_t)((r | kc) != 0);
+                            if (!(p.dbg & 1)) {
 #pragma unroll
-                        for (int s = 0; s < 3; ++s) {
+                                for (int s = 0; s < 3; ++s) {
 #pragma unroll
-                            for (int k = 0; k < KCH / 8; ++k) {
-                                const uint64_t ad = desc_hi | (uint64_t)(((a_addr + s * 128 + k * 32) & 0x3FFFFu) >> 4);
-                                const uint64_t bd = desc_hi | (uint64_t)(((b_base + s * b_step + k * 32) & 0x3FFFFu) >> 4);
-                                if (!(p.dbg & 1)) tc_mma_tf32_elect(d_base, ad, bd, idesc, (uint32_t)((r | kc | s | k) != 0));
+                                    for (int k = 0; k < KCH / 8; ++k)
+                                        mma_tf32_lo(d_base, a_lo + s * 8 + k * 2, b_lo + s * b_step + k * 2, idesc, (s | k) ? 1u : first);
+                                }
                             }
+                            tc_commit(&empty_bar[stage]);
                         }
-                        tc_commit_elect(&empty_bar[stage]);
+                        __syncwarp();
                         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                     }
                 }
@@ -477,64 +500,72 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const int nr = r_hi - r_lo + 1;
                     const uint32_t d_col = d_base + (uint32_t)((p.R - 1 - (j - r_lo)) * p.acc_stride);
                     const uint32_t idesc_n = (idesc & ~(0x3Fu << 17)) | ((uint32_t)((nr * p.Cout) >> 3) << 17);
-                    const uint32_t idesc_1 = idesc;                                               // N = Cout
                     const uint32_t idesc_m = (idesc & ~(0x3Fu << 17)) | ((uint32_t)(((nr - 1) * p.Cout) >> 3) << 17);
                     for (int kc = 0; kc < p.k_chunks; ++kc) {
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
-                        const uint32_t a_addr = ring_base + (uint32_t)stage * stage_bytes;
+                        if (leader) {
+                            const uint32_t a_lo = desc_lo(ring_base + (uint32_t)stage * stage_bytes);
+                            // weight tiles ordered [s][kc][r]: the three filter rows of tap s are consecutive
+                            const uint32_t b_lo = desc_lo(smem_base + (uint32_t)(kc * 3 + r_lo) * b_bytes);
+                            const uint32_t b_step = (uint32_t)(3 * p.k_chunks) * b_tile_lo;
+                            if (p.dbg & 1) {
+                            } else if (r_lo == 0 && kc == 0) {
+                                // this row opens the accumulator of output row t = j (r = 0): that slice must overwrite
+                                mma_tf32_lo(d_col, a_lo, b_lo, idesc, 0u);
+                                if (nr > 1) mma_tf32_lo(d_col + (uint32_t)p.acc_stride, a_lo, b_lo + b_tile_lo, idesc_m, 1u);
 #pragma unroll
-                        for (int s = 0; s < 3; ++s) {
-                            const uint32_t b_tile = smem_base + (uint32_t)((s * p.k_chunks + kc) * 3) * b_bytes;
+                                for (int sk = 1; sk < 3 * (KCH / 8); ++sk) {
+                                    const int s = sk / (KCH / 8), k = sk % (KCH / 8);
+                                    mma_tf32_lo(d_col, a_lo + s * 8 + k * 2, b_lo + s * b_step + k * 2, idesc_n, 1u);
+                                }
+                            } else {
 #pragma unroll
-                            for (int k = 0; k < KCH / 8; ++k) {
-                                const uint64_t ad = desc_hi | (uint64_t)(((a_addr + s * 128 + k * 32) & 0x3FFFFu) >> 4);
-                                if (p.dbg & 1) continue;
-                                if (r_lo == 0 && (kc | s | k) == 0) {
-                                    // this row opens the accumulator of output row t = j (r = 0): that slice must overwrite
-                                    const uint64_t b0 = desc_hi | (uint64_t)(((b_tile + k * 32) & 0x3FFFFu) >> 4);
-                                    tc_mma_tf32_elect(d_col, ad, b0, idesc_1, 0u);
-                                    if (nr > 1) {
-                                        const uint64_t b1 = desc_hi | (uint64_t)(((b_tile + b_bytes + k * 32) & 0x3FFFFu) >> 4);
-                                        tc_mma_tf32_elect(d_col + (uint32_t)p.acc_stride, ad, b1, idesc_m, 1u);
-                                    }
-                                } else {
-                                    const uint64_t bd = desc_hi | (uint64_t)(((b_tile + (uint32_t)r_lo * b_bytes + k * 32) & 0x3FFFFu) >> 4);
-                                    tc_mma_tf32_elect(d_col, ad, bd, idesc_n, 1u);
+                                for (int s = 0; s < 3; ++s) {
+#pragma unroll
+                                    for (int k = 0; k < KCH / 8; ++k)
+                                        mma_tf32_lo(d_col, a_lo + s * 8 + k * 2, b_lo + s * b_step + k * 2, idesc_n, 1u);
                                 }
                             }
+                            tc_commit(&empty_bar[stage]);
                         }
-                        tc_commit_elect(&empty_bar[stage]);
+                        __syncwarp();
                         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                     }
                 }
-            } else
-            for (int j = 0; j < rows + 2; ++j) {
-                for (int kc = 0; kc < p.k_chunks; ++kc) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = ring_base + (uint32_t)stage * stage_bytes;
-                    // the loaded input row is filter row r = j - t of every output row t of the super-tile it touches
-                    for (int t = max(0, j - 2); t <= min(rows - 1, j); ++t) {
-                        const int r = j - t;
-                        const uint32_t d_tmem = d_base + (uint32_t)(t * p.acc_stride);
-                        const uint32_t b_base = p.resident ? smem_base + (uint32_t)(r * 3 * p.k_chunks + kc) * b_bytes : a_addr + A2_STAGE;
-                        const uint32_t b_step = p.resident ? (uint32_t)p.k_chunks * b_bytes : b_bytes;
+            } else {
+                for (int j = 0; j < rows + 2; ++j) {
+                    for (int kc = 0; kc < p.k_chunks; ++kc) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        if (leader) {
+                            const uint32_t a_addr = ring_base + (uint32_t)stage * stage_bytes;
+                            const uint32_t a_lo = desc_lo(a_addr);
+                            // the loaded input row is filter row r = j - t of every output row t of the super-tile it touches
+                            for (int t = max(0, j - 2); t <= min(rows - 1, j); ++t) {
+                                const int r = j - t;
+                                const uint32_t d_tmem = d_base + (uint32_t)(t * p.acc_stride);
+                                const uint32_t b_lo = desc_lo(p.resident ? smem_base + (uint32_t)(r * 3 * p.k_chunks + kc) * b_bytes : a_addr + A2_STAGE);
+                                const uint32_t b_step = p.resident ? (uint32_t)p.k_chunks * b_tile_lo : b_tile_lo;
+                                const uint32_t first = (uint32_t)((r | kc) != 0);
+                                if (!(p.dbg & 1)) {
 #pragma unroll
-                        for (int s = 0; s < 3; ++s) {
+                                    for (int s = 0; s < 3; ++s) {
 #pragma unroll
-                            for (int k = 0; k < KCH / 8; ++k) {
-                                const uint64_t ad = desc_hi | (uint64_t)(((a_addr + s * 128 + k * 32) & 0x3FFFFu) >> 4);
-                                const uint64_t bd = desc_hi | (uint64_t)(((b_base + s * b_step + k * 32) & 0x3FFFFu) >> 4);
-                                if (!(p.dbg & 1)) tc_mma_tf32_elect(d_tmem, ad, bd, idesc, (uint32_t)((r | kc | s | k) != 0));
+                                        for (int k = 0; k < KCH / 8; ++k)
+                                            mma_tf32_lo(d_tmem, a_lo + s * 8 + k * 2, b_lo + s * b_step + k * 2, idesc, (s | k) ? 1u : first);
+                                    }
+                                }
                             }
+                            tc_commit(&empty_bar[stage]);
                         }
+                        __syncwarp();
+                        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                     }
-                    tc_commit_elect(&empty_bar[stage]);
-                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
             }
-            tc_commit_elect(&tfull_bar[acc]);
+            if (leader) tc_commit(&tfull_bar[acc]);
+            __syncwarp();
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
     } else if (warp >= 4) {

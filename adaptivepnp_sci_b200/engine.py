@@ -436,8 +436,13 @@ class FastDVDnetEngine(_EngineBase):
         s1 = g(keep("s1"), (B, h2, w2, 64), dev);          self.conv(L[10], u2b, B, h4, w4, s1, residual=x1)
         u1a = g(keep("u1a"), (B, h2, w2, 64), dev);        self.conv(L[11], s1, B, h2, w2, u1a)
         u1b = g(keep("u1b"), (B, h2, w2, 64), dev);        self.conv(L[12], u1a, B, h2, w2, u1b)
-        s0 = g(keep("s0"), (B, H, W, 32), dev);            self.conv(L[13], u1b, B, h2, w2, s0, residual=x0)
-        o0 = g(keep("o0"), (B, H, W, 32), dev);            self.conv(L[14], s0, B, H, W, o0)
+        # inference: the packed input is dead once a0 exists and x0 once s0 exists -> s0 / o0 reuse their buffers (two
+        # full-resolution tensors less: 26 GB at 2048x2048x24)
+        alias = (not train) and L[0].Ci_pad == 32 and L[1].Co_pad == 32
+        s0 = a_in if alias else g(keep("s0"), (B, H, W, 32), dev)
+        self.conv(L[13], u1b, B, h2, w2, s0, residual=x0)
+        o0 = x0 if alias else g(keep("o0"), (B, H, W, 32), dev)
+        self.conv(L[14], s0, B, H, W, o0)
         if self.impl == IMPL_TC and L[15].Co_pad == 32:
             xo = None                                       # fused epilogue: out = frames - conv, planar, no NHWC tensor
             self.conv(L[15], o0, B, H, W, None, round_out=False, planar=(frames, out))

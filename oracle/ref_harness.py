@@ -22,11 +22,16 @@ import types
 import numpy as np
 
 REF_ROOT = os.environ.get("SCI_REFERENCE_ROOT", "/root/reference")
+# ``baseline/_ref``: a git-ignored copy of the reference's Python sources made by ``baseline/install_ref.py`` in the build
+# container.  Unlike /root/reference it travels to the GPU box with the snapshot, where ``bench.py`` runs the UNMODIFIED
+# reference on the same B200 through PyTorch eager (``gpu_eager_baseline``) - the honest same-box comparator.
+BASELINE_REF = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
 _loaded = {}
 
 
-def available():
-    return os.path.isdir(REF_ROOT) and os.path.isfile(os.path.join(REF_ROOT, "utilspy.py"))
+def available(root=None):
+    root = root or REF_ROOT
+    return os.path.isdir(root) and os.path.isfile(os.path.join(root, "utilspy.py"))
 
 
 def _stub(name, **attrs):
@@ -36,7 +41,7 @@ def _stub(name, **attrs):
     return m
 
 
-def _install_shims():
+def _install_shims(cpu=True):
     import torch
     from . import iqa, tv_chambolle
 
@@ -68,6 +73,8 @@ def _install_shims():
         sk.metrics._structural_similarity = _stub("skimage.metrics._structural_similarity",
                                                   structural_similarity=iqa.compare_ssim)
         sk.measure = _stub("skimage.measure", compare_psnr=iqa.compare_psnr, compare_ssim=iqa.compare_ssim)
+    if not cpu:
+        return
     # CPU execution of hard-coded .cuda() calls
     torch.Tensor.cuda = lambda self, *a, **k: self
     torch.nn.Module.cuda = lambda self, *a, **k: self
@@ -75,15 +82,17 @@ def _install_shims():
     torch.cuda.manual_seed = lambda *a, **k: None
 
 
-def load():
-    """Returns a namespace with the reference's hot-path modules."""
+def load(root=None, device="cpu"):
+    """Returns a namespace with the reference's hot-path modules.  ``device='cuda'`` leaves the reference's hard-coded
+    ``.cuda()`` calls alone (the GPU-eager baseline of bench.py); the default neutralises them (CPU golden generation)."""
     if _loaded:
         return _loaded["ns"]
-    if not available():
-        raise RuntimeError("reference tree not present at %s" % REF_ROOT)
-    _install_shims()
-    if REF_ROOT not in sys.path:
-        sys.path.insert(0, REF_ROOT)
+    root = root or REF_ROOT
+    if not available(root):
+        raise RuntimeError("reference tree not present at %s" % root)
+    _install_shims(cpu=(device == "cpu"))
+    if root not in sys.path:
+        sys.path.insert(0, root)
     import importlib
     ns = types.SimpleNamespace()
     ns.utilspy = importlib.import_module("utilspy")
