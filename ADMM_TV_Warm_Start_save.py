@@ -20,13 +20,15 @@ from adaptivepnp_sci_b200.dvp_linear_inv_2_stage_ADMM_tensor_online import admm_
 from adaptivepnp_sci_b200.utilspy import mkdir, worker_init_fn
 
 
-def main():
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--datasetdir", default="./dataset/cacti/mid_scale")
     ap.add_argument("--synthetic", action="store_true", help="use the deterministic synthetic videos")
     ap.add_argument("--videos", type=int, default=6)
     ap.add_argument("--nmea", type=int, default=4)
-    args = ap.parse_args()
+    ap.add_argument("--synthetic-size", default="512x512x8", help="HxWxB of the synthetic videos (tests use a small one)")
+    args = ap.parse_args(argv)
+    shape = tuple(int(v) for v in args.synthetic_size.split('x'))
     ctx = parallel.init()
     worker_init_fn(0)
     resultsdir = "results/New1/" + str(int(time.time()))
@@ -38,7 +40,7 @@ def main():
     average_psnr, average_ssim = [], []
     for datname in matio.VIDEOS[:args.videos]:
         f.write(datname + ':\n')
-        meas_bayer, mask_bayer, orig_bayer = matio.load_video(args.datasetdir, datname, args.nmea,
+        meas_bayer, mask_bayer, orig_bayer = matio.load_video(args.datasetdir, datname, args.nmea, synthetic_shape=shape,
                                                               force_synthetic=args.synthetic)
         nrows, ncols, nmea = meas_bayer.shape
         nmask = mask_bayer.shape[2]

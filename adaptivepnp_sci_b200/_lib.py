@@ -38,7 +38,7 @@ PROTOTYPES = {
     "sci_A": [_p, _l, _l, _l, _p, _l, _l, _l, _p, _l, _l, _i, _i, _i, _p],
     "sci_At": [_p, _l, _l, _p, _l, _l, _l, _p, _l, _l, _l, _i, _i, _i, _p],
     "sci_project_stage1": [_p, _p, _p, _p, _p, _p, _l, _i, _f, _f, _p, _p, _p],
-    "sci_project_stage2": [_p, _p, _p, _p, _p, _p, _l, _i, _f, _f, _p],
+    "sci_project_stage2": [_p, _p, _p, _p, _p, _p, _l, _i, _d, _d, _p],
     "sci_tv_chambolle2d": [_p, _p, _f, _p, _p, _f, _i, _i, _i, _i, _f, _f, _i, _p, _sz, _p, _p],
     "sci_malvar2004": [_p, _p, _f, _p, _f, _p, _p, _i, _i, _i, _p],
     "sci_dual_update_rgb": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p],

@@ -320,10 +320,11 @@ extern "C" int sci_project_stage1(const float* theta, const float* b, const floa
 }
 
 extern "C" int sci_project_stage2(const float* theta, const float* b, const float* phi, const float* y,
-                                  const float* phisum, float* x, long npix, int B, float alpha, float rho, void* stream) {
-    // (1/rou) and alpha*rou are python doubles in the reference, cast to fp32 at the tensor op
-    const float c_b = -(float)(1.0 / (double)rho);
-    const float c_den = (float)((double)alpha * (double)rho);
+                                  const float* phisum, float* x, long npix, int B, double alpha, double rho, void* stream) {
+    // (1/rou) and alpha*rou are python doubles in the reference, cast to fp32 at the tensor op: rho arrives as a double so
+    // that float32(1/0.55) = 1.8181819f is formed exactly as there (a float rho gave 1.8181818f, 1 ulp off)
+    const float c_b = -(float)(1.0 / rho);
+    const float c_den = (float)(alpha * rho);
     return project_launch(theta, b, phi, y, phisum, x, npix, B, c_b, 1.0f, c_den, nullptr, nullptr, stream);
 }
 

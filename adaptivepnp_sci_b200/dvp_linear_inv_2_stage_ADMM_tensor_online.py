@@ -264,7 +264,8 @@ def twoStageAdmm_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, gamma=0.01,
     if name == 'fastdvd_color' and update_:
         # The FastDVDnet fine-tune perturbs its input with HOST numpy-RNG noise (utils_image.py:183-192); a helper
         # thread keeps those draws ahead of the GPU with exact global-RNG semantics (fastdvdnet_adapter.NoiseStream).
-        fastdvdnet_adapter.noise_stream.prefetch((B, 3, H, W))
+        # (tiled mode: every rank draws the noise of the WHOLE frame and cuts its rows out, so that is the shape to run ahead with)
+        fastdvdnet_adapter.noise_stream.prefetch((B, 3, tile.H_total if tile is not None else H, W))
     for idx, nsig in enumerate(sigma):
         for _ in range(iter_max[idx]):
             # p = theta - b/rho ; x = p + Phi*((y - A p)/(alpha*rho + Phi_sum))                     (:128-140)

@@ -168,7 +168,9 @@ class NoiseStream:
     def _worker(self, epoch):
         while True:
             with self.lock:
-                while self.epoch == epoch and len(self.queue) >= self.depth:
+                # whole-frame draws of the tiled mode are gigabytes each: keep one ahead, not ``depth``
+                depth = 1 if int(np.prod(self.shape)) > (1 << 25) else self.depth
+                while self.epoch == epoch and len(self.queue) >= depth:
                     self.lock.wait()
                 if self.epoch != epoch:
                     return
@@ -178,6 +180,7 @@ class NoiseStream:
             after = rs.get_state()
             with self.lock:
                 if self.epoch != epoch:
+                    _release_host_buffer(arr)         # drawn for a stream that was restarted meanwhile: back to the pool
                     return
                 self.queue.append((shape, before, after, arr))
                 self.lock.notify_all()

@@ -16,8 +16,20 @@ from .synthetic import make_case
 VIDEOS = ['Beauty_bayer', 'Bosphorus_bayer', 'Jockey_bayer', 'Runner_bayer', 'ShakeNDry_bayer', 'Traffic_bayer']
 
 
-def load_video(datasetdir, datname, nmea=4, synthetic_shape=(512, 512, 8), force_synthetic=False):
-    """Returns meas_bayer [H,W,nmea] (0..255 scale), mask_bayer [H,W,B], orig_bayer [H,W,B*nmea] (0..255 scale)."""
+def video_shape(datasetdir, datname, synthetic_shape=(512, 512, 8), force_synthetic=False):
+    """(H, W, B) of a video without keeping its data (used to fast-forward the fine-tune noise stream over videos another
+    rank owns)."""
+    path = os.path.join(datasetdir, datname + '.mat')
+    if not force_synthetic and os.path.exists(path):
+        mask = load_video(datasetdir, datname)[1]
+        return mask.shape
+    return tuple(synthetic_shape)
+
+
+def load_video(datasetdir, datname, nmea=4, synthetic_shape=(512, 512, 8), force_synthetic=False, with_orig_real=False):
+    """Returns meas_bayer [H,W,nmea] (0..255 scale), mask_bayer [H,W,B], orig_bayer [H,W,B*nmea] (0..255 scale)
+    [, orig_real: the file's 'orig' array as stored (ADMM_TV_Warm_Start_save.py:74), which the scripts copy into their
+    result files; the synthetic videos have no RGB ground truth on file, their Bayer ground truth stands in]."""
     path = os.path.join(datasetdir, datname + '.mat')
     if not force_synthetic and os.path.exists(path):
         try:
@@ -28,8 +40,9 @@ def load_video(datasetdir, datname, nmea=4, synthetic_shape=(512, 512, 8), force
             meas = np.float32(np.array(f['meas_bayer']))
             mask = np.float32(np.array(f['mask_bayer'])).transpose((2, 1, 0))
             orig = np.float32(np.array(f['orig_bayer'])).transpose((2, 1, 0))
+            orig_real = np.array(f['orig']) if 'orig' in f else orig
         meas = meas.transpose((1, 0))[:, :, None] if meas.ndim < 3 else meas.transpose((2, 1, 0))
-        return meas, mask, orig
+        return (meas, mask, orig, orig_real) if with_orig_real else (meas, mask, orig)
     H, W, B = synthetic_shape
     vid = VIDEOS.index(datname) if datname in VIDEOS else 0
     meas_l, orig_l, mask = [], [], None
@@ -38,7 +51,8 @@ def load_video(datasetdir, datname, nmea=4, synthetic_shape=(512, 512, 8), force
         mask = msk if mask is None else mask
         meas_l.append((o * mask).sum(2) * 255.0)
         orig_l.append(o * 255.0)
-    return np.stack(meas_l, 2).astype(np.float32), mask, np.concatenate(orig_l, 2).astype(np.float32)
+    meas, orig = np.stack(meas_l, 2).astype(np.float32), np.concatenate(orig_l, 2).astype(np.float32)
+    return (meas, mask, orig, orig) if with_orig_real else (meas, mask, orig)
 
 
 def warm_start_path(savedmatdir, datname, nmask):

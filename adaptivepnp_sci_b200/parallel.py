@@ -24,6 +24,13 @@ class Context:
         """Indices of the independent units (measurement groups) this rank owns."""
         return list(range(self.rank, n, self.world))
 
+    def check_even_split(self, n, what="units"):
+        """Lock-step collectives (the shared-weight gradient all-reduce) need every rank to own the same number of units:
+        a rank without a unit would never enter the all-reduce and the others would hang in NCCL until the timeout."""
+        if n % self.world != 0:
+            raise ValueError("%d %s do not divide evenly over %d ranks: a shared-weight run needs equal shares "
+                             "(every rank joins every gradient all-reduce)" % (n, what, self.world))
+
     def gather_units(self, results):
         """dict{unit: payload} from every rank -> merged dict on rank 0 (others get {})."""
         if self.world == 1:
@@ -98,7 +105,11 @@ class TileContext:
         return a[self.r0:self.r0 + self.rows]
 
     def halo_sizes(self, halo):
-        halo = min(halo, self.rows)
+        if self.world > 1 and halo > self.rows:
+            # a strip shorter than the denoiser's receptive field would need rows from rank +-2 as well; clamping the halo
+            # would silently break the "tiled == un-tiled" guarantee
+            raise ValueError("tiled mode: strips of %d rows are shorter than the %d-row halo the denoiser needs "
+                             "(use fewer ranks for a %d-row frame)" % (self.rows, halo, self.H_total))
         return (halo if self.rank > 0 else 0), (halo if self.rank < self.world - 1 else 0)
 
     def exchange(self, own, halo):

@@ -4,8 +4,22 @@ Keeps the reference scripts' flow: per-video hyper-parameter tables (two_stage_A
 two_stage_ADMM_Online_FastDVD_Warm.py:66-166; ``--deep-demosaicking`` selects the scripts' ``deep_demosaicking=True``
 columns and demosaics with DDnet, the default is the Malvar columns),
 warm start from results/savedmat/_Admm_tv_<name>8.mat, loop over measurement groups with ``reuse_model``
-carry-over, log lines and the result .mat.  With torchrun the groups are sharded over ranks; ``--share-weights``
-keeps one set of denoiser weights across ranks via the NCCL gradient all-reduce (BASELINE config 4)."""
+carry-over, log lines and the result .mat (same keys as two_stage_ADMM_Online_FFD_Warm.py:320-330 /
+two_stage_ADMM_Online_FastDVD_Warm.py:356-365).
+
+Multi-GPU (torchrun), in order of fidelity to the reference:
+* default: VIDEOS are dealt to the ranks.  The model is rebuilt per video (:218-241), so a video is the largest unit
+  whose result does not depend on what ran before it - except for the fine-tune noise, which the FastDVDnet adapter
+  draws from the global numpy stream: a rank therefore fast-forwards that stream over the videos it does not own
+  (``skip_finetune_noise``: same draws, discarded), and every video's groups still run in order with the
+  ``reuse_model`` carry-over (:270-275).  Results equal the one-GPU / reference run.
+* ``--no-update``: nothing carries over between groups, so the (video, group) pairs are dealt to the ranks.
+* ``--share-weights`` (BASELINE config 4; a SEMANTIC CHANGE): the groups of a video run in lock-step on
+  the ranks, one set of denoiser weights kept identical by an NCCL mean all-reduce of the gradients.  Needs
+  ``nmea % world == 0`` (a rank without a group would never join the all-reduce).
+* ``--shard-groups``: the groups of a video are dealt to the ranks although the update carries weights over between
+  them in the reference; every rank then starts from the pristine weights and from seed 42 - results DIFFER from
+  the reference (a warning is printed)."""
 import argparse
 import os
 import time
@@ -80,34 +94,73 @@ def build_model(denoiser):
     return m.eval().cuda()
 
 
-def main(denoiser):
+def count_updates(iter_max, interval_iter, update_times, inital_iter=1):
+    """Number of fine-tune calls one reconstruction makes (dvp...online.py:200,247)."""
+    n, ui = 0, 0
+    for k in range(int(sum(iter_max))):
+        if k > inital_iter and k % interval_iter == 0 and (update_times < 0 or ui < update_times):
+            n += 1
+            ui += 1
+    return n
+
+
+def skip_finetune_noise(n_calls, shape):
+    """Advance the global numpy RNG exactly as ``n_calls`` FastDVDnet fine-tune calls would (utils_image.py:186)."""
+    from .fastdvdnet_adapter import _release_host_buffer, noise_stream
+    for _ in range(n_calls):
+        _release_host_buffer(noise_stream.get(shape))
+
+
+def main(denoiser, argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--datasetdir", default="./dataset/cacti/mid_scale")
     ap.add_argument("--synthetic", action="store_true")
+    ap.add_argument("--synthetic-size", default="512x512x8", help="HxWxB of the synthetic videos (tests use a small one)")
     ap.add_argument("--videos", type=int, default=6)
     ap.add_argument("--nmea", type=int, default=4)
     ap.add_argument("--no-update", action="store_true", help="plain PnP (update=False)")
     ap.add_argument("--deep-demosaicking", action="store_true", help="demosaic with DDnet (the reference scripts' default)")
     ap.add_argument("--share-weights", action="store_true", help="multi-GPU: one weight set, NCCL gradient all-reduce")
-    args = ap.parse_args()
+    ap.add_argument("--shard-groups", action="store_true", help="multi-GPU: deal the groups of a video to the ranks even with "
+                    "the online update (drops the reuse_model carry-over: results differ from the reference)")
+    ap.add_argument("--resultsdir", default=None)
+    args = ap.parse_args(argv)
     ctx = parallel.init()
     worker_init_fn(0)
     update, reuse_model = not args.no_update, True
+    if args.share_weights and ctx.world > 1:
+        ctx.check_even_split(args.nmea, "measurement groups")
+    # what is dealt to the ranks (see the module docstring)
+    by_group = ctx.world > 1 and (args.share_weights or args.shard_groups or not update)
+    by_video = ctx.world > 1 and not by_group
+    if args.shard_groups and update and not args.share_weights and ctx.world > 1 and ctx.rank == 0:
+        print('WARNING: --shard-groups with the online update: every rank starts from the pristine weights and from seed 42; '
+              'PSNR and the .mat output differ from a one-GPU / reference run (reuse_model carry-over dropped)')
     table = FFD_TABLE if denoiser == 'ffdnet_color' else FASTDVD_TABLE
-    resultsdir = "results/New1/" + str(int(time.time()))
+    resultsdir = args.resultsdir or ("results/New1/" + str(int(time.time())))
     if ctx.rank == 0:
         mkdir(resultsdir + '/')
-    f = open(resultsdir + '/log.txt', 'a') if ctx.rank == 0 else open(os.devnull, 'w')
-    f.write('cacti midscale bayer: \n')
-    average_psnr, average_ssim = [], []
-    for datname in matio.VIDEOS[:args.videos]:
+    ctx.barrier()
+    f = open(resultsdir + '/log.txt', 'a') if (ctx.rank == 0 or by_video) else open(os.devnull, 'w')
+    if ctx.rank == 0:
+        f.write('cacti midscale bayer: \n')
+    average_psnr, average_ssim = {}, {}
+    shape = tuple(int(v) for v in args.synthetic_size.split('x'))
+    for vi, datname in enumerate(matio.VIDEOS[:args.videos]):
         sig255, iter_max, lr, update_per_iter, interval_iter, update_times = table[datname]
         if args.deep_demosaicking:
             sig255, iter_max, interval_iter = (FFD_DEEP if denoiser == 'ffdnet_color' else FASTDVD_DEEP)[datname]
         sigma = [s / 255 for s in sig255]
+        mine = (not by_video) or (vi % ctx.world == ctx.rank)
+        if not mine:
+            if denoiser == 'fastdvd_color' and update:
+                # keep the global noise stream where the sequential run would have it after this video
+                H_, W_, B_ = matio.video_shape(args.datasetdir, datname, shape, force_synthetic=args.synthetic)
+                skip_finetune_noise(args.nmea * count_updates(iter_max, interval_iter, update_times), (B_, 3, H_, W_))
+            continue
         f.write(datname + ':\n')
-        meas_bayer, mask_bayer, orig_bayer = matio.load_video(args.datasetdir, datname, args.nmea,
-                                                              force_synthetic=args.synthetic)
+        meas_bayer, mask_bayer, orig_bayer, orig_real = matio.load_video(args.datasetdir, datname, args.nmea, synthetic_shape=shape,
+                                                                         force_synthetic=args.synthetic, with_orig_real=True)
         recon_tv = matio.load_warm_start('./results/savedmat/', datname, mask_bayer.shape[2])
         nrows, ncols, nmea = meas_bayer.shape
         nmask = mask_bayer.shape[2]
@@ -115,7 +168,7 @@ def main(denoiser):
         model_demosaic = build_demosaicker() if args.deep_demosaicking else None
         MAXB = 255.
         results = {}
-        for iframe in ctx.my_units(nmea):
+        for iframe in (ctx.my_units(nmea) if by_group else range(nmea)):
             f.write('Measurement Frame {}.\n'.format(iframe))
             meas_t = meas_bayer[:, :, iframe] / MAXB
             orig_t = orig_bayer[:, :, iframe * nmask:(iframe + 1) * nmask] / MAXB
@@ -127,7 +180,7 @@ def main(denoiser):
                               demosaic_method='malvar2004', lr_=lr, interval_iter=interval_iter, logf=f, update_=update,
                               update_per_iter=update_per_iter,
                               grad_sync=ctx.grad_sync if (args.share_weights and ctx.world > 1) else None, **kw)
-            rgb, v, psnr_, ssim_, _, refined_model, _ = out
+            rgb, v, psnr_, ssim_, psnr_all_t, refined_model, _ = out
             if reuse_model and update:
                 model_denoise = refined_model                                                # :270-275
             else:
@@ -136,26 +189,34 @@ def main(denoiser):
                 denoiser.upper(), datname, iframe, mean(psnr_), mean(ssim_), time.time() - begin)
             print(msg)
             f.write(msg + ' \n')
-            results[iframe] = (v, np.asarray(psnr_, np.float32), np.asarray(ssim_, np.float32))
-        results = ctx.gather_units(results)
-        if ctx.rank == 0:
+            results[iframe] = (v, np.asarray(psnr_, np.float32), np.asarray(ssim_, np.float32), np.asarray(psnr_all_t, np.float64))
+        if by_group:
+            results = ctx.gather_units(results)
+        if ctx.rank == 0 or by_video:
             v_all = np.concatenate([results[i][0] for i in range(nmea)], 2)
             psnr = np.concatenate([results[i][1] for i in range(nmea)]).reshape(-1, 1)
             ssim = np.concatenate([results[i][2] for i in range(nmea)]).reshape(-1, 1)
             print(round(float(psnr.mean()), 2), end=', ')
             print(round(float(ssim.mean()), 4))
-            average_psnr.append(float(psnr.mean()))
-            average_ssim.append(float(ssim.mean()))
+            average_psnr[vi] = float(psnr.mean())
+            average_ssim[vi] = float(ssim.mean())
             savedmatdir = resultsdir + '/savedmat/'
             os.makedirs(savedmatdir, exist_ok=True)
-            tag = 'ffdnet' if denoiser == 'ffdnet_color' else 'fastdvd'
+            # keys of the reference's result file (two_stage_ADMM_Online_FFD_Warm.py:320-330, ..._FastDVD_Warm.py:356-365)
+            tag = 'ffd' if denoiser == 'ffdnet_color' else 'fastdvd'
+            mat = {'v_twoStageAdmm_%s_gray_bayer' % tag: v_all, 'psnr_%s_gray' % tag: psnr, 'ssim_%s_gray' % tag: ssim,
+                   'orig_real': orig_real, 'meas_bayer': meas_bayer}
+            if denoiser == 'ffdnet_color':
+                mat['psnr_all_iter'] = [results[i][3] for i in range(nmea)]                 # FFD script only (:327)
             sio.savemat('{}twoStageAdmm_{}_{}{:d}_sigma{:d}_all7_log.mat'.format(savedmatdir, denoiser.lower(), datname, nmask,
-                                                                               int(sigma[-1] * MAXB)),
-                        {'v_twoStageAdmm_%s_gray_bayer' % tag: v_all, 'psnr_%s_gray' % tag: psnr, 'ssim_%s_gray' % tag: ssim,
-                         'meas_bayer': meas_bayer})
+                                                                               int(sigma[-1] * MAXB)), mat)
+    if by_video:
+        average_psnr = ctx.gather_units(average_psnr)
+        average_ssim = ctx.gather_units(average_ssim)
     if ctx.rank == 0 and average_psnr:
         print('all= ')
-        print(round(mean(average_psnr), 2), end=', ')
-        print(round(mean(average_ssim), 4))
+        print(round(mean(average_psnr.values()), 2), end=', ')
+        print(round(mean(average_ssim.values()), 4))
     f.close()
     ctx.finalize()
+    return resultsdir

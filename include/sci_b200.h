@@ -87,8 +87,9 @@ int sci_project_stage1(const float* theta, const float* b, const float* phi, con
                        const float* phisum, float* x, long npix, int B, float lambda_, float gamma,
                        const float* orig, double* sse, void* stream);
 int sci_project_stage2(const float* theta, const float* b, const float* phi, const float* y,
-                       const float* phisum, float* x, long npix, int B, float alpha, float rho,
-                       void* stream);
+                       const float* phisum, float* x, long npix, int B, double alpha, double rho,
+                       void* stream);   /* alpha, rho are Python doubles in the reference: (1/rou) and alpha*rou are formed
+                                           in double and cast to fp32 at the tensor op (dvp...online.py:131-140) */
 
 /* ---- K4: TV prior (Chambolle projection) + fused dual update --------------
  * Replaces the D2H -> skimage.restoration.denoise_tv_chambolle(weight, n_iter_max=5,

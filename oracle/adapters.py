@@ -76,7 +76,7 @@ def fastdvdnet_seqdenoise(seq, noise_std, windsize, model):
 
 def fastdvdnet_denoiser_full_tensor_v2(vnoisy, sigma, y_bayer=None, Phi=None, model=None, useGPU=True,
                                        lr_=1e-6, updata_=False, update_per_iter=1, gray=False,
-                                       update_times=-1, losses=None):
+                                       update_times=-1, losses=None, grad_hook=None, rng=None):
     """vnoisy[H,W,3,B]; y_bayer[h,w,4]; Phi[h,w,B,4]; ``model`` exposes ``.module``.
 
     Fine-tune quirk reproduced verbatim (test_fastdvdnet.py:359 with
@@ -88,7 +88,8 @@ def fastdvdnet_denoiser_full_tensor_v2(vnoisy, sigma, y_bayer=None, Phi=None, mo
         n_update_iter, lr_all = ([update_per_iter], [lr_]) if isinstance(update_per_iter, int) else (update_per_iter, lr_)
         mse = nn.MSELoss()
         v = vnoisy.permute(3, 2, 0, 1)                                   # [B,3,H,W]
-        noise = np.random.normal(0, 5 / 255, tuple(v.shape))             # utils_image.py:186
+        # ``rng`` / ``grad_hook`` exist for the MODIFIED oracle of the shared-weight configuration only (oracle/shared.py)
+        noise = (rng or np.random).normal(0, 5 / 255, tuple(v.shape))    # utils_image.py:186
         v_plus = v + torch.from_numpy(v.detach().numpy() + noise).float()  # :359
         Phi_bayer = fourCh2OneCh(Phi)                                     # :362
         y_one = fourCh2OneCh(y_bayer)                                     # :363
@@ -111,6 +112,8 @@ def fastdvdnet_denoiser_full_tensor_v2(vnoisy, sigma, y_bayer=None, Phi=None, mo
                 loss = mse(up_meas, y_one)                                 # :431
                 opt.zero_grad()
                 loss.backward()
+                if grad_hook is not None:
+                    grad_hook([p for p in model.parameters() if p.requires_grad])
                 opt.step()
                 if losses is not None:
                     losses.append(float(loss.detach()))

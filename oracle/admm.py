@@ -85,7 +85,7 @@ def twoStageAdmm_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, gamma=0.01, denois
                                model_demosaic=None, show_iqa=True, demosaic_method='malvar2004', lr_=1e-6,
                                inital_iter=1, interval_iter=5, logf=None, useGPU=True, update_=False,
                                update_per_iter=1, close_form_demosaic=False, large=False, update_times=-1,
-                               args=None, trace=None):
+                               args=None, trace=None, grad_hook=None, rng=None):
     """Stage 2.  'tv' -> 4-tuple; deep denoisers -> (xbgr3_np[H,W,3,B], x_bayer_np, psnr_, ssim_,
     psnr_all, model_denoise, model_demosaic)."""
     y_bayer = torch.from_numpy(np.ascontiguousarray(y_bayer))
@@ -143,7 +143,7 @@ def twoStageAdmm_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, gamma=0.01, denois
                     if do_update and (update_i < update_times or update_times < 0):             # :247
                         xbgr3, model_denoise = fastdvdnet_denoiser_full_tensor_v2(
                             x_rgb_w, nsig, yall, Phiall, model_denoise, useGPU, lr_, update_, update_per_iter,
-                            update_times=update_times, losses=losses)
+                            update_times=update_times, losses=losses, grad_hook=grad_hook, rng=rng)
                         update_i += 1
                     else:
                         xbgr3 = fastdvdnet_denoiser_full_tensor_v2(x_rgb_w, nsig, yall, Phiall, model_denoise,

@@ -66,3 +66,15 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert "workload" in d["config"]
+
+
+def test_count_updates_and_noise_skip():
+    """Host logic of the video sharding: the fine-tune noise stream is fast-forwarded exactly."""
+    from adaptivepnp_sci_b200 import stage2_script as s
+    assert s.count_updates([21, 2], 9, -1) == 2 and s.count_updates([18], 9, 1) == 1 and s.count_updates([6, 6, 4], 6, -1) == 2
+    np.random.seed(42)
+    a = [np.random.normal(0, 5 / 255, (2, 3, 8, 8)) for _ in range(3)]
+    np.random.seed(42)
+    s.skip_finetune_noise(2, (2, 3, 8, 8))
+    b = np.random.normal(0, 5 / 255, (2, 3, 8, 8))
+    assert np.array_equal(a[2], b)

@@ -60,3 +60,45 @@ def test_single_rank_is_identity():
     assert ctx.world == 1 and ctx.my_units(3) == [0, 1, 2]
     g = torch.ones(4)
     assert ctx.grad_sync(g) is g and ctx.gather_units({1: 2}) == {1: 2}
+
+
+def _uneven_worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    from adaptivepnp_sci_b200 import parallel
+    ctx = parallel.init(backend="gloo")
+    try:
+        ctx.check_even_split(3, "measurement groups")       # 3 groups over 2 ranks: rank 1 would skip an all-reduce
+        q.put((rank, "accepted"))
+    except ValueError as e:
+        q.put((rank, str(e)))
+    ctx.check_even_split(4, "measurement groups")           # 4 over 2 is fine
+    ctx.finalize()
+
+
+def test_shared_weights_need_an_even_split():
+    """--share-weights with groups that do not divide over the ranks must fail loudly, not hang in NCCL."""
+    world, port = 2, _free_port()
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    procs = [ctxm.Process(target=_uneven_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all("do not divide evenly" in msg for _, msg in out)
+
+
+def test_halo_longer_than_strip_is_refused():
+    """a strip shorter than the denoiser's halo must raise instead of silently clamping the halo."""
+    import pytest
+    from adaptivepnp_sci_b200 import parallel
+    ctx = parallel.Context(rank=1, world=8, local_rank=1, backend="gloo")
+    tile = parallel.TileContext(ctx, 512, 64)                # 64-row strips
+    assert tile.halo_sizes(28) == (28, 28)
+    with pytest.raises(ValueError, match="shorter than the 80-row halo"):
+        tile.halo_sizes(80)
+    one = parallel.TileContext(parallel.Context(0, 1, 0, "gloo"), 64, 64)
+    assert one.halo_sizes(80) == (0, 0)
