@@ -57,6 +57,8 @@ PROTOTYPES = {
     "sci_conv3x3_wgrad": [_p, _i, _p],
     "sci_conv_pack_weights": [_p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _i, _p],
     "sci_conv_pack_weights_s2t": [_p, _p, _i, _i, _i, _i, _p, _i, _p],
+    "sci_conv_pack_weights_half": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
+    "sci_fastdvd_pack_input_half": [_p, _f, _p, _i, _i, _i, _p],
     "sci_conv_unpack_wgrad": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "sci_bn_fold": [_p, _p, _p, _p, _f, _p, _p, _i, _i, _p],
     "sci_act_bwd": [_p, _p, _p, _l, _i, _i, _p, _p, _p],

@@ -16,6 +16,7 @@
 //     (tmem_full/tmem_empty) between MMA and epilogue, so the epilogue of tile i overlaps the MMAs of i+1.
 // Weight-gradient kernel (conv_wgrad_tc_kernel): see the comment above its definition.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "sci_common.cuh"
@@ -35,6 +36,7 @@ struct FwdParams {
     const float* scale; const float* shift; const float* residual; float* y;
     int N, H, W, Ho, Wo, Cin, Cout, stride, relu, ps, round_tf32, wsplit, emit_lo;
     int tiles_w, tiles_h, num_tiles, k_chunks, stages, acc_stride, tmem_cols;
+    int Cstore;       // fp16 storage: channels per pixel of the stored output tensor
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -104,18 +106,54 @@ __device__ __forceinline__ void tc_mma_tf32_elect(uint32_t d_tmem, uint64_t ades
         "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
+template <bool HALF>
+__device__ __forceinline__ void tc_mma_elect(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    if (HALF) {
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+    } else {
+        tc_mma_tf32_elect(d_tmem, adesc, bdesc, idesc, accum);
+    }
+}
 // K-major SWIZZLE_128B descriptor split into its 32-bit halves: the low word carries the start address (>> 4) and
 // LBO = 16 B, the high word (SBO = 1024 B, version 1, layout SWIZZLE_128B) never changes.  Advancing an operand by whole
 // 16-byte units inside the tile is then ONE 32-bit add on the low word.
 constexpr uint32_t DESC_HI_K128 = 0x40004040u;
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | 0x10000u; }
-__device__ __forceinline__ void mma_tf32_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-        "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accum), "r"(DESC_HI_K128) : "memory");
+template <bool HALF>
+__device__ __forceinline__ void mma_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accum) {
+    if (HALF) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+            ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accum), "r"(DESC_HI_K128) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}"
+            ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accum), "r"(DESC_HI_K128) : "memory");
+    }
+}
+// instruction descriptor: D = f32, A and B K-major in `fmt` (0 = f16, 2 = tf32), N columns, M = 128
+__device__ __forceinline__ uint32_t mma_idesc(bool half, int n) {
+    const uint32_t fmt = half ? 0u : 2u;
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));      // low half <- a
+    return r;
+}
+__device__ __forceinline__ float2 unpack_half2(uint32_t h) {
+    float2 f;
+    asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}" : "=f"(f.x), "=f"(f.y) : "r"(h));
+    return f;
 }
 __device__ __forceinline__ void tc_commit_elect(uint64_t* bar) {
     asm volatile(
@@ -156,6 +194,7 @@ __device__ __forceinline__ float rna_tf32(float v) {
 // ---------------------------------------------------------------------------------------------------
 // forward / data-gradient kernel
 // ---------------------------------------------------------------------------------------------------
+template <bool HALF>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FwdParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -205,9 +244,9 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     if (elect_one()) {
                         mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
                         const uint32_t a_dst = smem_base + (uint32_t)stage * stage_bytes;
-                        tma_load_4d(a_dst, &tmA, &full_bar[stage], kc * KCH, iw0 + s, ih0 + r, n);
-                        tma_load_3d(a_dst + A_BYTES, &tmB, &full_bar[stage], kc * KCH, 0, tap);
-                        if (p.wsplit) tma_load_3d(a_dst + A_BYTES + b_bytes, &tmB, &full_bar[stage], kc * KCH, 0, tap + 9);
+                        tma_load_4d(a_dst, &tmA, &full_bar[stage], kc * (HALF ? 64 : KCH), iw0 + s, ih0 + r, n);
+                        tma_load_3d(a_dst + A_BYTES, &tmB, &full_bar[stage], kc * (HALF ? 64 : KCH), 0, tap);
+                        if (p.wsplit) tma_load_3d(a_dst + A_BYTES + b_bytes, &tmB, &full_bar[stage], kc * (HALF ? 64 : KCH), 0, tap + 9);
                     }
                     __syncwarp();
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -217,7 +256,8 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     } else if (warp == 1) {
         // ===== MMA issuer (warp-uniform loop, election folded into the instruction predicate) =====
         // instruction descriptor: D=f32, A=B=tf32, K-major both, N = Cout, M = 128
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Cout >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t fmt = HALF ? 0u : 2u;
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.Cout >> 3) << 17) | ((128u >> 4) << 24);
         const uint64_t desc_hi = umma_desc(0, 16, 1024);
         int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -230,13 +270,13 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 const uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes, b_addr = a_addr + A_BYTES;
 #pragma unroll
                 for (int k = 0; k < KCH / 8; ++k) {
-                    tc_mma_tf32_elect(d_tmem, desc_hi | (uint64_t)(((a_addr + k * 32) & 0x3FFFFu) >> 4),
+                    tc_mma_elect<HALF>(d_tmem, desc_hi | (uint64_t)(((a_addr + k * 32) & 0x3FFFFu) >> 4),
                                       desc_hi | (uint64_t)(((b_addr + k * 32) & 0x3FFFFu) >> 4), idesc, (uint32_t)((ks | k) != 0));
                 }
                 if (p.wsplit) {
 #pragma unroll
                     for (int k = 0; k < KCH / 8; ++k)
-                        tc_mma_tf32_elect(d_tmem, desc_hi | (uint64_t)(((a_addr + k * 32) & 0x3FFFFu) >> 4),
+                        tc_mma_elect<HALF>(d_tmem, desc_hi | (uint64_t)(((a_addr + k * 32) & 0x3FFFFu) >> 4),
                                           desc_hi | (uint64_t)(((b_addr + b_bytes + k * 32) & 0x3FFFFu) >> 4), idesc, 1u);
                 }
                 tc_commit_elect(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
@@ -262,7 +302,24 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 float v[32];
                 const int nc = min(32, p.Cout - c0);
                 if (nc == 32) tmem_ld32(t_row + c0, v); else tmem_ld16(t_row + c0, v);
-                if (valid) {
+                if (HALF) {
+                    // fp16 storage: 32 columns = 64 bytes of this pixel's row (stride-2 layers: no residual / shuffle / split)
+                    if (valid) {
+                        __half* yp = reinterpret_cast<__half*>(p.y) + (((long)n * p.Ho + ho) * p.Wo + wo) * p.Cstore + c0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            uint32_t h[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                float t0 = v[j + 2 * e] * s_scale[c0 + j + 2 * e] + s_shift[c0 + j + 2 * e];
+                                float t1 = v[j + 2 * e + 1] * s_scale[c0 + j + 2 * e + 1] + s_shift[c0 + j + 2 * e + 1];
+                                if (p.relu) { t0 = fmaxf(t0, 0.f); t1 = fmaxf(t1, 0.f); }
+                                h[e] = pack_half2(t0, t1);
+                            }
+                            if (j < nc) *reinterpret_cast<uint4*>(yp + j) = make_uint4(h[0], h[1], h[2], h[3]);
+                        }
+                    }
+                } else if (valid) {
                     long o;
                     if (p.ps) {
                         const int qq = c0 / Cq, cc = c0 % Cq;
@@ -336,6 +393,10 @@ struct Fwd2Params {
     int stack;        // filter rows stacked along N (see the MMA issuer); needs resident weights, R >= 2, 3*Cout <= 256
     int R, tiles_h;   // rows per super-tile (R output rows share their R+2 input rows), super-tiles per image column strip
     int dbg;   // SCI_CONV_DBG timing experiments (results invalid): 1 = no MMAs, 2 = no activation loads, 4 = no stores
+    // fp16 storage (HALF kernels): a 128-byte operand row holds 64 channels.  One epilogue unit = `ucols` accumulator columns
+    // (64, or 32 when the layer / its PixelShuffle sub-pixel group has 32 real channels) -> ONE 64-channel fp16 pixel row of
+    // the stored tensor (the missing half is written as zeros); Cstore = channels per pixel of the stored output tensor
+    int ucols, Cstore;
 };
 
 __device__ __forceinline__ uint64_t umma_desc_off(uint32_t saddr, int mode) {
@@ -359,7 +420,10 @@ __device__ __forceinline__ uint64_t umma_desc_off(uint32_t saddr, int mode) {
 //     output, 3 = direct stores) instead of run-time flags per element; scale / shift come from shared memory as float4;
 //   * the planar mode fetches the in1 values of ALL its rows before it waits for the accumulator (the per-row prefetch
 //     left the HBM latency of those loads exposed: 46 % of the epilogue's samples in the 32->3 layer).
-template <int EPI_WG, int MODE>
+//   * HALF: fp16 storage and operands (kind::f16, fp32 accumulation): the same 11-bit significand as TF32 - the products
+//     are as exact - at half the bytes per channel and twice the tensor rate.  Used for inference chains; the training
+//     passes keep fp32 activations (the weight-gradient kernels read them).
+template <int EPI_WG, int MODE, bool HALF>
 __global__ void __launch_bounds__(128 + 128 * EPI_WG, 1)
 conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmY, const Fwd2Params p) {
@@ -413,7 +477,7 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         // horizontal tap form ONE K-major B matrix of 3*Cout rows
                         const uint32_t slot = p.stack ? (uint32_t)(((tap % 3) * p.k_chunks + kc) * 3 + tap / 3)
                                                       : (uint32_t)(tap * p.k_chunks + kc);
-                        tma_load_3d(smem_base + slot * b_bytes, &tmB, &w_bar, kc * KCH, p.col0, tap);
+                        tma_load_3d(smem_base + slot * b_bytes, &tmB, &w_bar, kc * (HALF ? 64 : KCH), p.col0, tap);
                     }
             }
             __syncwarp();
@@ -434,10 +498,10 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         const bool skip_a = (p.dbg & 2) != 0;
                         mbar_arrive_expect_tx(&full_bar[stage], (skip_a ? 0u : ROW_BYTES) + (p.resident ? 0u : 3u * b_bytes));
                         const uint32_t a_dst = ring_base + (uint32_t)stage * stage_bytes;
-                        if (!skip_a) tma_load_4d(a_dst, &tmA, &full_bar[stage], kc * KCH, wt * 128 - 1, y0 + j - 1, n);
+                        if (!skip_a) tma_load_4d(a_dst, &tmA, &full_bar[stage], kc * (HALF ? 64 : KCH), wt * 128 - 1, y0 + j - 1, n);
                         if (!p.resident) {       // streamed weights: R == 1, j is the filter row
                             for (int s = 0; s < 3; ++s)
-                                tma_load_3d(a_dst + A2_STAGE + (uint32_t)s * b_bytes, &tmB, &full_bar[stage], kc * KCH, p.col0, j * 3 + s);
+                                tma_load_3d(a_dst + A2_STAGE + (uint32_t)s * b_bytes, &tmB, &full_bar[stage], kc * (HALF ? 64 : KCH), p.col0, j * 3 + s);
                         }
                     }
                     __syncwarp();
@@ -453,7 +517,7 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // on the barriers (warp-uniform), ONE lane elected once issues a stage's MMAs in straight-line code; descriptors are
         // a per-stage 32-bit low word plus compile-time increments, the high word is a constant.
         const bool leader = elect_one();
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Cout >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t idesc = mma_idesc(HALF, p.Cout);
         if (p.resident) { mbar_wait(&w_bar, 0); tc_fence_after(); }
         int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
         const uint32_t b_tile_lo = b_bytes >> 4;                  // one [Cout][32 ch] weight tile, in descriptor units
@@ -480,7 +544,7 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                 for (int s = 0; s < 3; ++s) {
 #pragma unroll
                                     for (int k = 0; k < KCH / 8; ++k)
-                                        mma_tf32_lo(d_base, a_lo + s * 8 + k * 2, b_lo + s * b_step + k * 2, idesc, (s | k) ? 1u : first);
+                                        mma_lo<HALF>(d_base, a_lo + s * 8 + k * 2, b_lo + s * b_step + k * 2, idesc, (s | k) ? 1u : first);
                                 }
                             }
                             tc_commit(&empty_bar[stage]);
@@ -512,19 +576,19 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             if (p.dbg & 1) {
                             } else if (r_lo == 0 && kc == 0) {
                                 // this row opens the accumulator of output row t = j (r = 0): that slice must overwrite
-                                mma_tf32_lo(d_col, a_lo, b_lo, idesc, 0u);
-                                if (nr > 1) mma_tf32_lo(d_col + (uint32_t)p.acc_stride, a_lo, b_lo + b_tile_lo, idesc_m, 1u);
+                                mma_lo<HALF>(d_col, a_lo, b_lo, idesc, 0u);
+                                if (nr > 1) mma_lo<HALF>(d_col + (uint32_t)p.acc_stride, a_lo, b_lo + b_tile_lo, idesc_m, 1u);
 #pragma unroll
                                 for (int sk = 1; sk < 3 * (KCH / 8); ++sk) {
                                     const int s = sk / (KCH / 8), k = sk % (KCH / 8);
-                                    mma_tf32_lo(d_col, a_lo + s * 8 + k * 2, b_lo + s * b_step + k * 2, idesc_n, 1u);
+                                    mma_lo<HALF>(d_col, a_lo + s * 8 + k * 2, b_lo + s * b_step + k * 2, idesc_n, 1u);
                                 }
                             } else {
 #pragma unroll
                                 for (int s = 0; s < 3; ++s) {
 #pragma unroll
                                     for (int k = 0; k < KCH / 8; ++k)
-                                        mma_tf32_lo(d_col, a_lo + s * 8 + k * 2, b_lo + s * b_step + k * 2, idesc_n, 1u);
+                                        mma_lo<HALF>(d_col, a_lo + s * 8 + k * 2, b_lo + s * b_step + k * 2, idesc_n, 1u);
                                 }
                             }
                             tc_commit(&empty_bar[stage]);
@@ -553,7 +617,7 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                     for (int s = 0; s < 3; ++s) {
 #pragma unroll
                                         for (int k = 0; k < KCH / 8; ++k)
-                                            mma_tf32_lo(d_tmem, a_lo + s * 8 + k * 2, b_lo + s * b_step + k * 2, idesc, (s | k) ? 1u : first);
+                                            mma_lo<HALF>(d_tmem, a_lo + s * 8 + k * 2, b_lo + s * b_step + k * 2, idesc, (s | k) ? 1u : first);
                                     }
                                 }
                             }
@@ -600,7 +664,7 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // operands from global memory are requested while the MMAs of this tile are still running
             float4 rr[8];
             float pin[PIN_ROWS][3];
-            if (MODE == 1 || MODE == 3) {
+            if (!HALF && (MODE == 1 || MODE == 3)) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) rr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (p.residual && valid && g < units) {
@@ -624,6 +688,79 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
+            if (HALF && MODE != 2) {
+                // ---- fp16 output: unit = `ucols` accumulator columns -> one 64-channel (128-byte) pixel row
+                const int nun = (p.Cout + p.ucols - 1) / p.ucols;
+                const int hunits = rows * nun;
+                for (int u = g; u < hunits; u += EPI_WG) {
+                    const int t = u / nun, col0 = (u - t * nun) * p.ucols;
+                    const int ncv = min(p.ucols, p.Cout - col0);           // valid accumulator columns of this unit (32 or 64)
+                    const int ho = y0 + t;
+                    const int cg = p.col0 + col0;
+                    int qq = 0, cx = cg;
+                    if (p.ps) { qq = cg / Cq; cx = cg - qq * Cq; }
+                    uint4 rres[8];
+                    if (MODE == 1) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) rres[j] = make_uint4(0u, 0u, 0u, 0u);
+                        if (valid) {
+                            const long pix = p.ps ? (((long)n * 2 * p.H + 2 * ho + (qq >> 1)) * 2 * p.W + 2 * wo + (qq & 1))
+                                                  : (((long)n * p.H + ho) * p.W + wo);
+                            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.residual) + pix * p.Cstore + cx);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (j * 8 < ncv) rres[j] = __ldg(rp + j);
+                        }
+                    }
+                    const uint32_t t_row = tmem_base + (uint32_t)((acc * p.R + (p.stack ? p.R - 1 - t : t)) * p.acc_stride) + ((uint32_t)(q * 32) << 16);
+                    uint32_t hv[32];                                        // 64 fp16 values of this lane's pixel
+#pragma unroll
+                    for (int hb = 0; hb < 2; ++hb) {
+                        if (hb * 32 < ncv) {
+                            float v[32];
+                            tmem_ld32(t_row + col0 + hb * 32, v);
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 sc = *reinterpret_cast<const float4*>(&s_scale[col0 + hb * 32 + j]);
+                                const float4 sh = *reinterpret_cast<const float4*>(&s_shift[col0 + hb * 32 + j]);
+                                float a0 = fmaxf(fmaf(v[j], sc.x, sh.x), lower), a1 = fmaxf(fmaf(v[j + 1], sc.y, sh.y), lower);
+                                float a2 = fmaxf(fmaf(v[j + 2], sc.z, sh.z), lower), a3 = fmaxf(fmaf(v[j + 3], sc.w, sh.w), lower);
+                                if (MODE == 1) {
+                                    const uint4 r4 = rres[hb * 4 + (j >> 3)];
+                                    const float2 r0 = unpack_half2((j & 4) ? r4.z : r4.x), r1 = unpack_half2((j & 4) ? r4.w : r4.y);
+                                    a0 += r0.x; a1 += r0.y; a2 += r1.x; a3 += r1.y;
+                                }
+                                hv[hb * 16 + (j >> 1)] = pack_half2(a0, a1);
+                                hv[hb * 16 + (j >> 1) + 1] = pack_half2(a2, a3);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) hv[hb * 16 + j] = 0u;
+                        }
+                    }
+                    const uint32_t sbuf = sbuf0 + (p.out_bufs == 2 ? (st_cnt & 1) * 4096u : 0u);
+                    if (lane == 0) {
+                        if (p.out_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        else                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t a = sbuf + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(hv[4 * j]), "r"(hv[4 * j + 1]), "r"(hv[4 * j + 2]), "r"(hv[4 * j + 3]) : "memory");
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        int cw = wt * 128 + q * 32, chh = ho;
+                        if (p.ps) { cw = 2 * cw + (qq & 1); chh = 2 * ho + (qq >> 1); }
+                        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                                     ::"l"(&tmY), "r"(sbuf), "r"(cx), "r"(cw), "r"(chh), "r"(n) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    ++st_cnt;
+                }
+            } else {
             // one unit = 32 channels of one output row for this lane's pixel
             auto unit = [&](int t, int c0, float (&v)[32]) {
                 const uint32_t t_row = tmem_base + (uint32_t)((acc * p.R + (p.stack ? p.R - 1 - t : t)) * p.acc_stride) + ((uint32_t)(q * 32) << 16);
@@ -717,6 +854,7 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
                 }
             }
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -753,14 +891,15 @@ EncodeTiledFn get_encode_fn() {
 
 // NHWC activation tensor [N][H][W][C], box = {32 ch, TILE_W*stride, TILE_H*stride, 1} traversed with element stride `stride`
 int make_act_map(CUtensorMap* tm, const float* x, int N, int H, int W, int C, int stride, int box_w, int box_h,
-                 CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+                 CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, bool half = false) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return sci_fail(SCI_ELAUNCH, "cuTensorMapEncodeTiled entry point not available");
+    const cuuint64_t esz = half ? 2 : 4;
     const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-    const cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-    const cuuint32_t box[4] = {KCH, (cuuint32_t)(box_w * stride), (cuuint32_t)(box_h * stride), 1};
+    const cuuint64_t strides[3] = {(cuuint64_t)C * esz, (cuuint64_t)W * C * esz, (cuuint64_t)H * W * C * esz};
+    const cuuint32_t box[4] = {(cuuint32_t)(half ? 64 : KCH), (cuuint32_t)(box_w * stride), (cuuint32_t)(box_h * stride), 1};
     const cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
+    CUresult r = fn(tm, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         char msg[96];
@@ -771,14 +910,15 @@ int make_act_map(CUtensorMap* tm, const float* x, int N, int H, int W, int C, in
 }
 
 // packed weights [taps][Cout][Cin] (taps = 9, or 18 with the hi/remainder split), box = {32 ch, Cout, 1}
-int make_weight_map(CUtensorMap* tm, const float* w, int Cout, int Cin, int taps, int box_rows = 0) {
+int make_weight_map(CUtensorMap* tm, const float* w, int Cout, int Cin, int taps, int box_rows = 0, bool half = false) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return sci_fail(SCI_ELAUNCH, "cuTensorMapEncodeTiled entry point not available");
+    const cuuint64_t esz = half ? 2 : 4;
     const cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)taps};
-    const cuuint64_t strides[2] = {(cuuint64_t)Cin * 4, (cuuint64_t)Cout * Cin * 4};
-    const cuuint32_t box[3] = {KCH, (cuuint32_t)(box_rows ? box_rows : Cout), 1};
+    const cuuint64_t strides[2] = {(cuuint64_t)Cin * esz, (cuuint64_t)Cout * Cin * esz};
+    const cuuint32_t box[3] = {(cuuint32_t)(half ? 64 : KCH), (cuuint32_t)(box_rows ? box_rows : Cout), 1};
     const cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(w), dims, strides, box, estr,
+    CUresult r = fn(tm, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(w), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -792,12 +932,16 @@ int make_weight_map(CUtensorMap* tm, const float* w, int Cout, int Cin, int taps
 int next_pow2_cols(int c) { int v = 32; while (v < c) v <<= 1; return v; }
 
 int conv_fwd_tc_launch(const sci_conv_desc* d, void* stream) {
-    if (d->Cin % KCH != 0 || d->Cout % 16 != 0 || d->Cout > 256)
-        return sci_fail(SCI_EUNSUPPORTED, "conv tc: needs Cin % 32 == 0, Cout % 16 == 0, Cout <= 256");
+    const bool half = d->half_io != 0;
+    const int kch = half ? 64 : KCH, esz = half ? 2 : 4;
+    if (d->Cin % kch != 0 || d->Cout % 16 != 0 || d->Cout > 256)
+        return sci_fail(SCI_EUNSUPPORTED, "conv tc: needs Cin % 32 == 0 (fp16: % 64), Cout % 16 == 0, Cout <= 256");
     if (((uintptr_t)d->x | (uintptr_t)d->w | (uintptr_t)d->y | (uintptr_t)d->residual) & 15)
         return sci_fail(SCI_EINVAL, "conv tc: pointers must be 16-byte aligned");
     if (d->pixel_shuffle && (d->Cout % 128 != 0))
         return sci_fail(SCI_EUNSUPPORTED, "conv tc: pixel_shuffle needs Cout % 128 == 0");
+    if (half && (d->pixel_shuffle || d->residual || d->w_split || d->emit_lo || d->Cout % 32))
+        return sci_fail(SCI_EUNSUPPORTED, "conv tc fp16 (tile kernel): plain layers with Cout % 32 == 0 only");
     FwdParams p;
     p.scale = d->scale; p.shift = d->shift; p.residual = d->residual; p.y = d->y;
     p.N = d->N; p.H = d->H; p.W = d->W; p.stride = d->stride;
@@ -805,31 +949,35 @@ int conv_fwd_tc_launch(const sci_conv_desc* d, void* stream) {
     p.Cin = d->Cin; p.Cout = d->Cout; p.relu = d->relu; p.ps = d->pixel_shuffle; p.round_tf32 = d->round_tf32;
     p.wsplit = d->w_split ? 1 : 0;
     p.emit_lo = d->emit_lo ? 1 : 0;
+    p.Cstore = (half && d->Cout_store) ? d->Cout_store : d->Cout;
     if (p.emit_lo && (d->pixel_shuffle || d->residual || !d->round_tf32))
         return sci_fail(SCI_EUNSUPPORTED, "conv tc: emit_lo needs round_tf32 and no pixel_shuffle / residual");
     p.tiles_w = (p.Wo + TILE_W - 1) / TILE_W; p.tiles_h = (p.Ho + TILE_H - 1) / TILE_H;
     p.num_tiles = p.tiles_w * p.tiles_h * p.N;
-    p.k_chunks = p.Cin / KCH;
-    const int stage_bytes = A_BYTES + p.Cout * KCH * 4 * (1 + p.wsplit);
+    p.k_chunks = p.Cin / kch;
+    const int stage_bytes = A_BYTES + p.Cout * 128 * (1 + p.wsplit);
     p.stages = min(MAX_STAGES, (216 * 1024) / stage_bytes);
     p.acc_stride = ((p.Cout + 31) / 32) * 32;
     p.tmem_cols = next_pow2_cols(2 * p.acc_stride);
     CUtensorMap tmA, tmB;
-    int rc = make_act_map(&tmA, d->x, d->N, d->H, d->W, d->Cin, d->stride, TILE_W, TILE_H);
+    const int cin_store = (half && d->Cin_store) ? d->Cin_store : d->Cin;
+    int rc = make_act_map(&tmA, d->x, d->N, d->H, d->W, cin_store, d->stride, TILE_W, TILE_H, CU_TENSOR_MAP_SWIZZLE_128B, half);
     if (rc) return rc;
-    rc = make_weight_map(&tmB, d->w, d->Cout, d->Cin, 9 * (1 + p.wsplit));
+    rc = make_weight_map(&tmB, d->w, d->Cout, d->Cin, 9 * (1 + p.wsplit), 0, half);
     if (rc) return rc;
     const size_t smem = (size_t)p.stages * stage_bytes + 1024;
-    static bool attr_set[64] = {};
+    static bool attr_set[64][2] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(conv_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (dev < 0 || dev >= 64 || !attr_set[dev][half ? 1 : 0]) {
+        cudaError_t e = half ? cudaFuncSetAttribute(conv_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)
+                             : cudaFuncSetAttribute(conv_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         if (e != cudaSuccess) return sci_fail(SCI_ELAUNCH, "conv tc: smem attribute", e);
-        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+        if (dev >= 0 && dev < 64) attr_set[dev][half ? 1 : 0] = true;
     }
     const int grid = min(p.num_tiles, SCI_NUM_SMS);
-    conv_fwd_tc_kernel<<<grid, TC_THREADS, smem, sci_stream(stream)>>>(tmA, tmB, p);
+    if (half) conv_fwd_tc_kernel<true><<<grid, TC_THREADS, smem, sci_stream(stream)>>>(tmA, tmB, p);
+    else      conv_fwd_tc_kernel<false><<<grid, TC_THREADS, smem, sci_stream(stream)>>>(tmA, tmB, p);
     SCI_CHECK_LAUNCH("conv tc fwd");
     return SCI_OK;
 }
@@ -843,15 +991,23 @@ int env_int(const char* name, int dflt) {
 
 bool fwd2_eligible(const sci_conv_desc* d) {
     if (d->planar_out) return true;                      // fused planar output exists in the v2 kernel only
+    if (d->half_io) return d->stride == 1;
     return d->stride == 1 && d->Cout % 32 == 0 && (d->Cout <= 128 || d->Cout == 256) && !d->w_split && !d->emit_lo &&
            env_int("SCI_CONV_V2", 1) != 0;
 }
 
 // columns [col0, col0 + ncols) of the layer
 int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream, int col0, int ncols) {
-    if (d->Cin % KCH != 0) return sci_fail(SCI_EUNSUPPORTED, "conv tc v2: Cin % 32");
+    const bool half = d->half_io != 0;
+    const int kch = half ? 64 : KCH;                 // channels per 128-byte operand row
+    const int esz = half ? 2 : 4;
+    if (d->Cin % kch != 0) return sci_fail(SCI_EUNSUPPORTED, "conv tc v2: Cin % 32 (fp32) / % 64 (fp16)");
     if (((uintptr_t)d->x | (uintptr_t)d->w | (uintptr_t)d->y | (uintptr_t)d->residual) & 15)
         return sci_fail(SCI_EINVAL, "conv tc: pointers must be 16-byte aligned");
+    const int cin_store = (half && d->Cin_store) ? d->Cin_store : d->Cin;       // channels per pixel of the stored input
+    const int cout_store = (half && d->Cout_store) ? d->Cout_store : (d->pixel_shuffle ? d->Cout / 4 : d->Cout);
+    if (half && (cin_store % 8 || cout_store % 8 || cin_store > d->Cin))
+        return sci_fail(SCI_EINVAL, "conv tc v2 fp16: stored channel counts must be multiples of 8 (16-byte TMA strides)");
     Fwd2Params p;
     p.scale = d->scale; p.shift = d->shift; p.residual = d->residual; p.y = d->y;
     p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = ncols; p.col0 = col0; p.Ctot = d->Cout;
@@ -860,9 +1016,17 @@ int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream, int col0, int ncol
     if (p.planar_out && (!p.planar_in1 || p.ps || p.Cout != 32 || d->residual))
         return sci_fail(SCI_EINVAL, "conv tc v2: planar output needs planar_in1, Cout == 32, no pixel_shuffle / residual");
     p.tiles_w = (p.W + 127) / 128;
-    p.k_chunks = p.Cin / KCH;
-    const int b_bytes = p.Cout * KCH * 4;
-    p.tma_store = (env_int("SCI_CONV_TMA_STORE", 1) && !p.planar_out) ? 1 : 0;
+    p.k_chunks = p.Cin / kch;
+    const int b_bytes = p.Cout * 128;
+    p.tma_store = ((half || env_int("SCI_CONV_TMA_STORE", 1)) && !p.planar_out) ? 1 : 0;
+    p.Cstore = cout_store;
+    p.ucols = 32;
+    if (half) {
+        const int cq = p.ps ? d->Cout / 4 : ncols;             // columns that belong to one stored pixel row
+        if (cq % 32 != 0) return sci_fail(SCI_EUNSUPPORTED, "conv tc v2 fp16: column groups of 32");
+        p.ucols = (cq % 64 == 0 || cq > 64) ? 64 : 32;
+        if (p.ps && cq != 32 && cq % 64 != 0) return sci_fail(SCI_EUNSUPPORTED, "conv tc v2 fp16: PixelShuffle groups of 32 or k*64 columns");
+    }
     const int mode = p.planar_out ? 2 : (!p.tma_store ? 3 : (d->residual ? 1 : 0));
     const int w_bytes = 9 * p.k_chunks * b_bytes;
     // shared-memory plan: [resident weights] [pipeline stages] [store staging: 4 * epi_wg warps x out_bufs x 4 KB].
@@ -873,7 +1037,7 @@ int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream, int col0, int ncol
     // measured per layer (tools/pass_layers.py): the second warpgroup pays where the epilogue work per MMA is high (K <= 32:
     // 12->90 0.270 -> 0.255 ms, or a skip-add: 64->128+PS 0.251 -> 0.178 ms) and costs where the MMA-issuing warp is the
     // critical path and now shares its scheduler with two epilogue warps (128->128: 0.067 -> 0.078 ms)
-    const int epi_first = epi_env ? (epi_env == 1 ? 1 : 2) : ((d->Cin <= 32 || d->residual) ? 2 : 1);
+    const int epi_first = epi_env ? (epi_env == 1 ? 1 : 2) : ((p.k_chunks <= 1 || d->residual) ? 2 : 1);
     for (epi_wg = epi_first; epi_wg >= 1; --epi_wg) {
         for (p.out_bufs = (epi_wg == 2 ? 1 : 2); p.out_bufs >= 1; --p.out_bufs) {
             out_stage = p.tma_store ? 4 * epi_wg * p.out_bufs * 4096 : 0;
@@ -913,16 +1077,18 @@ int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream, int col0, int ncol
     {
         EncodeTiledFn fn = get_encode_fn();
         if (!fn) return sci_fail(SCI_ELAUNCH, "cuTensorMapEncodeTiled entry point not available");
-        const cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
-        const cuuint64_t strides[3] = {(cuuint64_t)d->Cin * 4, (cuuint64_t)d->W * d->Cin * 4, (cuuint64_t)d->H * d->W * d->Cin * 4};
-        const cuuint32_t box[4] = {KCH, ROW_PX, 1, 1};
+        // fp16: the channel extent is the STORED one; a box that sticks out of it (e.g. channels 64..127 of a 96-channel tensor)
+        // is zero-filled by TMA, matching the zero rows of the packed weights
+        const cuuint64_t dims[4] = {(cuuint64_t)cin_store, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+        const cuuint64_t strides[3] = {(cuuint64_t)cin_store * esz, (cuuint64_t)d->W * cin_store * esz, (cuuint64_t)d->H * d->W * cin_store * esz};
+        const cuuint32_t box[4] = {(cuuint32_t)kch, ROW_PX, 1, 1};
         const cuuint32_t estr[4] = {1, 1, 1, 1};
-        CUresult r = fn(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(d->x), dims, strides, box, estr,
+        CUresult r = fn(&tmA, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(d->x), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return sci_fail(SCI_ELAUNCH, "cuTensorMapEncodeTiled(row box) failed");
     }
-    int rc = make_weight_map(&tmB, d->w, d->Cout, d->Cin, 9, ncols);
+    int rc = make_weight_map(&tmB, d->w, d->Cout, d->Cin, 9, ncols, half);
     if (rc) return rc;
     CUtensorMap tmY = tmA;
     if (p.tma_store) {
@@ -930,29 +1096,32 @@ int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream, int col0, int ncol
         // plain layers: [N][H][W][Cout], box {32 ch, 32 px}.  PixelShuffle layers: the map covers the up-sampled tensor
         // [N][2H][2W][Cout/4]; the 32 pixels of a warp land on every second column (element stride 2).
         const int ps = d->pixel_shuffle ? 1 : 0;
-        const cuuint64_t oc = (cuuint64_t)(ps ? d->Cout / 4 : d->Cout), ow = (cuuint64_t)(d->W << ps), oh = (cuuint64_t)(d->H << ps);
+        const cuuint64_t oc = (cuuint64_t)cout_store, ow = (cuuint64_t)(d->W << ps), oh = (cuuint64_t)(d->H << ps);
         const cuuint64_t dims[4] = {oc, ow, oh, (cuuint64_t)d->N};
-        const cuuint64_t strides[3] = {oc * 4, ow * oc * 4, oh * ow * oc * 4};
-        const cuuint32_t box[4] = {KCH, (cuuint32_t)(32 << ps), 1, 1};
+        const cuuint64_t strides[3] = {oc * esz, ow * oc * esz, oh * ow * oc * esz};
+        const cuuint32_t box[4] = {(cuuint32_t)kch, (cuuint32_t)(32 << ps), 1, 1};
         const cuuint32_t estr[4] = {1, (cuuint32_t)(1 << ps), 1, 1};
-        CUresult r = fn(&tmY, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d->y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CUresult r = fn(&tmY, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d->y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return sci_fail(SCI_ELAUNCH, "cuTensorMapEncodeTiled(output) failed");
     }
     const size_t smem = (size_t)(p.resident ? w_bytes : 0) + (size_t)p.stages * stage_bytes + out_stage + 1024;
     if (smem > 220 * 1024) return sci_fail(SCI_EUNSUPPORTED, "conv tc v2: shared memory budget exceeded");
     typedef void (*Fwd2Kernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const Fwd2Params);
-    static const Fwd2Kernel kernels[2][4] = {
-        {conv_fwd2_tc_kernel<1, 0>, conv_fwd2_tc_kernel<1, 1>, conv_fwd2_tc_kernel<1, 2>, conv_fwd2_tc_kernel<1, 3>},
-        {conv_fwd2_tc_kernel<2, 0>, conv_fwd2_tc_kernel<2, 1>, conv_fwd2_tc_kernel<2, 2>, conv_fwd2_tc_kernel<2, 3>}};
-    const Fwd2Kernel kern = kernels[epi_wg - 1][mode];
-    static bool attr_set[64][2][4] = {};
+    static const Fwd2Kernel kernels[2][2][4] = {
+        {{conv_fwd2_tc_kernel<1, 0, false>, conv_fwd2_tc_kernel<1, 1, false>, conv_fwd2_tc_kernel<1, 2, false>, conv_fwd2_tc_kernel<1, 3, false>},
+         {conv_fwd2_tc_kernel<2, 0, false>, conv_fwd2_tc_kernel<2, 1, false>, conv_fwd2_tc_kernel<2, 2, false>, conv_fwd2_tc_kernel<2, 3, false>}},
+        {{conv_fwd2_tc_kernel<1, 0, true>, conv_fwd2_tc_kernel<1, 1, true>, conv_fwd2_tc_kernel<1, 2, true>, nullptr},
+         {conv_fwd2_tc_kernel<2, 0, true>, conv_fwd2_tc_kernel<2, 1, true>, conv_fwd2_tc_kernel<2, 2, true>, nullptr}}};
+    const Fwd2Kernel kern = kernels[half ? 1 : 0][epi_wg - 1][mode];
+    if (!kern) return sci_fail(SCI_EUNSUPPORTED, "conv tc v2 fp16: direct-store epilogue not built");
+    static bool attr_set[64][2][2][4] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !attr_set[dev][epi_wg - 1][mode]) {
+    if (dev < 0 || dev >= 64 || !attr_set[dev][half ? 1 : 0][epi_wg - 1][mode]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         if (e != cudaSuccess) return sci_fail(SCI_ELAUNCH, "conv tc v2: smem attribute", e);
-        if (dev >= 0 && dev < 64) attr_set[dev][epi_wg - 1][mode] = true;
+        if (dev >= 0 && dev < 64) attr_set[dev][half ? 1 : 0][epi_wg - 1][mode] = true;
     }
     const int grid = min(p.num_tiles, SCI_NUM_SMS);
     const int threads = 128 + 128 * epi_wg;
@@ -1533,6 +1702,7 @@ int check_conv_desc(const sci_conv_desc* d) {
     SCI_REQUIRE(!d->planar_out || (d->stride == 1 && !d->w_split && !d->emit_lo), "conv: planar output options");
     SCI_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "conv: shape");
     SCI_REQUIRE(d->Cin % 8 == 0 && d->Cout % 4 == 0, "conv: Cin % 8, Cout % 4");
+    SCI_REQUIRE(!d->half_io || (d->Cin % 64 == 0 && d->Cout % 32 == 0 && !d->w_split && !d->emit_lo), "conv fp16: Cin % 64, Cout % 32, no split options");
     SCI_REQUIRE(d->stride == 1 || d->stride == 2, "conv: stride");
     SCI_REQUIRE(!d->pixel_shuffle || d->stride == 1, "conv: pixel_shuffle with stride 2");
     return SCI_OK;
@@ -1546,7 +1716,7 @@ extern "C" int sci_conv3x3_fwd(const sci_conv_desc* d, int impl, void* stream) {
     int rc = check_conv_desc(d);
     if (rc) return rc;
     if (impl == SCI_CONV_REF) {
-        SCI_REQUIRE(!d->w_split && !d->emit_lo && !d->planar_out, "conv ref: w_split / emit_lo / planar_out are tensor-core options");
+        SCI_REQUIRE(!d->w_split && !d->emit_lo && !d->planar_out && !d->half_io, "conv ref: w_split / emit_lo / planar_out / half_io are tensor-core options");
         return sci_conv3x3_ref_launch(d, stream);
     }
     if (impl == SCI_CONV_TC) {

@@ -2,6 +2,8 @@
 // network-boundary packers (FFDNet pixel-(un)shuffle + sigma map, FastDVDnet circular frame
 // triples + residual output), the fused measurement-consistency loss, and Adam.
 // All HBM-bound elementwise / index-remap work; compiled with --fmad=false.
+#include <cuda_fp16.h>
+
 #include "sci_common.cuh"
 
 namespace {
@@ -380,6 +382,57 @@ inline int grid1d(long n, int block = 256) { return (int)((n + block - 1) / bloc
 
 }  // namespace
 
+// ---- fp16 forms (inference chains on the kind::f16 tensor-core kernels) ---------------------------------------------
+// packed[tap][col][k] as IEEE binary16 (round to nearest), forward form only.  Same column / dup rules as above.
+__global__ void pack_weights_half_kernel(const float* __restrict__ w, __half* __restrict__ packed, int Co, int Ci, int groups,
+                                         int Co_pad, int Ci_pad, int ps, int ci_dup) {
+    const long total = (long)9 * Co_pad * Ci_pad;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int ci = (int)(idx % Ci_pad);
+    const int col = (int)((idx / Ci_pad) % Co_pad), tap = (int)(idx / ((long)Ci_pad * Co_pad));
+    float v = 0.f;
+    if (ci_dup > 0 && ci >= ci_dup && ci < ci_dup + Ci) ci -= ci_dup;
+    const int q = Co_pad >> 2;
+    const int co = ps ? (col % q) * 4 + col / q : col;
+    if ((ps ? (col % q) < (Co >> 2) : col < Co) && ci < Ci) {
+        const int cig = Ci / groups, cog = Co / groups, g = co / cog;
+        if (ci / cig == g) v = w[((long)co * cig + (ci - g * cig)) * 9 + tap];
+    }
+    packed[idx] = __float2half_rn(v);
+}
+
+// FastDVDnet input block as fp16 NHWC rows of 64 channels (128 bytes): channel k = fp16(v), channel k + 16 = fp16(v - fp16(v))
+// (the first layer's weights are duplicated there, ci_dup = 16), everything else zero.  One thread per pixel, eight
+// 16-byte stores = one full 128-byte line.
+__global__ void __launch_bounds__(256) fastdvd_pack_half_kernel(const float* __restrict__ frames, float sigma,
+                                                                __half* __restrict__ out, int B, int H, int W) {
+    const long plane = (long)H * W;
+    const int f = blockIdx.y;
+    const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= plane) return;
+    __half hi[12], lo[12];
+#pragma unroll
+    for (int slot = 0; slot < 3; ++slot) {
+        const int src = (f + slot - 1 + B) % B;                              // circular window (fastdvdnet.py:115)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float v = (c == 3) ? sigma : __ldg(frames + ((long)src * 3 + c) * plane + p);
+            const __half h = __float2half_rn(v);
+            hi[slot * 4 + c] = h;
+            lo[slot * 4 + c] = __float2half_rn(v - __half2float(h));
+        }
+    }
+    auto pk = [](__half a, __half b) -> uint32_t { return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16); };
+    uint4* dst = reinterpret_cast<uint4*>(out + ((long)f * plane + p) * 64);
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    dst[0] = make_uint4(pk(hi[0], hi[1]), pk(hi[2], hi[3]), pk(hi[4], hi[5]), pk(hi[6], hi[7]));
+    dst[1] = make_uint4(pk(hi[8], hi[9]), pk(hi[10], hi[11]), 0u, 0u);
+    dst[2] = make_uint4(pk(lo[0], lo[1]), pk(lo[2], lo[3]), pk(lo[4], lo[5]), pk(lo[6], lo[7]));
+    dst[3] = make_uint4(pk(lo[8], lo[9]), pk(lo[10], lo[11]), 0u, 0u);
+    dst[4] = z; dst[5] = z; dst[6] = z; dst[7] = z;
+}
+
 extern "C" int sci_conv_pack_weights(const float* w, float* packed, int Co, int Ci, int groups, int Co_pad, int Ci_pad,
                                      int ps, const float* oscale, int transpose_flip, int round_tf32, int ci_dup,
                                      void* stream) {
@@ -392,6 +445,26 @@ extern "C" int sci_conv_pack_weights(const float* w, float* packed, int Co, int 
     pack_weights_kernel<<<grid1d(total), 256, 0, sci_stream(stream)>>>(w, packed, Co, Ci, groups, Co_pad, Ci_pad, ps, oscale,
                                                                        transpose_flip, round_tf32, ci_dup);
     SCI_CHECK_LAUNCH("pack_weights");
+    return SCI_OK;
+}
+
+extern "C" int sci_conv_pack_weights_half(const float* w, void* packed, int Co, int Ci, int groups, int Co_pad, int Ci_pad,
+                                          int ps, int ci_dup, void* stream) {
+    SCI_REQUIRE(w && packed && Co > 0 && Ci > 0 && groups > 0 && Co % groups == 0 && Ci % groups == 0, "pack_weights_half");
+    SCI_REQUIRE(Co_pad >= Co && Ci_pad >= Ci && Ci_pad % 64 == 0 && (!ps || (Co % 4 == 0 && Co_pad % 4 == 0)), "pack_weights_half: padding");
+    SCI_REQUIRE(ci_dup == 0 || (ci_dup >= Ci && ci_dup + Ci <= Ci_pad), "pack_weights_half: ci_dup block does not fit");
+    const long total = (long)9 * Co_pad * Ci_pad;
+    pack_weights_half_kernel<<<grid1d(total), 256, 0, sci_stream(stream)>>>(w, reinterpret_cast<__half*>(packed), Co, Ci, groups,
+                                                                            Co_pad, Ci_pad, ps, ci_dup);
+    SCI_CHECK_LAUNCH("pack_weights_half");
+    return SCI_OK;
+}
+
+extern "C" int sci_fastdvd_pack_input_half(const float* frames, float sigma, void* out, int B, int H, int W, void* stream) {
+    SCI_REQUIRE(frames && out && B > 0 && H > 0 && W > 0 && B <= 65535, "fastdvd_pack_input_half");
+    fastdvd_pack_half_kernel<<<dim3(grid1d((long)H * W, 256), B), 256, 0, sci_stream(stream)>>>(frames, sigma,
+                                                                                               reinterpret_cast<__half*>(out), B, H, W);
+    SCI_CHECK_LAUNCH("fastdvd_pack_input_half");
     return SCI_OK;
 }
 

@@ -34,7 +34,8 @@ class ConvDesc(ctypes.Structure):
                 ("N", ctypes.c_int), ("H", ctypes.c_int), ("W", ctypes.c_int), ("Cin", ctypes.c_int),
                 ("Cout", ctypes.c_int), ("stride", ctypes.c_int), ("relu", ctypes.c_int),
                 ("pixel_shuffle", ctypes.c_int), ("round_tf32", ctypes.c_int), ("w_split", ctypes.c_int), ("emit_lo", ctypes.c_int),
-                ("planar_in1", _f32p), ("planar_out", _f32p), ("pdl", ctypes.c_int)]
+                ("planar_in1", _f32p), ("planar_out", _f32p), ("pdl", ctypes.c_int),
+                ("half_io", ctypes.c_int), ("Cin_store", ctypes.c_int), ("Cout_store", ctypes.c_int)]
 
 
 class WgradDesc(ctypes.Structure):
@@ -169,17 +170,39 @@ class ConvLayer:
              self.Co_pad, self.Ci_pad, int(self.ps), ptr(self.scale), 1, int(tf32), self.ci_dup, stream())
 
 
+class HalfLayer:
+    """fp16 forward form of a ConvLayer (inference chains on the kind::f16 kernels, ``sci_conv_desc.half_io``).
+
+    Shares the fp32 layer's epilogue vectors (folded BatchNorm scale / shift: same GEMM column layout); its own state is the
+    packed fp16 weight tensor ``[9][N][K]`` with ``N = Co_pad`` GEMM columns and ``K`` = stored input channels rounded up to
+    64 (one 128-byte operand row).  ``cin_store`` / ``cout_store`` are the channels per pixel of the fp16 NHWC tensors it
+    reads / writes (96 for the 90-channel tensor, otherwise 64 or 128; tensors with 32 real channels carry 32 zeros)."""
+
+    def __init__(self, base, cin_store, cout_store, ci_dup=0):
+        self.base = base
+        self.cin_store, self.cout_store, self.ci_dup = cin_store, cout_store, ci_dup
+        self.K = _pad(cin_store, 64)
+        self.N = base.Co_pad
+        self.stride, self.relu, self.ps = base.stride, base.relu, base.ps
+        self.wpk = torch.empty(9 * self.N * self.K, dtype=torch.float16, device=base.conv.weight.device)
+
+    def refresh_fwd(self, tf32):
+        c = self.base.conv
+        call("sci_conv_pack_weights_half", ptr(c.weight.data), ptr(self.wpk), self.base.Co, self.base.Ci, self.base.groups,
+             self.N, self.K, int(self.ps), self.ci_dup, stream())
+
+
 class _Workspace:
     """Named, shape-keyed device buffers that live as long as the engine (no allocation in steady state)."""
 
     def __init__(self):
         self.bufs = {}
 
-    def get(self, name, shape, device, zero=False):
-        key = (name, tuple(shape))
+    def get(self, name, shape, device, zero=False, dtype=torch.float32):
+        key = (name, tuple(shape), dtype)
         t = self.bufs.get(key)
         if t is None:
-            t = torch.empty(shape, dtype=torch.float32, device=device)
+            t = torch.empty(shape, dtype=dtype, device=device)
             self.bufs[key] = t
             if zero:
                 t.zero_()
@@ -249,6 +272,23 @@ class _EngineBase:
             Ho, Wo = (H - 1) // L.stride + 1, (W - 1) // L.stride + 1
             self.profile.append((ev0, ev1, 2.0 * N * Ho * Wo * 9 * (L.Ci // L.groups) * L.Co,
                                  "fwd %dx%d %d->%d s%d" % (H, W, L.Ci, L.Co, L.stride)))
+        self.n_launch += 1
+
+    def conv_h(self, Lh, x, N, H, W, y, residual=None, planar=None):
+        """fp16 inference conv (tensor-core path only): x / y / residual are torch.float16 NHWC tensors."""
+        b = Lh.base
+        d = ConvDesc(_dp(x), _dp(Lh.wpk), _dp(b.scale), _dp(b.shift), _dp(residual), _dp(y), N, H, W, Lh.K, Lh.N,
+                     Lh.stride, int(Lh.relu), int(Lh.ps), 0, 0, 0, _dp(planar[0]) if planar else None,
+                     _dp(planar[1]) if planar else None, int(self.pdl_chain), 1, Lh.cin_store, Lh.cout_store)
+        if self.profile is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+        call("sci_conv3x3_fwd", ctypes.byref(d), IMPL_TC, stream())
+        if self.profile is not None:
+            ev1.record()
+            Ho, Wo = (H - 1) // Lh.stride + 1, (W - 1) // Lh.stride + 1
+            self.profile.append((ev0, ev1, 2.0 * N * Ho * Wo * 9 * (b.Ci // b.groups) * b.Co,
+                                 "fwd %dx%d %d->%d s%d" % (H, W, b.Ci, b.Co, Lh.stride)))
         self.n_launch += 1
 
     def dgrad_s2(self, L, dz, N, Ho, Wo, dx, residual=None):
@@ -408,10 +448,53 @@ class FastDVDnetEngine(_EngineBase):
     """packages/fastdvdnet/models.py:200-253 + the circular sequence driver fastdvdnet.py:82-146, with every
     temp1 triple evaluated once (B distinct triples instead of 3B; identical values)."""
 
+    # stored channels per pixel of each layer's fp16 input / output tensor (see HalfLayer): the 90-channel tensor keeps 96,
+    # 32-channel tensors are stored as 64 (32 zeros) so that every pixel row is one 128-byte operand row
+    _H_IN = [64, 96, 64, 64, 64, 64, 128, 128, 128, 128, 128, 64, 64, 64, 64, 64]
+    _H_OUT = [96, 64, 64, 64, 64, 128, 128, 128, 128, 128, 64, 64, 64, 64, 64, 64]
+
     def __init__(self, module):
         self.t1 = _DenBlockLayers(module.temp1)
         self.t2 = _DenBlockLayers(module.temp2)
         super().__init__(module, self.t1.L + self.t2.L)
+        # inference chains in fp16 (kind::f16 MMAs, fp32 accumulation: TF32's 11-bit significand, half the bytes, twice the
+        # tensor rate); SCI_CONV_HALF=0 keeps them on the TF32 kernels
+        self.half = self.impl == IMPL_TC and os.environ.get("SCI_CONV_HALF", "1") != "0"
+        self.layers_inf = None
+        if self.half:
+            self.t1h = [HalfLayer(L, ci, co, ci_dup=16 if i == 0 else 0)
+                        for i, (L, ci, co) in enumerate(zip(self.t1.L, self._H_IN, self._H_OUT))]
+            self.t2h = [HalfLayer(L, ci, co, ci_dup=16 if i == 0 else 0)
+                        for i, (L, ci, co) in enumerate(zip(self.t2.L, self._H_IN, self._H_OUT))]
+            self.layers_inf = self.t1h + self.t2h
+
+    def _block_forward_h(self, Lh, frames, sigma, out):
+        """One DenBlock on the fp16 kernels (inference): planar fp32 frames in, planar fp32 ``frames - net`` out."""
+        B, _, H, W = frames.shape
+        dev = frames.device
+        f16 = torch.float16
+        g = lambda n, shape: self.ws.get("h_" + n, shape, dev, dtype=f16)
+        h2, w2, h4, w4 = H // 2, W // 2, H // 4, W // 4
+        a_in = g("in", (B, H, W, 64))
+        call("sci_fastdvd_pack_input_half", ptr(frames), float(sigma), ptr(a_in), B, H, W, stream())
+        a0 = g("a0", (B, H, W, 96));        self.conv_h(Lh[0], a_in, B, H, W, a0)
+        x0 = g("x0", (B, H, W, 64));        self.conv_h(Lh[1], a0, B, H, W, x0)
+        d0a = g("d0a", (B, h2, w2, 64));    self.conv_h(Lh[2], x0, B, H, W, d0a)
+        d0b = g("d0b", (B, h2, w2, 64));    self.conv_h(Lh[3], d0a, B, h2, w2, d0b)
+        x1 = g("x1", (B, h2, w2, 64));      self.conv_h(Lh[4], d0b, B, h2, w2, x1)
+        d1a = g("d1a", (B, h4, w4, 128));   self.conv_h(Lh[5], x1, B, h2, w2, d1a)
+        d1b = g("d1b", (B, h4, w4, 128));   self.conv_h(Lh[6], d1a, B, h4, w4, d1b)
+        x2 = g("x2", (B, h4, w4, 128));     self.conv_h(Lh[7], d1b, B, h4, w4, x2)
+        u2a = g("u2a", (B, h4, w4, 128));   self.conv_h(Lh[8], x2, B, h4, w4, u2a)
+        u2b = g("u2b", (B, h4, w4, 128));   self.conv_h(Lh[9], u2a, B, h4, w4, u2b)
+        s1 = g("s1", (B, h2, w2, 64));      self.conv_h(Lh[10], u2b, B, h4, w4, s1, residual=x1)
+        u1a = g("u1a", (B, h2, w2, 64));    self.conv_h(Lh[11], s1, B, h2, w2, u1a)
+        u1b = g("u1b", (B, h2, w2, 64));    self.conv_h(Lh[12], u1a, B, h2, w2, u1b)
+        s0 = a_in                           # the packed input is dead once a0 exists; x0 once s0 exists
+        self.conv_h(Lh[13], u1b, B, h2, w2, s0, residual=x0)
+        o0 = x0
+        self.conv_h(Lh[14], s0, B, H, W, o0)
+        self.conv_h(Lh[15], o0, B, H, W, None, planar=(frames, out))
 
     # ---- one DenBlock ---------------------------------------------------------------------------------
     def _block_forward(self, tag, blk, frames, sigma, out, train):
@@ -468,8 +551,13 @@ class FastDVDnetEngine(_EngineBase):
         # prologue with the previous layer's tail (programmatic dependent launch); not while profiling per layer
         self.pdl_chain = (not train) and self.profile is None and self.impl == IMPL_TC
         try:
-            s1 = self._block_forward("t1", self.t1, frames, sigma, t1_out, train)
-            s2 = self._block_forward("t2", self.t2, t1_out, sigma, out, train)
+            if self.half and not train:
+                self._block_forward_h(self.t1h, frames, sigma, t1_out)
+                self._block_forward_h(self.t2h, t1_out, sigma, out)
+                s1 = s2 = None
+            else:
+                s1 = self._block_forward("t1", self.t1, frames, sigma, t1_out, train)
+                s2 = self._block_forward("t2", self.t2, t1_out, sigma, out, train)
         finally:
             self.pdl_chain = False
         if train:

@@ -203,6 +203,16 @@ typedef struct sci_conv_desc {
                                of the stream is still draining; it sets up barriers / TMEM / resident weights meanwhile and
                                waits for that kernel's completion before touching x / residual / planar_in1.  Only valid when
                                the previous kernel does not write w, scale or shift (engine: inference chains) */
+    int half_io;            /* TC only. 1: x, w, residual and y hold IEEE binary16 values (the pointers are typed float* for the
+                               ABI only); kind::f16 MMAs with fp32 accumulation - the same 11-bit significand as TF32 at half
+                               the bytes and twice the tensor rate.  scale / shift / planar_in1 / planar_out stay fp32.  Cin is
+                               then the K extent of the packed weights (a multiple of 64), Cout the GEMM columns (multiple of 32);
+                               inference chains only (the weight-gradient kernels read fp32 activations) */
+    int Cin_store;          /* half_io: channels per pixel of the stored input tensor (<= Cin, multiple of 8; the K columns
+                               beyond it are zero-filled by TMA); 0 = Cin */
+    int Cout_store;         /* half_io: channels per pixel of the stored output tensor (every pixel row written is 64 channels:
+                               real columns, then zeros; rows sticking out of the tensor are clipped); 0 = Cout (Cout/4 with
+                               pixel_shuffle) */
 } sci_conv_desc;
 
 /* 1 if this build contains the tcgen05 tensor-core convolution kernels. */
@@ -233,6 +243,15 @@ int sci_conv3x3_wgrad(const sci_wgrad_desc* d, int impl, void* stream);
  * anyway); sci_conv_unpack_wgrad then sums the two gradient blocks. */
 int sci_conv_pack_weights(const float* w, float* packed, int Co, int Ci, int groups, int Co_pad, int Ci_pad,
                           int ps, const float* oscale, int transpose_flip, int round_tf32, int ci_dup, void* stream);
+/* fp16 form of the forward packing for sci_conv_desc.half_io layers: packed [9][Co_pad][Ci_pad] IEEE binary16, round to
+ * nearest; Ci_pad % 64 == 0 (one 128-byte operand row = 64 channels).  Same grouped / PixelShuffle / ci_dup rules as above
+ * (the fp16 network-boundary packer puts fp16(v) in channel k and fp16(v - fp16(v)) in channel k + ci_dup). */
+int sci_conv_pack_weights_half(const float* w, void* packed, int Co, int Ci, int groups, int Co_pad, int Ci_pad, int ps,
+                               int ci_dup, void* stream);
+/* fp16 form of sci_fastdvd_pack_input (packages/fastdvdnet/models.py:185 input block, circular window fastdvdnet.py:115):
+ * out [B][H][W][64] binary16, channels 0..11 = fp16 of [f0 RGB, sigma, f1 RGB, sigma, f2 RGB, sigma], 16..27 = the fp16
+ * remainders, others zero. */
+int sci_fastdvd_pack_input_half(const float* frames, float sigma, void* out, int B, int H, int W, void* stream);
 /* Data-gradient weights of a STRIDE-2 layer (groups = 1) as a sub-pixel convolution over dz at the low resolution:
  * packed [9][4*Ci_pad][Co_pad]; run sci_conv3x3_dgrad with x = dz [N][Ho][Wo][Co_pad], Cin = Co_pad, Cout = 4*Ci_pad,
  * stride 1, pixel_shuffle = 1 -> dx [N][2Ho][2Wo][Ci_pad].  Replaces "zero-dilate dz, then convolve at full resolution"
