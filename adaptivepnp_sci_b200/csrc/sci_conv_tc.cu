@@ -692,6 +692,26 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 // ---- fp16 output: unit = `ucols` accumulator columns -> one 64-channel (128-byte) pixel row
                 const int nun = (p.Cout + p.ucols - 1) / p.ucols;
                 const int hunits = rows * nun;
+                // skip values of unit u (fp16, up to 128 bytes of this lane's pixel row), requested one unit ahead
+                auto load_res = [&](int u, uint4 (&r)[8]) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) r[j] = make_uint4(0u, 0u, 0u, 0u);
+                    if (u < hunits && valid) {
+                        const int t = u / nun, col0 = (u - t * nun) * p.ucols;
+                        const int ncv = min(p.ucols, p.Cout - col0);
+                        const int cg = p.col0 + col0, ho = y0 + t;
+                        int qq = 0, cx = cg;
+                        if (p.ps) { qq = cg / Cq; cx = cg - qq * Cq; }
+                        const long pix = p.ps ? (((long)n * 2 * p.H + 2 * ho + (qq >> 1)) * 2 * p.W + 2 * wo + (qq & 1))
+                                              : (((long)n * p.H + ho) * p.W + wo);
+                        const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.residual) + pix * p.Cstore + cx);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (j * 8 < ncv) r[j] = __ldg(rp + j);
+                    }
+                };
+                uint4 rres[8];
+                if (MODE == 1) load_res(g, rres);
                 for (int u = g; u < hunits; u += EPI_WG) {
                     const int t = u / nun, col0 = (u - t * nun) * p.ucols;
                     const int ncv = min(p.ucols, p.Cout - col0);           // valid accumulator columns of this unit (32 or 64)
@@ -699,19 +719,8 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const int cg = p.col0 + col0;
                     int qq = 0, cx = cg;
                     if (p.ps) { qq = cg / Cq; cx = cg - qq * Cq; }
-                    uint4 rres[8];
-                    if (MODE == 1) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) rres[j] = make_uint4(0u, 0u, 0u, 0u);
-                        if (valid) {
-                            const long pix = p.ps ? (((long)n * 2 * p.H + 2 * ho + (qq >> 1)) * 2 * p.W + 2 * wo + (qq & 1))
-                                                  : (((long)n * p.H + ho) * p.W + wo);
-                            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.residual) + pix * p.Cstore + cx);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                if (j * 8 < ncv) rres[j] = __ldg(rp + j);
-                        }
-                    }
+                    uint4 rnext[8];
+                    if (MODE == 1) load_res(u + EPI_WG, rnext);
                     const uint32_t t_row = tmem_base + (uint32_t)((acc * p.R + (p.stack ? p.R - 1 - t : t)) * p.acc_stride) + ((uint32_t)(q * 32) << 16);
                     uint32_t hv[32];                                        // 64 fp16 values of this lane's pixel
 #pragma unroll
@@ -759,6 +768,10 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                     ++st_cnt;
+                    if (MODE == 1) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) rres[j] = rnext[j];
+                    }
                 }
             } else {
             // one unit = 32 channels of one output row for this lane's pixel
@@ -1037,7 +1050,7 @@ int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream, int col0, int ncol
     // measured per layer (tools/pass_layers.py): the second warpgroup pays where the epilogue work per MMA is high (K <= 32:
     // 12->90 0.270 -> 0.255 ms, or a skip-add: 64->128+PS 0.251 -> 0.178 ms) and costs where the MMA-issuing warp is the
     // critical path and now shares its scheduler with two epilogue warps (128->128: 0.067 -> 0.078 ms)
-    const int epi_first = epi_env ? (epi_env == 1 ? 1 : 2) : ((p.k_chunks <= 1 || d->residual) ? 2 : 1);
+    const int epi_first = epi_env ? (epi_env == 1 ? 1 : 2) : ((half || p.k_chunks <= 1 || d->residual) ? 2 : 1);
     for (epi_wg = epi_first; epi_wg >= 1; --epi_wg) {
         for (p.out_bufs = (epi_wg == 2 ? 1 : 2); p.out_bufs >= 1; --p.out_bufs) {
             out_stage = p.tma_store ? 4 * epi_wg * p.out_bufs * 4096 : 0;
@@ -1050,7 +1063,9 @@ int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream, int col0, int ncol
             if (p.out_bufs == 1) break;
         }
         const bool resident_with_one = w_bytes + 3 * A2_STAGE <= total_budget - (p.tma_store ? 4 * 4096 : 0);
-        if (epi_wg == 1 || epi_env == 2 || p.resident || !resident_with_one) break;
+        // fp16 chains: the MMAs are twice as fast, so the epilogue decides more often - two warpgroups even where that costs
+        // the weights their residency (64->128 + PixelShuffle: 0.215 ms resident with one group, 0.135 ms streamed with two)
+        if (epi_wg == 1 || epi_env == 2 || half || p.resident || !resident_with_one) break;
     }
     if (env_int("SCI_CONV_RESIDENT", 1) == 0) p.resident = 0;
     const int stage_bytes = A2_STAGE + (p.resident ? 0 : 3 * b_bytes);

@@ -405,32 +405,51 @@ __global__ void pack_weights_half_kernel(const float* __restrict__ w, __half* __
 // FastDVDnet input block as fp16 NHWC rows of 64 channels (128 bytes): channel k = fp16(v), channel k + 16 = fp16(v - fp16(v))
 // (the first layer's weights are duplicated there, ci_dup = 16), everything else zero.  One thread per pixel, eight
 // 16-byte stores = one full 128-byte line.
+__device__ __forceinline__ uint4 pack8(const __half* v) {
+    auto pk = [](__half a, __half b) -> uint32_t { return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16); };
+    return make_uint4(pk(v[0], v[1]), pk(v[2], v[3]), pk(v[4], v[5]), pk(v[6], v[7]));
+}
 __global__ void __launch_bounds__(256) fastdvd_pack_half_kernel(const float* __restrict__ frames, float sigma,
                                                                 __half* __restrict__ out, int B, int H, int W) {
+    __shared__ uint4 tile[8][32 * 8];                 // per warp: 32 pixels x 8 chunks of 16 bytes, XOR-swizzled
     const long plane = (long)H * W;
     const int f = blockIdx.y;
-    const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= plane) return;
-    __half hi[12], lo[12];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long p0 = (long)blockIdx.x * blockDim.x + warp * 32;       // first pixel of this warp
+    const long p = p0 + lane;
+    __half hi[16], lo[16];
 #pragma unroll
-    for (int slot = 0; slot < 3; ++slot) {
-        const int src = (f + slot - 1 + B) % B;                              // circular window (fastdvdnet.py:115)
+    for (int k = 0; k < 16; ++k) { hi[k] = __float2half_rn(0.f); lo[k] = hi[k]; }
+    if (p < plane) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const float v = (c == 3) ? sigma : __ldg(frames + ((long)src * 3 + c) * plane + p);
-            const __half h = __float2half_rn(v);
-            hi[slot * 4 + c] = h;
-            lo[slot * 4 + c] = __float2half_rn(v - __half2float(h));
+        for (int slot = 0; slot < 3; ++slot) {
+            const int src = (f + slot - 1 + B) % B;                          // circular window (fastdvdnet.py:115)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float v = (c == 3) ? sigma : __ldg(frames + ((long)src * 3 + c) * plane + p);
+                const __half h = __float2half_rn(v);
+                hi[slot * 4 + c] = h;
+                lo[slot * 4 + c] = __float2half_rn(v - __half2float(h));
+            }
         }
     }
-    auto pk = [](__half a, __half b) -> uint32_t { return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16); };
-    uint4* dst = reinterpret_cast<uint4*>(out + ((long)f * plane + p) * 64);
+    // stage the warp's 32 rows of 128 bytes (chunk j of pixel l at slot l*8 + (j ^ (l & 7)): conflict-free both ways) ...
+    uint4* t = tile[warp];
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    dst[0] = make_uint4(pk(hi[0], hi[1]), pk(hi[2], hi[3]), pk(hi[4], hi[5]), pk(hi[6], hi[7]));
-    dst[1] = make_uint4(pk(hi[8], hi[9]), pk(hi[10], hi[11]), 0u, 0u);
-    dst[2] = make_uint4(pk(lo[0], lo[1]), pk(lo[2], lo[3]), pk(lo[4], lo[5]), pk(lo[6], lo[7]));
-    dst[3] = make_uint4(pk(lo[8], lo[9]), pk(lo[10], lo[11]), 0u, 0u);
-    dst[4] = z; dst[5] = z; dst[6] = z; dst[7] = z;
+    t[lane * 8 + (0 ^ (lane & 7))] = pack8(hi);
+    t[lane * 8 + (1 ^ (lane & 7))] = pack8(hi + 8);
+    t[lane * 8 + (2 ^ (lane & 7))] = pack8(lo);
+    t[lane * 8 + (3 ^ (lane & 7))] = pack8(lo + 8);
+#pragma unroll
+    for (int j = 4; j < 8; ++j) t[lane * 8 + (j ^ (lane & 7))] = z;
+    __syncwarp();
+    // ... and write them as 8 fully coalesced 512-byte warp stores
+    uint4* dst = reinterpret_cast<uint4*>(out + ((long)f * plane + p0) * 64);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int o = i * 32 + lane, px = o >> 3, j = o & 7;
+        if (p0 + px < plane) dst[o] = t[px * 8 + (j ^ (px & 7))];
+    }
 }
 
 extern "C" int sci_conv_pack_weights(const float* w, float* packed, int Co, int Ci, int groups, int Co_pad, int Ci_pad,
