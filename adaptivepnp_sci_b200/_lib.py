@@ -58,6 +58,13 @@ PROTOTYPES = {
     "sci_conv_pack_weights": [_p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _i, _p],
     "sci_conv_pack_weights_s2t": [_p, _p, _i, _i, _i, _i, _p, _i, _p],
     "sci_conv_pack_weights_half": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
+    "sci_p2p_alloc": [_sz, _p],
+    "sci_p2p_free": [_p],
+    "sci_p2p_get_handle": [_p, _p],
+    "sci_p2p_open_handle": [_p, _p],
+    "sci_p2p_close_handle": [_p],
+    "sci_halo_send": [_p, _i, _i, _i, _i, _p, _p, _p, _p, ctypes.c_uint, _p, _p],
+    "sci_halo_assemble": [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, ctypes.c_uint, _p, _p, _p],
     "sci_fastdvd_pack_input_half": [_p, _f, _p, _i, _i, _i, _p],
     "sci_conv_unpack_wgrad": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "sci_bn_fold": [_p, _p, _p, _p, _f, _p, _p, _i, _i, _p],

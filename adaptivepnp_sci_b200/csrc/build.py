@@ -28,6 +28,7 @@ SOURCES = [
     ("sci_train.cu", ["--fmad=false"]),
     ("sci_ddnet.cu", ["--fmad=false"]),
     ("sci_host_rng.cu", ["-Xcompiler", "-ffp-contract=off"]),
+    ("sci_p2p.cu", []),
 ]
 
 

@@ -166,6 +166,9 @@ def _tiled_demosaic_denoise(tile, adapter, halo, x, b, inv_rou, w, tau, x_rgb, u
     ops.malvar2004(m_ext.view(B, m_ext.shape[2], W), None, 0.0, None, 0.0, rgb_ext, None)
     x_rgb.copy_(rgb_ext[:, :, top2:top2 + rows])
     ops.axpy(x_rgb, -float(np.float32(1 / tau)), w, out=u)                              # u = x_rgb - w/tau (:198)
+    if adapter.__name__.endswith("fastdvdnet_adapter") and not do_update:
+        # inference: one 40-row exchange per DenBlock instead of an 80-row overlap for the whole cascade
+        return adapter._unwrap(model).engine().forward_tiled(u, nsig, tile)
     u_ext, top = tile.exchange(u, halo)
     view = _TileView(tile, top, u_ext.shape[2])
     xhat_ext = adapter.denoise_planar(u_ext, pb, nsig, model, lr_, do_update, update_per_iter, grad_sync=grad_sync, tile=view)
@@ -234,6 +237,7 @@ def twoStageAdmm_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, gamma=0.01,
             raise ValueError("tiled mode: pass this rank's rows (%d x %d), got %d x %d" % (tile.rows, tile.W, H, W))
         if grad_sync is None:
             grad_sync = tile.all_reduce_sum          # loss is normalised by the whole frame -> gradients ADD over strips
+        tile.enable_p2p(3 * B, 28 if name == 'ffdnet_color' else 80)      # boundary rows go peer to peer over NVLink
     alpha = 0.01 if name == 'tv' else 1                                  # :101-104
     rou = 0.55 if name == 'fastdvd_color' else 1                         # :106-109
     tau = 100                                                            # :110

@@ -564,6 +564,38 @@ class FastDVDnetEngine(_EngineBase):
             self._saved = (s1, s2, B, H, W)
         return out
 
+    BLOCK_HALO = 40      # rows: one DenBlock sees -38..+36 full-resolution rows (two stride-2 levels, 16 convs); multiple of 4
+
+    def forward_tiled(self, u_own, sigma, tile):
+        """Inference on a row strip of a larger frame (``parallel.TileContext``): u_own [B,3,rows,W] -> denoised own rows.
+
+        One halo exchange PER DenBlock (40 rows each) instead of one 80-row halo for the two-block cascade: block 1 runs on
+        the strip extended by 40 rows, its own rows are exact; their boundary rows are exchanged again and block 2 runs on
+        that.  Redundant convolution work: (rows + 80) / rows instead of (rows + 160) / rows (1.31 vs 1.62 at 256-row strips).
+        Zero padding is only ever applied at true image borders, so the result equals the un-tiled one."""
+        B, _, rows, W = u_own.shape
+        self.prepare(training=False)
+        dev = u_own.device
+        h = self.BLOCK_HALO
+        ext1, top = tile.exchange(u_own, h)
+        t1_ext = self.ws.get("tl_t1", tuple(ext1.shape), dev)
+        self.pdl_chain = self.profile is None and self.impl == IMPL_TC
+        try:
+            self._run_block(0, ext1, sigma, t1_ext)
+            t1_own = t1_ext[:, :, top:top + rows].contiguous()
+            ext2, top = tile.exchange(t1_own, h)
+            out_ext = self.ws.get("tl_out", tuple(ext2.shape), dev)
+            self._run_block(1, ext2, sigma, out_ext)
+        finally:
+            self.pdl_chain = False
+        return out_ext[:, :, top:top + rows].contiguous()
+
+    def _run_block(self, which, frames, sigma, out):
+        if self.half:
+            self._block_forward_h(self.t1h if which == 0 else self.t2h, frames, sigma, out)
+        else:
+            self._block_forward("t%d" % (which + 1), self.t1 if which == 0 else self.t2, frames, sigma, out, False)
+
     # ---- backward of one DenBlock -----------------------------------------------------------------------
     def _block_backward(self, blk, S, dout, B, H, W, need_input_grad):
         """dout [B,3,H,W] = d loss / d block output.  Returns d loss / d (packed input) [B,H,W,32] or None."""

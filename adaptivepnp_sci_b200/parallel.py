@@ -73,6 +73,79 @@ class Context:
                 dist.destroy_process_group()
 
 
+class P2PRegion:
+    """One cudaMalloc'ed region per rank, mapped into its two neighbours through CUDA IPC (``sci_p2p_*``):
+
+        [ flags: u32 from_up @0, u32 from_down @4 ... 256 B ][ slot(parity 0, TOP) | slot(0, BOTTOM) | slot(1, TOP) | slot(1, BOTTOM) ]
+
+    ``exchange`` stores this rank's boundary rows straight into the neighbours' slots over NVLink (``sci_halo_send``) and
+    assembles its halo-extended strip from its own slots once the neighbours' sequence numbers have arrived
+    (``sci_halo_assemble``): no NCCL call, no staging copy, no host synchronisation.  All ranks count exchanges in lock-step."""
+    HDR = 256
+
+    def __init__(self, ctx, slot_bytes):
+        import ctypes
+        import torch.distributed as dist
+        from ._lib import call
+        self.ctx, self.slot = ctx, (int(slot_bytes) + 255) // 256 * 256
+        self.seq = 0
+        base = ctypes.c_void_p()
+        call("sci_p2p_alloc", self.HDR + 4 * self.slot, ctypes.byref(base))
+        self.base = base.value
+        h = ctypes.create_string_buffer(64)
+        call("sci_p2p_get_handle", ctypes.c_void_p(self.base), h)
+        handles = [None] * ctx.world
+        dist.all_gather_object(handles, bytes(h.raw))
+        self.peer = {}
+        for r in (ctx.rank - 1, ctx.rank + 1):
+            if 0 <= r < ctx.world:
+                q = ctypes.c_void_p()
+                call("sci_p2p_open_handle", ctypes.create_string_buffer(handles[r], 64), ctypes.byref(q))
+                self.peer[r] = q.value
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.scratch = torch.zeros(2, dtype=torch.int32, device=dev)          # [done counter of the send kernel, error word]
+        dist.barrier()                                                        # every region is mapped before anyone stores into it
+
+    def slot_ptr(self, base, parity, side):
+        return base + self.HDR + (parity * 2 + side) * self.slot
+
+    def exchange(self, own, top, bot, halo):
+        import ctypes
+        from ._lib import call, ptr, stream
+        B, C, rows, W = own.shape
+        if B * C * halo * W * 4 > self.slot:
+            raise ValueError("halo of %d bytes exceeds the P2P slot (%d)" % (B * C * halo * W * 4, self.slot))
+        self.seq += 1
+        par, r = self.seq & 1, self.ctx.rank
+        vp = ctypes.c_void_p
+        up, down = self.peer.get(r - 1) if top else None, self.peer.get(r + 1) if bot else None
+        # my top rows are the BOTTOM halo (side 1, flag from_down @4) of the upper neighbour, and vice versa
+        call("sci_halo_send", ptr(own), B * C, rows, W, halo,
+             vp(self.slot_ptr(up, par, 1)) if up else None, vp(self.slot_ptr(down, par, 0)) if down else None,
+             vp(up + 4) if up else None, vp(down) if down else None, self.seq, vp(self.scratch.data_ptr()), stream())
+        ext = torch.empty((B, C, top + rows + bot, W), dtype=own.dtype, device=own.device)
+        call("sci_halo_assemble", ptr(own), B * C, rows, W, top, bot, vp(self.slot_ptr(self.base, par, 0)),
+             vp(self.slot_ptr(self.base, par, 1)), vp(self.base), vp(self.base + 4), self.seq, ptr(ext),
+             vp(self.scratch.data_ptr() + 4), stream())
+        return ext
+
+    def check(self):
+        """Host-side check of the bounded wait (call at a synchronisation point)."""
+        e = int(self.scratch[1])
+        if e:
+            raise RuntimeError("P2P halo exchange: neighbour %s did not deliver within 10 s" % ("above" if e == 1 else "below"))
+
+    def close(self):
+        from ._lib import call
+        import ctypes
+        for q in self.peer.values():
+            call("sci_p2p_close_handle", ctypes.c_void_p(q))
+        self.peer = {}
+        if self.base:
+            call("sci_p2p_free", ctypes.c_void_p(self.base))
+            self.base = None
+
+
 class TileContext:
     """Row-strip spatial tiling of ONE large frame over the ranks (BASELINE config 5).
 
@@ -85,8 +158,9 @@ class TileContext:
       FFDNet-colour: -24..+25 -> 28), exchanged once per ADMM iteration; the strip is then denoised with its halo and
       cropped ("overlap-tile"), so zero padding is only ever applied at true image borders.
 
-    ``exchange`` moves the halo rows with point-to-point sends between neighbouring ranks (NCCL over NVLink on GPUs,
-    gloo in the CPU/one-GPU tests).  No collective is on the per-iteration path; the only reductions are the scalar
+    ``exchange`` moves the halo rows peer to peer: after ``enable_p2p`` the boundary rows are stored straight into the
+    neighbour's memory over NVLink by ``sci_halo_send`` / ``sci_halo_assemble`` (``P2PRegion``); without it (CPU tests,
+    ``SCI_TILE_P2P=0``) with point-to-point sends of torch.distributed.  No collective is on the per-iteration path; the only reductions are the scalar
     PSNR sums, the fine-tune loss/gradient all-reduce (SUM: the loss is normalised by the pixel count of the whole frame)
     and the final gather of the result strips."""
 
@@ -99,6 +173,20 @@ class TileContext:
         self.rows = H_total // ctx.world
         self.r0 = self.rank * self.rows
         self.total_pixels = H_total * W
+        self.p2p = None
+        self.halo_bytes_moved = 0
+
+    def enable_p2p(self, max_planes, max_halo):
+        """Peer-to-peer halo exchange over NVLink (``P2PRegion``) for CUDA strips of fp32 planes; every rank must call it with
+        the same sizes.  ``SCI_TILE_P2P=0`` keeps the point-to-point sends of torch.distributed (NCCL / gloo)."""
+        if self.world == 1 or not torch.cuda.is_available() or os.environ.get("SCI_TILE_P2P", "1") == "0":
+            return False
+        need = max_planes * max_halo * self.W * 4
+        if self.p2p is None or self.p2p.slot < need:
+            if self.p2p is not None:
+                self.p2p.close()
+            self.p2p = P2PRegion(self.ctx, need)
+        return True
 
     def slice_rows(self, a):
         """numpy/torch [H_total, ...] -> this rank's rows."""
@@ -117,6 +205,9 @@ class TileContext:
         import torch.distributed as dist
         top, bot = self.halo_sizes(halo)
         B, C, rows, W = own.shape
+        self.halo_bytes_moved += (top + bot) * B * C * W * own.element_size()
+        if self.world > 1 and self.p2p is not None and own.is_cuda and own.dtype == torch.float32 and W % 4 == 0:
+            return self.p2p.exchange(own.contiguous(), top, bot, halo), top
         ext = torch.empty((B, C, top + rows + bot, W), dtype=own.dtype, device=own.device)
         ext[:, :, top:top + rows].copy_(own)
         if self.world == 1:
@@ -152,6 +243,8 @@ class TileContext:
 
     def gather_rows(self, strip):
         """strip [..., rows, W] on every rank -> full [..., H_total, W] on every rank."""
+        if self.p2p is not None:
+            self.p2p.check()
         if self.world == 1:
             return strip
         import torch.distributed as dist

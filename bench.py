@@ -71,7 +71,7 @@ def config_dict(c, cfg):
          "l2": "working set per step >> 126 MB L2 (solver state + activations): no flush needed; roofline_hbm flushes L2 between launches"}
     if cfg["denoiser"] == "fastdvd_color":
         d["weights"] = "synthetic contractive init seed 4242 (trained FastDVDnet weights absent from the reference)"
-        d["conv"] = "tcgen05 TF32 operands, fp32 accumulate"
+        d["conv"] = "tcgen05: inference passes kind::f16 (fp16 operands, same 11-bit significand as TF32), online update kind::tf32; fp32 accumulate"
         d["finetune"] = "k=9,18; 2 Adam steps; lr 2e-6" if c == 4 else "none (inference schedule; the fine-tune of one 2048x2048x24 frame needs all 8 GPUs)"
     elif cfg["denoiser"].startswith("ffdnet"):
         d["weights"] = "model_zoo/%s.pth (the reference's own file)" % cfg["denoiser"]
@@ -477,8 +477,8 @@ def main():
             kw["grad_sync"] = grad_sync                                   # shared weights: NCCL mean all-reduce of the gradients
         if c == 5:
             kw["tile"] = tile
-        if device_out and c != 5:
-            kw["return_device"] = True
+        if device_out:
+            kw["return_device"] = True                                   # config 5: the rank's own strips stay on its GPU
         return twoStageAdmm_denoise_bayer(y, phi, 1, 0.01, cfg["denoiser"], cfg["iters"], False, cfg["sigma"], x0_bayer=x0,
                                           X_orig=None, show_iqa=False, logf=None, **kw)
 
@@ -559,10 +559,12 @@ def main():
             if os.path.exists(tpath) and cfg["denoiser"] == "fastdvd_color" and c == 4:
                 traffic, tsrc = json.load(open(tpath))["dram_bytes_per_launch"], "profiles/" + name    # ncu --set full capture, per launch
                 break
-        roofline = {"bound": "tensor", "kernel": "conv_fwd2_tc_kernel / conv_fwd_tc_kernel (tcgen05.mma kind::tf32)", "achieved": achieved,
+        kind = "kind::f16" if cfg["denoiser"] == "fastdvd_color" else "kind::tf32"
+        roofline = {"bound": "tensor", "kernel": "conv_fwd2_tc_kernel / conv_fwd_tc_kernel (tcgen05.mma %s)" % kind, "achieved": achieved,
                     "peak": peak_bf16, "unit": "TFLOP/s", "frac": achieved / peak_bf16, "traffic": traffic, "traffic_source": tsrc,
-                    "peak_kind": pk_kind + " cuBLAS bf16 (sustained); TF32 operands run at half the bf16 rate",
-                    "frac_of_tf32_rate": achieved / (peak_bf16 / 2),
+                    "peak_kind": pk_kind + " cuBLAS bf16 (sustained)" + ("; fp16 operands run at the bf16 rate" if kind == "kind::f16"
+                                                                        else "; TF32 operands run at half the bf16 rate"),
+                    "frac_of_operand_rate": achieved / (peak_bf16 if kind == "kind::f16" else peak_bf16 / 2),
                     "flops_per_pass": flops, "launches_per_pass": len(prof), "avg_launch_ms": 1e3 * conv_s / len(prof),
                     "pass": "one inference pass over %dx%dx%d (algorithmic flops, temp1 evaluated once per frame)" % (bb, hh, W)}
         del u
@@ -615,7 +617,9 @@ def main():
     line = {"metric": "admm_iters_per_sec", "value": value, "unit": "iters/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "sec_per_recon": ms * 1e-3 / args.steps,
             "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None,
-            "dtype": "f32" if c == 1 else "tf32", "data": "synthetic",
+            "dtype": {"tv": "f32", "fastdvd_color": "f16 operands / f32 accumulate (inference convs); tf32 / f32 (online update); f32 elsewhere",
+                      "ffdnet_color": "tf32 (3-product split) / f32", "ffdnet_gray": "tf32 (3-product split) / f32"}[cfg["denoiser"]],
+            "data": "synthetic",
             "config": config_dict(c, cfg), "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "iters/s", "sec_per_recon": ms_e2e * 1e-3 / args.steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

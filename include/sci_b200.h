@@ -373,6 +373,28 @@ int sci_axpy(const float* x, float a, const float* y, float* out, long n, void* 
 int sci_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long n, double lr,
                   double beta1, double beta2, double eps, int step, void* stream);
 
+/* ---- peer-to-peer halo exchange (spatial row-strip tiling of one large frame, BASELINE config 5; SURVEY 8(b) export
+ * `sci_halo_exchange`, 8(e) row 3).  Replaces the reference-side "one GPU holds the whole frame" with strips whose boundary
+ * rows are stored straight into the neighbouring GPU's memory over NVLink.
+ * sci_p2p_alloc / get_handle / open_handle: a cudaMalloc'ed, zeroed region, its 64-byte CUDA IPC handle, and the mapping
+ * of a neighbour's region into this process (peer access enabled lazily).  The caller exchanges the handles once
+ * (torch.distributed object all-gather).
+ * sci_halo_send: copies the first / last `halo` rows of own [planes][rows][W] (fp32) into up_dst / down_dst (PEER pointers,
+ * NULL = no neighbour on that side), then release-stores `seq` into up_flag / down_flag (peer flag words).
+ * sci_halo_assemble (same stream): waits until *flag_top / *flag_bot (LOCAL flag words written by the neighbours) have
+ * reached `seq`, then writes ext [planes][top + rows + bot][W] = [recv_top | own | recv_bot].  *err becomes non-zero if a
+ * neighbour did not deliver within ~10 s (the wait is bounded: a lost peer must not hang the GPU). */
+int sci_p2p_alloc(size_t bytes, void** ptr);
+int sci_p2p_free(void* ptr);
+int sci_p2p_get_handle(void* ptr, void* handle64);
+int sci_p2p_open_handle(const void* handle64, void** ptr);
+int sci_p2p_close_handle(void* ptr);
+int sci_halo_send(const float* own, int planes, int rows, int W, int halo, float* up_dst, float* down_dst,
+                  unsigned* up_flag, unsigned* down_flag, unsigned seq, unsigned* done_counter, void* stream);
+int sci_halo_assemble(const float* own, int planes, int rows, int W, int top, int bot, const float* recv_top,
+                      const float* recv_bot, const unsigned* flag_top, const unsigned* flag_bot, unsigned seq,
+                      float* ext, unsigned* err, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

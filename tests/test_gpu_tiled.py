@@ -67,9 +67,9 @@ def _fcase():
     return meas, mask, orig, warm
 
 
-def _fworker(rank, world, port, q):
+def _fworker(rank, world, port, q, impl="ref"):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK="0", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
-                      SCI_CONV_IMPL="ref")
+                      SCI_CONV_IMPL=impl)
     from adaptivepnp_sci_b200 import parallel
     from adaptivepnp_sci_b200.dvp_linear_inv_2_stage_ADMM_tensor_online import twoStageAdmm_denoise_bayer
     from adaptivepnp_sci_b200.utilspy import worker_init_fn
@@ -82,12 +82,16 @@ def _fworker(rank, world, port, q):
                                    [12 / 255], x0_bayer=torch.from_numpy(tile.slice_rows(warm)).cuda(),
                                    X_orig=tile.slice_rows(orig), model_denoise=m, logf=io.StringIO(), tile=tile,
                                    update_times=-1, **KW)
-    q.put((rank, r[0], r[1], np.array(r[4]), m.state_dict()["module.temp2.inc.convblock.3.weight"].cpu().numpy()))
+    q.put((rank, r[0], r[1], np.array(r[4]), m.state_dict()["module.temp2.inc.convblock.3.weight"].cpu().numpy(),
+           tile.p2p is not None))
     ctx.finalize()
 
 
-def test_tiled_fastdvdnet_equals_untiled(cuda, monkeypatch):
-    monkeypatch.setenv("SCI_CONV_IMPL", "ref")
+@pytest.mark.parametrize("impl", ["ref", "tc"])
+def test_tiled_fastdvdnet_equals_untiled(cuda, monkeypatch, impl):
+    """Strips + one 40-row P2P halo exchange per DenBlock (inference iterations) / 80-row overlap (the online update) equal
+    the un-tiled run, on the fp32 engine and on the tensor-core (fp16 inference / TF32 training) engine."""
+    monkeypatch.setenv("SCI_CONV_IMPL", impl)
     from adaptivepnp_sci_b200.dvp_linear_inv_2_stage_ADMM_tensor_online import twoStageAdmm_denoise_bayer
     from adaptivepnp_sci_b200.utilspy import worker_init_fn
     meas, mask, orig, warm = _fcase()
@@ -100,17 +104,21 @@ def test_tiled_fastdvdnet_equals_untiled(cuda, monkeypatch):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctxm = mp.get_context("spawn")
     q = ctxm.Queue()
-    procs = [ctxm.Process(target=_fworker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctxm.Process(target=_fworker, args=(r, 2, port, q, impl)) for r in range(2)]
     for p in procs:
         p.start()
     outs = sorted((q.get(timeout=300) for _ in range(2)), key=lambda t: t[0])
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, rgb, xb, psnr_all, w in outs:
-        assert np.max(np.abs(rgb - ref[0])) < 2e-5 and np.max(np.abs(xb - ref[1])) < 2e-5
+    # the tensor-core engine computes every output pixel with the same operands in the same order whether tiled or not,
+    # except for the fine-tune gradients (summed over strips in a different order)
+    tol = 2e-5 if impl == "ref" else 2e-4
+    for rank, rgb, xb, psnr_all, w, used_p2p in outs:
+        assert used_p2p                                   # the boundary rows went through sci_halo_send / sci_halo_assemble
+        assert np.max(np.abs(rgb - ref[0])) < tol and np.max(np.abs(xb - ref[1])) < tol
         assert np.max(np.abs(psnr_all - np.array(ref[4]))) < 1e-3
-        assert np.max(np.abs(w - w_ref)) <= 2 * 2e-6 * 1.01 and np.mean(np.abs(w - w_ref)) < 0.1 * 2e-6
+        assert np.max(np.abs(w - w_ref)) <= 2 * 2e-6 * 1.01 and np.mean(np.abs(w - w_ref)) < (0.1 if impl == "ref" else 0.5) * 2e-6
 
 
 def test_tiled_equals_untiled(cuda, monkeypatch):
