@@ -42,7 +42,9 @@ PROTOTYPES = {
     "sci_tv_chambolle2d": [_p, _p, _f, _p, _p, _f, _i, _i, _i, _i, _f, _f, _i, _p, _sz, _p, _p],
     "sci_malvar2004": [_p, _p, _f, _p, _f, _p, _p, _i, _i, _i, _p],
     "sci_dual_update_rgb": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p],
+    "sci_dual_update_stage1": [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p],
     "sci_reflect_pad2d": [_p, _p, _l, _i, _i, _i, _i, _p],
+    "sci_replicate_pad2d": [_p, _p, _l, _i, _i, _i, _i, _p],
     "sci_crop2d": [_p, _p, _l, _i, _i, _i, _i, _p],
     "sci_closed_form_demosaic": [_p, _p, _p, _p, _f, _f, _f, _i, _p, _p, _i, _i, _i, _p],
     "sci_rgb_to_bayer": [_p, _p, _i, _i, _i, _p],

@@ -466,6 +466,61 @@ extern "C" int sci_dual_update_rgb(const float* xhat, const float* x_rgb, float*
     return SCI_OK;
 }
 
+// Stage-1 bookkeeping of the deep branches of admm_denoise_bayer_demosaic_pre (dvp:439-503): ONE dual variable,
+//   theta = clip(RGGB samples of xhat);  b = b - (x - theta);  PSNR of x (not theta, :507-512).
+// first_iter: xall and theta_all are the same tensor at k = 0 (:375-377), so the sampling overwrites x with the UNCLIPPED
+// samples before the clip rebinds theta: x is written back here, b receives -(theta_unclipped - theta), the PSNR sees it.
+__global__ void __launch_bounds__(256) dual_update_stage1_kernel(const float* __restrict__ xhat, float* __restrict__ x,
+                                                                  float* __restrict__ b, float* __restrict__ theta, int first_iter,
+                                                                  int H, int W, const float* __restrict__ orig,
+                                                                  double* __restrict__ sse) {
+    __shared__ double red[32];
+    const int t = blockIdx.z;
+    const long plane = (long)H * W;
+    const int col = (blockIdx.x * blockDim.x + threadIdx.x) * 2, row = blockIdx.y;
+    double err = 0.0;
+    if (col < W) {
+        const long p = (long)row * W + col;
+        const long o = (long)t * 3 * plane + p;
+        // RGGB: even row -> (R, G), odd row -> (G, B)
+        const float2 ca = *reinterpret_cast<const float2*>(xhat + o + ((row & 1) ? 1 : 0) * plane);
+        const float2 cb = *reinterpret_cast<const float2*>(xhat + o + ((row & 1) ? 2 : 1) * plane);
+        const float s0 = ca.x, s1 = cb.y;
+        const float t0 = fminf(fmaxf(s0, 0.f), 1.f), t1 = fminf(fmaxf(s1, 0.f), 1.f);
+        const long q = (long)t * plane + p;
+        float2 xv = *reinterpret_cast<const float2*>(x + q);
+        if (first_iter) {
+            xv.x = s0; xv.y = s1;
+            *reinterpret_cast<float2*>(x + q) = xv;
+        }
+        float2 bv = *reinterpret_cast<const float2*>(b + q);
+        bv.x = bv.x - (xv.x - t0);
+        bv.y = bv.y - (xv.y - t1);
+        *reinterpret_cast<float2*>(b + q) = bv;
+        *reinterpret_cast<float2*>(theta + q) = make_float2(t0, t1);
+        if (orig) {
+            const float2 og = *reinterpret_cast<const float2*>(orig + q);
+            const float d0 = xv.x - og.x, d1 = xv.y - og.y;
+            err = (double)(d0 * d0) + (double)(d1 * d1);
+        }
+    }
+    if (orig) {
+        const double s = block_sum(err, red);
+        if (threadIdx.x == 0) atomicAdd(sse, s);
+    }
+}
+
+extern "C" int sci_dual_update_stage1(const float* xhat, float* x, float* b, float* theta, int first_iter, int H, int W, int B,
+                                      const float* orig, double* sse, void* stream) {
+    SCI_REQUIRE(xhat && x && b && theta, "dual_update_stage1: null pointer");
+    SCI_REQUIRE(H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && B > 0 && H <= 65535 && B <= 65535, "dual_update_stage1: shape");
+    SCI_REQUIRE(!orig || sse, "dual_update_stage1: orig given without sse");
+    dual_update_stage1_kernel<<<dim3(sci_ceil_div(W / 2, 256), H, B), 256, 0, sci_stream(stream)>>>(xhat, x, b, theta, first_iter,
+                                                                                                   H, W, orig, sse);
+    SCI_CHECK_LAUNCH("dual_update_stage1");
+    return SCI_OK;
+}
+
 // ---------------------------------------------------------------------------
 // Closed-form demosaic update of the `close_form_demosaic` branch (dvp:112-118, 175-182, 224-230), all frames:
 //   x_rgb[c] = (rho * x3[c] + b3[c] + tau * xhat[c] + w[c]) / (rho * m[c] + tau)   [clip to [0,1] on the FFDNet branch]
@@ -695,6 +750,25 @@ __global__ void reflect_pad_kernel(const float* __restrict__ in, float* __restri
     const long pl = idx / ((long)Wo * Ho);
     const int rs = r < H ? r : 2 * (H - 1) - r, cs = c < W ? c : 2 * (W - 1) - c;      // Ho <= 2H-1, Wo <= 2W-1 for crop: rs = r
     out[idx] = in[(pl * H + rs) * W + cs];
+}
+
+// Right/bottom REPLICATION padding (torch.nn.ReplicationPad2d): KAIR-FFDNet pads odd sizes to even this way before its
+// PixelUnShuffle (models/network_ffdnet.py:56-59) and crops afterwards (:68).
+__global__ void replicate_pad_kernel(const float* __restrict__ in, float* __restrict__ out, long planes, int H, int W, int Ho, int Wo) {
+    const long total = planes * Ho * Wo;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = (int)(idx % Wo), r = (int)((idx / Wo) % Ho);
+    const long pl = idx / ((long)Wo * Ho);
+    out[idx] = in[(pl * H + min(r, H - 1)) * W + min(c, W - 1)];
+}
+
+extern "C" int sci_replicate_pad2d(const float* in, float* out, long planes, int H, int W, int Ho, int Wo, void* stream) {
+    SCI_REQUIRE(in && out && planes > 0 && H > 0 && W > 0 && Ho >= H && Wo >= W, "replicate_pad2d");
+    const long total = planes * Ho * Wo;
+    replicate_pad_kernel<<<sci_ceil_div(total, 256), 256, 0, sci_stream(stream)>>>(in, out, planes, H, W, Ho, Wo);
+    SCI_CHECK_LAUNCH("replicate_pad2d");
+    return SCI_OK;
 }
 
 extern "C" int sci_reflect_pad2d(const float* in, float* out, long planes, int H, int W, int Ho, int Wo, void* stream) {

@@ -112,10 +112,17 @@ def admm_denoise_bayer_demosaic_pre(y_bayer, Phi_bayer, _lambda=1, gamma=0.01,
 
     y_bayer [H,W], Phi_bayer [H,W,B] float32 numpy.  Returns
     ``(x_bayer_np[H,W,B], psnr_[B], ssim_[B], psnr_all[iters])`` like the reference's
-    'tv' branch (:548-549).  Only 'tv' is reachable from ADMM_TV_Warm_Start_save.py; the deep
-    branches of this function in the reference duplicate stage 2 without the second dual
-    variable and are served by ``twoStageAdmm_denoise_bayer``.
+    'tv' branch (:548-549) - the only one ADMM_TV_Warm_Start_save.py reaches - or, for the deep
+    branches 'ffdnet_color' / 'fastdvd_color' (:456-500: Malvar demosaic of x - b, plug-in denoiser,
+    ONE dual variable), the 6-tuple ``(xbgr3_np, x_bayer_np, psnr_, ssim_, psnr_all, model)`` (:552).
+    The reference's 'PPP' branch compares ``denoiser.lower()`` with an upper-case literal (:411) and can
+    never be taken.
     """
+    name = denoiser if denoiser == 'tv' else str(denoiser).lower()
+    if name in ('ffdnet_color', 'fastdvd_color'):
+        return _stage1_deep(y_bayer, Phi_bayer, _lambda, gamma, name, denoiser, iter_max, noise_estimate, sigma, x0_bayer,
+                            X_orig, model, show_iqa, demosaic_method, lr_, inital_iter, interval_iter, logf, update_,
+                            update_per_iter)
     if denoiser != 'tv':
         raise ValueError('Unsupported denoiser {}!'.format(denoiser))
     sigma, iter_max = _as_list(sigma, iter_max)
@@ -145,6 +152,47 @@ def admm_denoise_bayer_demosaic_pre(y_bayer, Phi_bayer, _lambda=1, gamma=0.01,
     x_bayer_np = pb.to_hwb(x)                                           # stage 1 returns x, not theta (:538-541)
     psnr_, ssim_ = pb.frame_iqa(x, x_bayer_np, X_orig)
     return x_bayer_np, psnr_, ssim_, psnr_all
+
+
+def _stage1_deep(y_bayer, Phi_bayer, _lambda, gamma, name, denoiser, iter_max, noise_estimate, sigma, x0_bayer, X_orig, model,
+                 show_iqa, demosaic_method, lr_, inital_iter, interval_iter, logf, update_, update_per_iter):
+    """Deep branches of stage 1 (dvp...online.py:456-503): v = x - b -> Malvar -> denoiser -> theta; b -= x - theta."""
+    from . import fastdvdnet_adapter, ffdnet_adapter
+    if demosaic_method != 'malvar2004':
+        raise ValueError("demosaic_method must be 'malvar2004'")       # anything else leaves x_rgb at zeros in the reference (:451)
+    if update_ and name == 'ffdnet_color':
+        # the reference passes update_ as ``updata_`` on EVERY iteration here (:467): off the update interval the adapter
+        # then returns a (tensor, model) tuple that the sampling below indexes -> TypeError.  Only update_=False runs.
+        raise NotImplementedError("stage 1 with ffdnet_color and update_=True fails in the reference itself (dvp...online.py:467); "
+                                  "use twoStageAdmm_denoise_bayer for the online-adaptive loop")
+    sigma, iter_max = _as_list(sigma, iter_max)
+    pb = _Problem(y_bayer, Phi_bayer, x0_bayer, X_orig)
+    dev = pb.y.device
+    H, W, B = pb.H, pb.W, pb.B
+    n_total = int(sum(iter_max))
+    want_iqa = bool(show_iqa and X_orig is not None)
+    sse = torch.zeros(max(n_total, 1), dtype=torch.float64, device=dev) if want_iqa else None
+    theta, b, x = pb.theta, pb.b, pb.x
+    x_rgb = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
+    adapter = ffdnet_adapter if name == 'ffdnet_color' else fastdvdnet_adapter
+    sched, k, xhat = [], 0, None
+    for idx, nsig in enumerate(sigma):
+        for _ in range(iter_max[idx]):
+            ops.project_stage1(theta, b, pb.phi, pb.y, pb.phisum, x, _lambda, gamma)             # :389-391
+            ops.malvar2004(x, b, -1.0, None, 0.0, x_rgb, None)                                   # x_rgb = Malvar(merge(x - b)) :458-466
+            xhat = adapter.denoise_planar(x_rgb, pb, nsig, model, lr_, False, update_per_iter)   # :467-470 / :492
+            ops.dual_update_stage1(xhat, x, b, theta, first_iter=(k == 0),
+                                   orig=pb.orig if want_iqa else None, sse=sse[k:k + 1] if want_iqa else None)
+            sched.append(nsig)
+            k += 1
+    psnr_all = []
+    if want_iqa:
+        psnr_all = list(iqa.psnr_from_sse(sse.cpu().numpy()[:n_total], pb.npix * B))
+        _log_iterations(denoiser, sched, psnr_all, noise_estimate, logf)
+    x_bayer_np = pb.to_hwb(x)                                                                    # stage 1 returns x (:538-541)
+    psnr_, ssim_ = pb.frame_iqa(x, x_bayer_np, X_orig)
+    xbgr3_np = cuda2np(ops.planar_to_pixlast(xhat, 3, B).view(H, W, 3, B))
+    return xbgr3_np, x_bayer_np, psnr_, ssim_, psnr_all, model
 
 
 class _TileView:

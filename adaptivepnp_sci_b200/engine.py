@@ -428,10 +428,13 @@ class FFDNetEngine(_EngineBase):
 
     def forward_nchw(self, x, sigma):
         """Reference call convention model(img[N,3,H,W], sigma[N,1,1,1]) (test_ffdnet_ipol.py:350-351)."""
+        from . import ops
         s = float(sigma.flatten()[0])
         if sigma.numel() > 1 and not bool((sigma == sigma.flatten()[0]).all()):
             raise NotImplementedError("one noise level per call on the native path")
-        return self.forward(x.contiguous().float(), s, train=False).clone()
+        # odd sizes: replication pad to even, crop the result (network_ffdnet.py:56-59, :68)
+        xp, H, W = ops.replicate_pad_to_even(x.contiguous().float())
+        return ops.crop_to(self.forward(xp, s, train=False), H, W).clone()
 
 
 class _DenBlockLayers:

@@ -320,7 +320,7 @@ def fastdvdnet_denoiser_full_tensor_v2(vnoisy, sigma, y_bayer=None, Phi=None, mo
     """vnoisy [H,W,3,B] CUDA, y_bayer [h,w,4], Phi [h,w,B,4] -> outv [H,W,3,B] (or ``(outv, model)``)."""
     from .utils_image import fourCh2OneCh
     if gray:
-        raise NotImplementedError("gray FastDVDnet is SURVEY §8(f).3 (next)")
+        raise NotImplementedError("gray FastDVDnet: the 1-channel model class / model_gray.pth are absent from the reference")
     vnoisy = vnoisy.contiguous().float()
     H, W, _, B = vnoisy.shape
     v = ops.pixlast_to_planar(vnoisy, 3, B).view(B, 3, H, W)
@@ -336,3 +336,22 @@ def fastdvdnet_denoiser_full_tensor_v2(vnoisy, sigma, y_bayer=None, Phi=None, mo
         out = _unwrap(model).engine().forward(v, sigma, train=False)
     outv = ops.planar_to_pixlast(out, 3, B).view(H, W, 3, B)
     return (outv, model) if updata_ else outv
+
+
+def fastdvdnet_denoiser(vnoisy, sigma, model=None, useGPU=True, lr_=0.000001, updata_=False, gray=False):
+    """packages/fastdvdnet/test_fastdvdnet.py:149-235 - frame-wise colour adapter: numpy ``vnoisy`` [H,W,F,3] in [0,1] ->
+    numpy [H,W,F,3], whole circular sequence through ``fastdvdnet_seqdenoise``.
+
+    Not on the hot path (the solvers call ``fastdvdnet_denoiser_full_tensor_v2``); kept for API parity.
+    ``gray=True`` needs the single-channel FastDVDnet whose class and weights (``model_gray.pth``) are absent from the
+    reference tree (.MISSING_LARGE_BLOBS), and ``updata_=True`` takes one Adam step on MSE(input, output) - a loss whose
+    backward is not built here; both raise."""
+    if gray:
+        raise NotImplementedError("gray FastDVDnet: the 1-channel model class / model_gray.pth are absent from the reference")
+    if updata_:
+        raise NotImplementedError("fastdvdnet_denoiser(updata_=True) (MSE(input, output) self-loss) is not on any script's path; "
+                                  "the online adaptation of the solvers is fastdvdnet_denoiser_full_tensor_v2")
+    v = torch.from_numpy(np.ascontiguousarray(vnoisy, dtype=np.float32)).cuda()           # [H,W,F,3]
+    seq = v.permute(2, 3, 0, 1).contiguous()                                                # :215 -> [F,3,H,W]
+    out = fastdvdnet_seqdenoise(seq, torch.tensor([float(sigma)], device=seq.device), NUM_IN_FR_EXT, model)
+    return out.permute(2, 3, 0, 1).contiguous().cpu().numpy()                              # :226-230

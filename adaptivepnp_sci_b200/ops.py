@@ -99,6 +99,14 @@ def dual_update_rgb(xhat, x_rgb, w, x, b, theta, first_iter, orig=None, sse=None
          H, W, B, ptr(orig), ptr(sse), stream())
 
 
+def dual_update_stage1(xhat, x, b, theta, first_iter, orig=None, sse=None):
+    """Stage-1 deep branches: theta = clip(samples(xhat)), b -= x - theta, PSNR of x (dvp:439-512); in place."""
+    require_cuda_f32(xhat, x, b, theta, orig)
+    B, H, W = x.shape
+    call("sci_dual_update_stage1", ptr(xhat), ptr(x), ptr(b), ptr(theta), int(bool(first_iter)), H, W, B, ptr(orig), ptr(sse),
+         stream())
+
+
 def closed_form_demosaic(x, b, xhat, w, rho, tau, clip, x_rgb_out, u_out):
     """x_rgb = (rho*x3 + b3 + tau*xhat + w) / (rho*mask + tau) [clip]; u = x_rgb - w/tau  (dvp:175-182, 198)."""
     require_cuda_f32(x, b, xhat, w, x_rgb_out, u_out)
@@ -151,6 +159,18 @@ def pad_to_multiple(t, m):
         return t, H, W
     out = torch.empty(t.shape[:-2] + (Ho, Wo), dtype=torch.float32, device=t.device)
     call("sci_reflect_pad2d", ptr(t.contiguous()), ptr(out), t.numel() // (H * W), H, W, Ho, Wo, stream())
+    return out, H, W
+
+
+def replicate_pad_to_even(t):
+    """[..., H, W] -> replication-padded (right / bottom) to even H, W (network_ffdnet.py:56-59); returns (padded, H, W)."""
+    require_cuda_f32(t)
+    H, W = t.shape[-2:]
+    Ho, Wo = H + (H & 1), W + (W & 1)
+    if (Ho, Wo) == (H, W):
+        return t, H, W
+    out = torch.empty(t.shape[:-2] + (Ho, Wo), dtype=torch.float32, device=t.device)
+    call("sci_replicate_pad2d", ptr(t.contiguous()), ptr(out), t.numel() // (H * W), H, W, Ho, Wo, stream())
     return out, H, W
 
 

@@ -125,11 +125,19 @@ int sci_malvar2004(const float* x, const float* b, float c_b, const float* w, fl
 int sci_dual_update_rgb(const float* xhat, const float* x_rgb, float* w, const float* x,
                         float* b, float* theta, int first_iter, int H, int W, int B,
                         const float* orig, double* sse, void* stream);
+/* Stage-1 bookkeeping of the deep branches of admm_denoise_bayer_demosaic_pre (dvp...online.py:439-503, single dual
+ * variable): theta = clip(RGGB samples of xhat), b -= x - theta, sse[0] += sum (x - orig)^2 (PSNR of x, :507-512).
+ * first_iter != 0 reproduces the k = 0 aliasing of xall / theta_all (:375-377): x is overwritten with the unclipped samples. */
+int sci_dual_update_stage1(const float* xhat, float* x, float* b, float* theta, int first_iter, int H, int W, int B,
+                           const float* orig, double* sse, void* stream);
 
 /* Right/bottom reflect padding (torch F.pad mode='reflect') of `planes` [H][W] planes to [Ho][Wo] and the matching crop:
  * the sequence drivers pad every frame to a multiple of 4 before the network and cut the result back
  * (packages/fastdvdnet/fastdvdnet.py:119-141, packages/DDnet/DDnet_test.py:180-196). */
 int sci_reflect_pad2d(const float* in, float* out, long planes, int H, int W, int Ho, int Wo, void* stream);
+/* Right/bottom replication padding (torch.nn.ReplicationPad2d) of [planes][H][W] to [planes][Ho][Wo]: the odd-size path of
+ * KAIR-FFDNet (models/network_ffdnet.py:56-59, cropped again at :68 with sci_crop2d). */
+int sci_replicate_pad2d(const float* in, float* out, long planes, int H, int W, int Ho, int Wo, void* stream);
 int sci_crop2d(const float* in, float* out, long planes, int H, int W, int Hc, int Wc, void* stream);
 /* Closed-form demosaic update of the `close_form_demosaic` branch (dvp_linear_inv_2_stage_ADMM_tensor_online.py:112-118,
  * 175-182, 224-230), all frames in one launch:

@@ -50,9 +50,13 @@ def _final_iqa(X_orig, x_bayer_np, nmask):
 def admm_denoise_bayer_demosaic_pre(y_bayer, Phi_bayer, _lambda=1, gamma=0.01, denoiser='tv', iter_max=50,
                                     noise_estimate=True, sigma=None, x0_bayer=None, X_orig=None, model=None,
                                     show_iqa=True, trace=None, **_unused):
-    """Stage 1 (TV warm start).  Returns (x_bayer_np[H,W,B], psnr_, ssim_, psnr_all)."""
+    """Stage 1.  'tv' (the warm start the scripts use) returns (x_bayer_np[H,W,B], psnr_, ssim_, psnr_all); the deep branches
+    'ffdnet_color' / 'fastdvd_color' (:456-500, inference only: see the product's note on update_) return the 6-tuple of :552."""
+    if denoiser != 'tv' and denoiser.lower() not in ('ffdnet_color', 'fastdvd_color'):
+        raise ValueError('Unsupported denoiser {}!'.format(denoiser))
     if denoiser != 'tv':
-        raise ValueError('oracle restates only the tv branch of stage 1 (the only one the scripts reach)')
+        return _stage1_deep(y_bayer, Phi_bayer, _lambda, gamma, denoiser.lower(), iter_max, sigma, x0_bayer, X_orig, model,
+                            show_iqa)
     y_bayer = torch.from_numpy(np.ascontiguousarray(y_bayer))
     Phi_bayer = torch.from_numpy(np.ascontiguousarray(Phi_bayer))
     sigma, iter_max = _listify(sigma, iter_max)
@@ -78,6 +82,42 @@ def admm_denoise_bayer_demosaic_pre(y_bayer, Phi_bayer, _lambda=1, gamma=0.01, d
     if trace is not None:
         trace.update(theta=theta_all.clone(), b=ball.clone(), x=xall.clone())
     return x_bayer_np, psnr_, ssim_, psnr_all
+
+
+def _stage1_deep(y_bayer, Phi_bayer, _lambda, gamma, denoiser, iter_max, sigma, x0_bayer, X_orig, model, show_iqa):
+    """dvp...online.py:456-503 with update_ = False: single dual variable, PSNR of x, k = 0 aliasing of xall / theta_all."""
+    y_bayer = torch.from_numpy(np.ascontiguousarray(y_bayer))
+    Phi_bayer = torch.from_numpy(np.ascontiguousarray(Phi_bayer))
+    sigma, iter_max = _listify(sigma, iter_max)
+    nrow, ncol, nmask = Phi_bayer.shape
+    yall, Phiall, Phi_sumall, x0all = bayer_split_init(y_bayer, Phi_bayer, x0_bayer)
+    xall = x0all
+    theta_all = x0all                                                # :375-377 (same tensor)
+    ball = torch.zeros_like(x0all)
+    R_m, G_m, B_m = masks_CFA_Bayer_tensor((nrow, ncol))
+    psnr_all, xbgr3 = [], None
+    for idx, nsig in enumerate(sigma):
+        for it in range(iter_max[idx]):
+            project_stage1(theta_all, ball, yall, Phiall, Phi_sumall, _lambda, gamma, out=xall)
+            x_bayer = bayer_merge(xall - ball)
+            x_rgb = torch.zeros([nrow, ncol, 3, nmask])
+            for t in range(nmask):
+                x_rgb[:, :, :, t] = malvar2004_tensor(x_bayer[:, :, t], R_m, G_m, B_m)
+            if denoiser == 'ffdnet_color':
+                xbgr3 = ffdnet_rgb_denoise_full_tensor(x_rgb, yall, Phiall, nsig, model, True, 1e-6)
+            else:
+                xbgr3 = fastdvdnet_denoiser_full_tensor_v2(x_rgb, nsig, yall, Phiall, model, True, 1e-6)
+            theta_all[..., 0] = xbgr3[0::2, 0::2, 0, :]
+            theta_all[..., 1] = xbgr3[0::2, 1::2, 1, :]
+            theta_all[..., 2] = xbgr3[1::2, 0::2, 1, :]
+            theta_all[..., 3] = xbgr3[1::2, 1::2, 2, :]
+            theta_all = torch.clip(theta_all, 0, 1)
+            ball = ball - (xall - theta_all)
+            if show_iqa and X_orig is not None:
+                psnr_all.append(compare_psnr(X_orig, bayer_merge(xall).numpy(), data_range=1.))
+    x_bayer_np = bayer_merge(xall).numpy()
+    psnr_, ssim_ = _final_iqa(X_orig, x_bayer_np, nmask)
+    return xbgr3.detach().numpy(), x_bayer_np, psnr_, ssim_, psnr_all, model
 
 
 def twoStageAdmm_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, gamma=0.01, denoiser='tv', iter_max=50,

@@ -418,6 +418,32 @@ def loops(ns):
     np.savez_compressed(os.path.join(HERE, "loops.npz"), **out)
 
 
+def stage1_deep(ns):
+    """Deep branches of stage 1 (admm_denoise_bayer_demosaic_pre with 'ffdnet_color' / 'fastdvd_color', dvp:456-503, :552)."""
+    print("stage-1 deep branches")
+    out = {}
+    meas, mask, orig = synthetic.make_case(64, 64, 8, 3000, bayer=True)
+    warm = np.load(os.path.join(HERE, "loops.npz"))["s2_warm"]
+    for tag, den, ref_m, orc_m, sig, its in (("ffd", 'ffdnet_color', _ref_ffdnet, _orc_ffdnet, [25 / 255, 12 / 255], [3, 2]),
+                                             ("fdvd", 'fastdvd_color', _ref_fastdvd, _orc_fastdvd, [12 / 255], [4])):
+        for wtag, x0 in (("", torch.from_numpy(warm)), ("_cold", None)):
+            r = ns.dvp.admm_denoise_bayer_demosaic_pre(meas, mask, 1, 0.01, den, its, False, sig, x0_bayer=x0, X_orig=orig,
+                                                       model=ref_m(ns), show_iqa=True, logf=io.StringIO())
+            o = admm.admm_denoise_bayer_demosaic_pre(meas, mask, 1, 0.01, den, its, False, sig, x0_bayer=x0, X_orig=orig,
+                                                     model=orc_m(None) if False else (orc_m()), show_iqa=True)
+            assert len(r) == 6
+            _eq(r[0], o[0], "stage1 %s%s xbgr3" % (den, wtag))
+            _eq(r[1], o[1], "stage1 %s%s x_bayer" % (den, wtag))
+            _eq(np.array(r[4]), np.array(o[4]), "stage1 %s%s psnr_all" % (den, wtag))
+            out.update({"%s%s_rgb" % (tag, wtag): r[0], "%s%s_x" % (tag, wtag): r[1], "%s%s_psnr_all" % (tag, wtag): np.array(r[4]),
+                        "%s%s_psnr" % (tag, wtag): np.array(r[2])})
+    np.savez_compressed(os.path.join(HERE, "stage1_deep.npz"), **out)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "stage1_deep":
+    stage1_deep(ref_harness.load())
+    sys.exit(0)
+
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "ddnet":
     ddnet_(ref_harness.load())        # regenerate only tests/golden/ddnet.npz (needs loops.npz)
     sys.exit(0)
@@ -437,4 +463,5 @@ if __name__ == "__main__":
     loops(ns)
     ddnet_(ns)
     closed_form(ns)
+    stage1_deep(ns)
     print("golden vectors written to", HERE)

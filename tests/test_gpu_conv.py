@@ -176,6 +176,9 @@ def test_networks_vs_golden(cuda, impl):
     m = _ffdnet(cuda)
     y = m(torch.from_numpy(d["ffd_x"]).cuda(), torch.full((2, 1, 1, 1), 25 / 255).cuda())
     assert _rel(y.cpu(), d["ffd_y"]) < tol
+    # odd size (23x37): replication pad to even, crop (models/network_ffdnet.py:56-59, :68)
+    yo = m(torch.from_numpy(d["ffd_xo"]).cuda(), torch.full((1, 1, 1, 1), 25 / 255).cuda())
+    assert tuple(yo.shape) == d["ffd_yo"].shape and _rel(yo.cpu(), d["ffd_yo"]) < tol
     f = _fastdvd(cuda)
     y5 = f(torch.from_numpy(d["fdvd_x"]).cuda(), torch.full((1, 1, 32, 48), 12 / 255).cuda())
     assert _rel(y5.cpu(), d["fdvd_y"]) < tol

@@ -134,3 +134,22 @@ def test_sequence_drivers_reflect_pad_to_multiple_of_4(cuda, impl):
     got = fastdvdnet_adapter.fastdvdnet_seqdenoise(seq.cuda(), torch.tensor([12 / 255]).cuda(), 5, _fastdvd(cuda))
     assert got.shape == (6, 3, 30, 46)
     assert float((got.cpu() - want).abs().max()) < TOL[impl] * 5
+
+
+def test_fastdvdnet_framewise_adapter(cuda):
+    """fastdvdnet_denoiser (test_fastdvdnet.py:149-235, colour, inference): numpy [H,W,F,3] in / out, equals the sequence driver."""
+    from adaptivepnp_sci_b200.fastdvdnet_adapter import DataParallelLike, fastdvdnet_denoiser, fastdvdnet_seqdenoise
+    from adaptivepnp_sci_b200.fastdvdnet_models import FastDVDnet
+    from oracle import adapters, networks, synthetic
+    sd = {"module." + k: v for k, v in synthetic.fastdvdnet_synthetic_state_dict().items()}
+    m = DataParallelLike(FastDVDnet()); m.load_state_dict(sd, strict=True); m = m.eval().cuda()
+    g = torch.Generator().manual_seed(3)
+    v = torch.rand(30, 46, 6, 3, generator=g).numpy()                       # 30x46: exercises the reflect pad to x4
+    out = fastdvdnet_denoiser(v, 12 / 255, m)
+    assert out.shape == v.shape and out.dtype == np.float32
+    mo = networks.Wrapped(networks.FastDVDnet()); mo.load_state_dict(sd, strict=True); mo.eval()
+    with torch.no_grad():
+        ref = adapters.fastdvdnet_seqdenoise(torch.from_numpy(v).permute(2, 3, 0, 1), torch.FloatTensor([12 / 255]), 5, mo)
+    assert np.max(np.abs(out - ref.permute(2, 3, 0, 1).numpy())) < 1e-3
+    with pytest.raises(NotImplementedError):
+        fastdvdnet_denoiser(v[..., 0], 12 / 255, m, gray=True)

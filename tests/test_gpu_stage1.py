@@ -98,3 +98,44 @@ def test_tv_kernel_generations_agree(cuda, shape, monkeypatch):
         outs[v] = (theta.cpu(), b_out.cpu(), nstop.cpu())
     assert torch.equal(outs["0"][2], outs["1"][2])
     assert torch.equal(outs["0"][0], outs["1"][0]) and torch.equal(outs["0"][1], outs["1"][1])
+
+
+@pytest.mark.parametrize("impl", ["ref", "tc"])
+def test_stage1_deep_branches_vs_golden(cuda, impl, monkeypatch):
+    """Deep branches of admm_denoise_bayer_demosaic_pre ('ffdnet_color' / 'fastdvd_color', dvp...online.py:456-503, :552)
+    against the reference's own outputs: warm-started and from x0 = At(y), both conv engines."""
+    monkeypatch.setenv("SCI_CONV_IMPL", impl)
+    from adaptivepnp_sci_b200.dvp_linear_inv_2_stage_ADMM_tensor_online import admm_denoise_bayer_demosaic_pre, np2tch_cuda
+    from adaptivepnp_sci_b200.fastdvdnet_adapter import DataParallelLike
+    from adaptivepnp_sci_b200.fastdvdnet_models import FastDVDnet
+    from adaptivepnp_sci_b200.network_ffdnet import FFDNet
+    from oracle import synthetic
+    d = np.load(os.path.join(G, "stage1_deep.npz"))
+    warm = np.load(os.path.join(G, "loops.npz"))["s2_warm"]
+    meas, mask, orig = synthetic.make_case(64, 64, 8, 3000, bayer=True)
+
+    def ffd():
+        m = FFDNet(3, 3, 96, 12, 'R')
+        m.load_state_dict(torch.load(os.path.join(ROOT, "model_zoo", "ffdnet_color.pth")), strict=True)
+        return m.eval().cuda()
+
+    def fdvd():
+        m = DataParallelLike(FastDVDnet())
+        m.load_state_dict({"module." + k: v for k, v in synthetic.fastdvdnet_synthetic_state_dict().items()}, strict=True)
+        return m.eval().cuda()
+    tol = {"ref": 2e-4, "tc": 1e-3}[impl]
+    for tag, den, mk, sig, its in (("ffd", 'ffdnet_color', ffd, [25 / 255, 12 / 255], [3, 2]),
+                                   ("fdvd", 'fastdvd_color', fdvd, [12 / 255], [4])):
+        for wtag in ("", "_cold"):
+            m = mk()
+            r = admm_denoise_bayer_demosaic_pre(meas, mask, 1, 0.01, den, its, False, sig,
+                                                x0_bayer=None if wtag else np2tch_cuda(warm), X_orig=orig, model=m,
+                                                show_iqa=True, logf=io.StringIO())
+            assert len(r) == 6 and r[5] is m and r[0].shape == (64, 64, 3, 8) and r[1].shape == (64, 64, 8)
+            assert np.max(np.abs(r[0] - d[tag + wtag + "_rgb"])) < tol and np.max(np.abs(r[1] - d[tag + wtag + "_x"])) < tol
+            assert np.max(np.abs(np.array(r[4]) - d[tag + wtag + "_psnr_all"])) < 0.05
+            assert np.max(np.abs(np.array(r[2]) - d[tag + wtag + "_psnr"])) < 0.05
+    with pytest.raises(NotImplementedError):
+        admm_denoise_bayer_demosaic_pre(meas, mask, 1, 0.01, 'ffdnet_color', [3], False, [25 / 255], model=ffd(), update_=True)
+    with pytest.raises(ValueError):
+        admm_denoise_bayer_demosaic_pre(meas, mask, 1, 0.01, 'PPP', [3], False, [25 / 255])
