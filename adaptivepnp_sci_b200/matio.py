@@ -3,9 +3,10 @@
 The reference reads MATLAB v7.3 datasets with h5py (ADMM_TV_Warm_Start_save.py:69-74) and hands the warm start
 to stage 2 through ``results/savedmat/_Admm_tv_<name>8.mat`` (key ``v_Admm_tv_denoise``, [H,W,B*nmea] float32;
 :174-178 <-> two_stage_ADMM_Online_FFD_Warm.py:171-176).  The hand-off file is written/read with scipy.io exactly
-as in the reference.  Dataset files are read with h5py when it is installed; no dataset ships with the
-reference (readme.md:22-23), so the scripts fall back to the deterministic synthetic videos of ``synthetic.py``
-when ``dataset/cacti/mid_scale/<name>.mat`` is absent (``--synthetic`` forces it)."""
+as in the reference.  Dataset files (MATLAB -v7.3 = HDF5) are read with h5py when it is installed and with the package's
+own minimal HDF5 reader (``h5lite.py``) otherwise; no dataset ships with the reference (readme.md:22-23), so the scripts
+fall back to the deterministic synthetic videos of ``synthetic.py`` when ``dataset/cacti/mid_scale/<name>.mat`` is absent
+(``--synthetic`` forces it)."""
 import os
 
 import numpy as np
@@ -32,15 +33,20 @@ def load_video(datasetdir, datname, nmea=4, synthetic_shape=(512, 512, 8), force
     result files; the synthetic videos have no RGB ground truth on file, their Bayer ground truth stands in]."""
     path = os.path.join(datasetdir, datname + '.mat')
     if not force_synthetic and os.path.exists(path):
+        # MATLAB -v7.3 = HDF5 (ADMM_TV_Warm_Start_save.py:69-74 reads it with h5py).  h5py when it is installed, otherwise
+        # the package's own reader of the HDF5 subset such files use (h5lite.py): same arrays, same (C-order) shapes
         try:
             import h5py
-        except ImportError as e:
-            raise ImportError("reading the MATLAB v7.3 dataset %s needs h5py, which is not installed" % path) from e
-        with h5py.File(path, 'r') as f:
-            meas = np.float32(np.array(f['meas_bayer']))
-            mask = np.float32(np.array(f['mask_bayer'])).transpose((2, 1, 0))
-            orig = np.float32(np.array(f['orig_bayer'])).transpose((2, 1, 0))
-            orig_real = np.array(f['orig']) if 'orig' in f else orig
+            f = h5py.File(path, 'r')
+        except ImportError:
+            from . import h5lite
+            f = h5lite.File(path)
+        meas = np.float32(np.array(f['meas_bayer']))
+        mask = np.float32(np.array(f['mask_bayer'])).transpose((2, 1, 0))
+        orig = np.float32(np.array(f['orig_bayer'])).transpose((2, 1, 0))
+        orig_real = np.array(f['orig']) if 'orig' in f else orig
+        if hasattr(f, "close"):
+            f.close()
         meas = meas.transpose((1, 0))[:, :, None] if meas.ndim < 3 else meas.transpose((2, 1, 0))
         return (meas, mask, orig, orig_real) if with_orig_real else (meas, mask, orig)
     H, W, B = synthetic_shape
