@@ -60,6 +60,7 @@ PROTOTYPES = {
     "sci_conv_pack_weights": [_p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _i, _p],
     "sci_conv_pack_weights_s2t": [_p, _p, _i, _i, _i, _i, _p, _i, _p],
     "sci_conv_pack_weights_half": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
+    "sci_layer_ops_batch": [_p, _i, _i, _p],
     "sci_p2p_alloc": [_sz, _p],
     "sci_p2p_free": [_p],
     "sci_p2p_get_handle": [_p, _p],

@@ -452,6 +452,127 @@ __global__ void __launch_bounds__(256) fastdvd_pack_half_kernel(const float* __r
     }
 }
 
+// ---- batched per-layer bookkeeping ------------------------------------------------------------------------------------
+// A fine-tune step used to issue ~250 launches of 3-4 us each (weight (re)packing, BatchNorm folding, gradient unpacking,
+// BatchNorm parameter gradients: one launch per layer and kind).  The engine now keeps a device-side table of these
+// operations (pointers are stable: parameters live in one flat bucket) and runs a whole phase as ONE launch:
+// blockIdx.y selects the table entry, blockIdx.x the 256-element slice of it.
+__device__ __forceinline__ void layer_op_element(const sci_layer_op& d, long idx) {
+    switch (d.kind) {
+    case 0: {   // pack_weights (forward or transposed / flipped data-gradient form), see pack_weights_kernel
+        const long total = (long)9 * d.Co_pad * d.Ci_pad;
+        if (idx >= total) return;
+        const float* w = static_cast<const float*>(d.a);
+        const float* oscale = static_cast<const float*>(d.b);
+        float* packed = static_cast<float*>(d.o0);
+        int tap, col, ci;
+        if (!d.tflip) { ci = (int)(idx % d.Ci_pad); col = (int)((idx / d.Ci_pad) % d.Co_pad); tap = (int)(idx / ((long)d.Ci_pad * d.Co_pad)); }
+        else          { col = (int)(idx % d.Co_pad); ci = (int)((idx / d.Co_pad) % d.Ci_pad); tap = (int)(idx / ((long)d.Ci_pad * d.Co_pad)); }
+        float v = 0.f;
+        if (d.ci_dup > 0 && ci >= d.ci_dup && ci < d.ci_dup + d.Ci) ci -= d.ci_dup;
+        const int q = d.Co_pad >> 2;
+        const int co = d.ps ? (col % q) * 4 + col / q : col;
+        if ((d.ps ? (col % q) < (d.Co >> 2) : col < d.Co) && ci < d.Ci) {
+            const int cig = d.Ci / d.groups, cog = d.Co / d.groups, g = co / cog;
+            if (ci / cig == g) {
+                v = w[((long)co * cig + (ci - g * cig)) * 9 + (d.tflip ? 8 - tap : tap)];
+                if (d.tflip && oscale) v = v * oscale[col];
+            }
+        }
+        if (d.round_tf32 == 2) {
+            const float hi = rna_tf32(v);
+            packed[idx] = hi;
+            packed[idx + total] = rna_tf32(v - hi);
+            return;
+        }
+        packed[idx] = d.round_tf32 ? rna_tf32(v) : v;
+        return;
+    }
+    case 1: {   // pack_weights_s2t
+        const long total = (long)9 * 4 * d.Ci_pad * d.Co_pad;
+        if (idx >= total) return;
+        const float* w = static_cast<const float*>(d.a);
+        const float* oscale = static_cast<const float*>(d.b);
+        const int co = (int)(idx % d.Co_pad);
+        const int col = (int)((idx / d.Co_pad) % (4 * d.Ci_pad));
+        const int tap = (int)(idx / ((long)d.Co_pad * 4 * d.Ci_pad));
+        const int q = col / d.Ci_pad, ci = col % d.Ci_pad;
+        const int kh = s2t_src_tap(q >> 1, tap / 3 - 1), kw = s2t_src_tap(q & 1, tap % 3 - 1);
+        float v = 0.f;
+        if (co < d.Co && ci < d.Ci && kh >= 0 && kw >= 0) {
+            v = w[((long)co * d.Ci + ci) * 9 + kh * 3 + kw];
+            if (oscale) v = v * oscale[co];
+        }
+        static_cast<float*>(d.o0)[idx] = d.round_tf32 ? rna_tf32(v) : v;
+        return;
+    }
+    case 2: {   // pack_weights_half
+        const long total = (long)9 * d.Co_pad * d.Ci_pad;
+        if (idx >= total) return;
+        const float* w = static_cast<const float*>(d.a);
+        int ci = (int)(idx % d.Ci_pad);
+        const int col = (int)((idx / d.Ci_pad) % d.Co_pad), tap = (int)(idx / ((long)d.Ci_pad * d.Co_pad));
+        float v = 0.f;
+        if (d.ci_dup > 0 && ci >= d.ci_dup && ci < d.ci_dup + d.Ci) ci -= d.ci_dup;
+        const int q = d.Co_pad >> 2;
+        const int co = d.ps ? (col % q) * 4 + col / q : col;
+        if ((d.ps ? (col % q) < (d.Co >> 2) : col < d.Co) && ci < d.Ci) {
+            const int cig = d.Ci / d.groups, cog = d.Co / d.groups, g = co / cog;
+            if (ci / cig == g) v = w[((long)co * cig + (ci - g * cig)) * 9 + tap];
+        }
+        static_cast<__half*>(d.o0)[idx] = __float2half_rn(v);
+        return;
+    }
+    case 3: {   // unpack_wgrad
+        const int cig = d.Ci / d.groups, cog = d.Co / d.groups;
+        if (idx >= (long)d.Co * cig * 9) return;
+        const float* packed = static_cast<const float*>(d.a);
+        const int tap = (int)(idx % 9), cil = (int)((idx / 9) % cig), co = (int)(idx / (9L * cig));
+        const int ci = (co / cog) * cig + cil;
+        const int col = out_column(co, d.Co_pad, d.ps);
+        float g = packed[((long)tap * d.Co_pad + col) * d.Ci_pad + ci];
+        if (d.ci_dup > 0) g += packed[((long)tap * d.Co_pad + col) * d.Ci_pad + ci + d.ci_dup];
+        static_cast<float*>(d.o0)[idx] = g;
+        return;
+    }
+    case 4: {   // bn_fold: a gamma, b beta, c mean, d var -> o0 scale, o1 shift (Co real of Co_pad columns)
+        if (idx >= d.Co_pad) return;
+        float sc = 0.f, sh = 0.f;
+        if (idx < d.Co) {
+            sc = static_cast<const float*>(d.a)[idx] / sqrtf(static_cast<const float*>(d.d)[idx] + d.eps);
+            sh = static_cast<const float*>(d.b)[idx] - static_cast<const float*>(d.c)[idx] * sc;
+        }
+        static_cast<float*>(d.o0)[idx] = sc;
+        static_cast<float*>(d.o1)[idx] = sh;
+        return;
+    }
+    case 5: {   // bn_param_grad: a s1, b s2, c gamma, d beta -> o0 dgamma, o1 dbeta
+        if (idx >= d.Co) return;
+        const float s1 = static_cast<const float*>(d.a)[idx], g = static_cast<const float*>(d.c)[idx];
+        static_cast<float*>(d.o1)[idx] = s1;
+        static_cast<float*>(d.o0)[idx] = (g != 0.f) ? (static_cast<const float*>(d.b)[idx] - static_cast<const float*>(d.d)[idx] * s1) / g : 0.f;
+        return;
+    }
+    case 6:     // copy Co floats (bias -> shift column vector, column sums -> bias gradient)
+        if (idx < d.Co) static_cast<float*>(d.o0)[idx] = static_cast<const float*>(d.a)[idx];
+        return;
+    default:
+        return;
+    }
+}
+
+__global__ void __launch_bounds__(256) layer_ops_batch_kernel(const sci_layer_op* __restrict__ table) {
+    const sci_layer_op d = table[blockIdx.y];
+    layer_op_element(d, (long)blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+extern "C" int sci_layer_ops_batch(const sci_layer_op* table_device, int n_ops, int max_blocks, void* stream) {
+    SCI_REQUIRE(table_device && n_ops > 0 && n_ops <= 65535 && max_blocks > 0, "layer_ops_batch");
+    layer_ops_batch_kernel<<<dim3(max_blocks, n_ops), 256, 0, sci_stream(stream)>>>(table_device);
+    SCI_CHECK_LAUNCH("layer_ops_batch");
+    return SCI_OK;
+}
+
 extern "C" int sci_conv_pack_weights(const float* w, float* packed, int Co, int Ci, int groups, int Co_pad, int Ci_pad,
                                      int ps, const float* oscale, int transpose_flip, int round_tf32, int ci_dup,
                                      void* stream) {

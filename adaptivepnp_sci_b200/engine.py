@@ -44,6 +44,43 @@ class WgradDesc(ctypes.Structure):
                 ("Cout", ctypes.c_int), ("stride", ctypes.c_int)]
 
 
+class LayerOp(ctypes.Structure):
+    """sci_layer_op (include/sci_b200.h): one entry of a batched bookkeeping launch."""
+    _fields_ = [("kind", ctypes.c_int), ("Co", ctypes.c_int), ("Ci", ctypes.c_int), ("groups", ctypes.c_int),
+                ("Co_pad", ctypes.c_int), ("Ci_pad", ctypes.c_int), ("ps", ctypes.c_int), ("tflip", ctypes.c_int),
+                ("round_tf32", ctypes.c_int), ("ci_dup", ctypes.c_int), ("eps", ctypes.c_float),
+                ("a", _f32p), ("b", _f32p), ("c", _f32p), ("d", _f32p), ("o0", _f32p), ("o1", _f32p)]
+
+    def elements(self):
+        k = self.kind
+        if k in (0, 2):
+            return 9 * self.Co_pad * self.Ci_pad
+        if k == 1:
+            return 9 * 4 * self.Ci_pad * self.Co_pad
+        if k == 3:
+            return self.Co * (self.Ci // self.groups) * 9
+        return self.Co_pad if k == 4 else self.Co
+
+
+def _op(kind, Co=0, Ci=1, groups=1, Co_pad=0, Ci_pad=0, ps=0, tflip=0, round_tf32=0, ci_dup=0, eps=0.0, a=None, b=None, c=None,
+        d=None, o0=None, o1=None):
+    return LayerOp(kind, Co, Ci, groups, Co_pad, Ci_pad, int(ps), int(tflip), int(round_tf32), ci_dup, eps,
+                   _dp(a), _dp(b), _dp(c), _dp(d), _dp(o0), _dp(o1))
+
+
+class OpTable:
+    """Device-resident table of LayerOps run as ONE launch (``sci_layer_ops_batch``)."""
+
+    def __init__(self, ops, device):
+        self.n = len(ops)
+        arr = (LayerOp * self.n)(*ops)
+        self.dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
+        self.max_blocks = max((op.elements() + 255) // 256 for op in ops)
+
+    def run(self):
+        call("sci_layer_ops_batch", ptr(self.dev), self.n, self.max_blocks, stream())
+
+
 IMPL_TC, IMPL_REF = 0, 1
 
 
@@ -151,6 +188,45 @@ class ConvLayer:
         call("sci_conv_pack_weights", ptr(c.weight.data), ptr(self.wpk), self.Co, self.Ci, self.groups, self.Co_pad,
              self.Ci_pad, int(self.ps), None, 0, (2 if (tf32 and self.wsplit) else int(tf32)), self.ci_dup, stream())
 
+    # ---- the same work as table entries of a batched launch (engine: one launch per phase instead of one per layer) ----
+    def fwd_ops(self, tf32):
+        c = self.conv
+        ops = []
+        if self.bn is not None:
+            bn = self.bn
+            ops.append(_op(4, Co=self.Co, Co_pad=self.Co_pad, eps=float(bn.eps), a=bn.weight.data, b=bn.bias.data,
+                           c=bn.running_mean, d=bn.running_var, o0=self.scale, o1=self.shift))
+        elif c.bias is not None:
+            ops.append(_op(6, Co=self.Co, a=c.bias.data, o0=self.shift))
+        self.ci_dup = self.ci_half if self.dup_in else (16 if (self.first and tf32) else 0)
+        ops.append(_op(0, self.Co, self.Ci, self.groups, self.Co_pad, self.Ci_pad, self.ps, 0,
+                       (2 if (tf32 and self.wsplit) else int(tf32)), self.ci_dup, a=c.weight.data, o0=self.wpk))
+        return ops
+
+    def bwd_ops(self, tf32, s1, s2):
+        """Allocates the data-gradient weights; s1 / s2 are this layer's slices of the engine's flat column-sum buffer."""
+        dev = self.wpk.device
+        self.s1, self.s2 = s1, s2
+        self.s2t = bool(self.stride == 2 and self.groups == 1 and not self.ps and self.ci_dup == 0)
+        n = (36 if self.s2t else 9) * self.Co_pad * self.Ci_pad
+        if self.wpk_t is None or self.wpk_t.numel() != n:
+            self.wpk_t = torch.empty(n, dtype=torch.float32, device=dev)
+        if self.s2t:
+            return [_op(1, Co=self.Co, Ci=self.Ci, Co_pad=self.Co_pad, Ci_pad=self.Ci_pad, round_tf32=int(tf32),
+                        a=self.conv.weight.data, b=self.scale, o0=self.wpk_t)]
+        return [_op(0, self.Co, self.Ci, self.groups, self.Co_pad, self.Ci_pad, self.ps, 1, int(tf32), self.ci_dup,
+                    a=self.conv.weight.data, b=self.scale, o0=self.wpk_t)]
+
+    def grad_ops(self, bucket):
+        ops = [_op(3, self.Co, self.Ci, self.groups, self.Co_pad, self.Ci_pad, self.ps, ci_dup=self.ci_dup, a=self.dwpk,
+                   o0=bucket.grad_view(self.conv.weight))]
+        if self.bn is not None:
+            ops.append(_op(5, Co=self.Co, a=self.s1, b=self.s2, c=self.bn.weight.data, d=self.bn.bias.data,
+                           o0=bucket.grad_view(self.bn.weight), o1=bucket.grad_view(self.bn.bias)))
+        elif self.conv.bias is not None:
+            ops.append(_op(6, Co=self.Co, a=self.s1, o0=bucket.grad_view(self.conv.bias)))
+        return ops
+
     def refresh_bwd(self, tf32):
         """Data-gradient form of the weights: transposed, taps flipped, rows scaled by the folded BN scale."""
         if self.wpk_t is None:
@@ -191,6 +267,10 @@ class HalfLayer:
         call("sci_conv_pack_weights_half", ptr(c.weight.data), ptr(self.wpk), self.base.Co, self.base.Ci, self.base.groups,
              self.N, self.K, int(self.ps), self.ci_dup, stream())
 
+    def fwd_ops(self, tf32):
+        b = self.base
+        return [_op(2, b.Co, b.Ci, b.groups, self.N, self.K, self.ps, ci_dup=self.ci_dup, a=b.conv.weight.data, o0=self.wpk)]
+
 
 class _Workspace:
     """Named, shape-keyed device buffers that live as long as the engine (no allocation in steady state)."""
@@ -223,6 +303,9 @@ class _EngineBase:
         self._bwd_valid = False
         self.dirty = True
         self.n_launch = 0
+        self.batch = os.environ.get("SCI_BATCH_OPS", "1") != "0"
+        self._tables = None
+        self.s12_flat = None
         self.pdl_chain = False   # True inside an inference chain: weights are packed, consecutive convs may overlap (PDL)
         self.profile = None      # set to a list to record (start_event, end_event, algorithmic_flops, tag) per conv launch
 
@@ -238,16 +321,17 @@ class _EngineBase:
         if self.bucket is None or not self.bucket.intact():
             self.bucket = ParamBucket(list(self.module.parameters()))
             self.dirty = True
+        if self._tables is not None and self._tables["bucket"] is not self.bucket:
+            self._tables = None                                       # new parameter storage: every table entry points at the old one
         if self.dirty or self._version() != self._seen_version:
-            for L in self.layers + (getattr(self, "layers_inf", None) or []):
-                L.refresh_fwd(self.tf32)
+            if self.batch:
+                self._table("fwd").run()
+            else:
+                for L in self.layers + (getattr(self, "layers_inf", None) or []):
+                    L.refresh_fwd(self.tf32)
             self._seen_version = self._version()
             self._bwd_valid = False
             self.dirty = False
-        if training and not self._bwd_valid:
-            for L in self.layers:
-                L.refresh_bwd(self.tf32)
-            self._bwd_valid = True
         if training and self.layers[0].dwpk is None:
             sizes = [9 * L.Co_pad * L.Ci_pad for L in self.layers]
             self.dw_flat = torch.zeros(sum(sizes), dtype=torch.float32, device=self.layers[0].wpk.device)
@@ -255,6 +339,48 @@ class _EngineBase:
             for L, n in zip(self.layers, sizes):
                 L.dwpk = self.dw_flat[off:off + n]
                 off += n
+        if training and not self._bwd_valid:
+            if self.batch:
+                self._table("bwd").run()
+            else:
+                for L in self.layers:
+                    L.refresh_bwd(self.tf32)
+            self._bwd_valid = True
+
+    def _table(self, which):
+        """Batched bookkeeping (SCI_BATCH_OPS=0 restores one launch per layer): 'fwd' = BatchNorm folding / bias + weight
+        packing of every layer (+ the fp16 / split inference forms), 'bwd' = data-gradient weight forms, 'grads' = packed
+        weight gradients -> parameter gradients + BatchNorm / bias gradients from the column sums."""
+        if self._tables is None:
+            self._tables = {"bucket": self.bucket}
+        t = self._tables.get(which)
+        if t is None:
+            dev = self.layers[0].wpk.device
+            if which == "fwd":
+                ops = [op for L in self.layers + (getattr(self, "layers_inf", None) or []) for op in L.fwd_ops(self.tf32)]
+            elif which == "bwd":
+                if self.s12_flat is None:
+                    self.s12_flat = torch.zeros(2 * sum(L.Co_pad for L in self.layers), dtype=torch.float32, device=dev)
+                ops, off = [], 0
+                for L in self.layers:
+                    ops += L.bwd_ops(self.tf32, self.s12_flat[off:off + L.Co_pad], self.s12_flat[off + L.Co_pad:off + 2 * L.Co_pad])
+                    off += 2 * L.Co_pad
+            else:
+                ops = [op for L in self.layers for op in L.grad_ops(self.bucket)]
+            t = self._tables[which] = OpTable(ops, dev)
+        return t
+
+    def begin_backward(self):
+        """Zero the packed weight-gradient accumulators and the per-column sums (one memset each)."""
+        self.dw_flat.zero_()
+        if self.batch:
+            self.s12_flat.zero_()
+
+    def finish_param_grads(self):
+        """Batched mode: all parameter gradients in one launch at the end of the backward pass."""
+        if self.batch:
+            self._table("grads").run()
+            self.n_launch += 1
 
     # ---- kernel wrappers ------------------------------------------------------------------------------
     def conv(self, L, x, N, H, W, y, residual=None, round_out=True, emit_lo=False, planar=None):
@@ -315,7 +441,7 @@ class _EngineBase:
         need = L.has_affine
         if not (L.relu or need):
             return dy
-        if need:
+        if need and not self.batch:
             L.s1.zero_()
             L.s2.zero_()
         call("sci_act_bwd", ptr(dy), ptr(y) if (L.relu or L.bn is not None) else None, ptr(dy), n_pix, C, int(L.relu),
@@ -325,6 +451,8 @@ class _EngineBase:
 
     def param_grads(self, L):
         """packed dW -> torch-layout grad slot; bias / BatchNorm affine grads from the column sums."""
+        if self.batch:
+            return                                   # done for all layers at once by finish_param_grads()
         b = self.bucket
         call("sci_conv_unpack_wgrad", ptr(L.dwpk), ptr(b.grad_view(L.conv.weight)), L.Co, L.Ci, L.groups, L.Co_pad,
              L.Ci_pad, int(L.ps), L.ci_dup, stream())
@@ -412,7 +540,7 @@ class FFDNetEngine(_EngineBase):
         dev = dxhat.device
         h2, w2 = H // 2, W // 2
         n_pix = B * h2 * w2
-        self.dw_flat.zero_()
+        self.begin_backward()
         Lt = self.layers[-1]
         dy = self.ws.get("g_tail", (B, h2, w2, Lt.Co_pad), dev)
         call("sci_ffdnet_unpack_output_grad", ptr(dxhat), ptr(dy), B, self.out_nc, H, W, Lt.Co_pad, stream())
@@ -425,6 +553,7 @@ class FFDNetEngine(_EngineBase):
                 self.dgrad(L, dz, B, h2, w2, dx)
                 dy = dx
             self.param_grads(L)
+        self.finish_param_grads()
 
     def forward_nchw(self, x, sigma):
         """Reference call convention model(img[N,3,H,W], sigma[N,1,1,1]) (test_ffdnet_ipol.py:350-351)."""
@@ -659,13 +788,14 @@ class FastDVDnetEngine(_EngineBase):
         """Parameter gradients of both DenBlocks given d loss / d output [B,3,H,W]."""
         s1, s2, B, H, W = self._saved
         dev = dout.device
-        self.dw_flat.zero_()
+        self.begin_backward()
         d_in2 = self._block_backward(self.t2, s2, dout, B, H, W, need_input_grad=True)
         # temp1 output j feeds slot (j - f + 1) of temp2 block f = j-1, j, j+1, and is `in1` of block j
         d_t1 = self.ws.get("g_t1", (B, 3, H, W), dev)
         d_t1.copy_(dout)
         call("sci_fastdvd_pack_input_grad", ptr(d_in2), ptr(d_t1), B, H, W, self.t2.L[0].Ci_pad, 1, stream())
         self._block_backward(self.t1, s1, d_t1, B, H, W, need_input_grad=False)
+        self.finish_param_grads()
 
     def forward_window(self, x, noise_map):
         """Reference call convention model(x[1,15,H,W], noise_map[1,1,H,W]) for ONE 5-frame window
@@ -842,7 +972,7 @@ class DDnetEngine(_EngineBase):
         gv = self.bucket.grad_view
         da, da2, da3 = gv(m.weight_tensor_in), gv(m.weight_tensor_in2), gv(m.weight_tensor_out)
         da.zero_(); da2.zero_(); da3.zero_()
-        self.dw_flat.zero_()
+        self.begin_backward()
         # output mix and the two residual adds of temp2
         d_xo2 = g("ddg_xo2", (2 * B, H, W, 32), dev)
         d_res1, d_res2 = g("ddg_res1", (B, 3, H, W), dev), g("ddg_res2", (B, 3, H, W), dev)
@@ -864,6 +994,7 @@ class DDnetEngine(_EngineBase):
         call("sci_ddnet_pack_input4_bwd", ptr(d_y4), ptr(mosaic), ptr(da2), B, H, W, 1, stream())
         d_in4 = self._body_backward(self.t11, sv["S4"], d_y4, 3 * B, H // 2, W // 2, True, "t11")
         call("sci_ddnet_pack_input4_bwd", ptr(d_in4), ptr(mosaic), ptr(da2), B, H, W, 0, stream())
+        self.finish_param_grads()
         self.n_launch += 8
 
     def forward_window(self, x):

@@ -270,6 +270,21 @@ int sci_conv_pack_weights_s2t(const float* w, float* packed, int Co, int Ci, int
 int sci_conv_unpack_wgrad(const float* packed_dw, float* dw, int Co, int Ci, int groups, int Co_pad, int Ci_pad,
                           int ps, int ci_dup, void* stream);
 
+/* Batched per-layer bookkeeping: one launch runs a whole TABLE of the small operations above / below (device-resident array
+ * of n_ops entries; blockIdx.y = entry, max_blocks = ceil(largest element count / 256)).  kind: 0 sci_conv_pack_weights
+ * (a = w, b = oscale, o0 = packed; tflip / round_tf32 / ci_dup as there), 1 sci_conv_pack_weights_s2t, 2
+ * sci_conv_pack_weights_half, 3 sci_conv_unpack_wgrad (a = packed_dw, o0 = dw), 4 sci_bn_fold (a gamma, b beta, c mean,
+ * d var, eps -> o0 scale, o1 shift; C = Co, C_pad = Co_pad), 5 sci_bn_param_grad (a s1, b s2, c gamma, d beta -> o0 dgamma,
+ * o1 dbeta), 6 copy of Co floats a -> o0.  Entries of one table must not depend on each other. */
+typedef struct sci_layer_op {
+    int kind;
+    int Co, Ci, groups, Co_pad, Ci_pad, ps, tflip, round_tf32, ci_dup;
+    float eps;
+    const void *a, *b, *c, *d;
+    void *o0, *o1;
+} sci_layer_op;
+int sci_layer_ops_batch(const sci_layer_op* table_device, int n_ops, int max_blocks, void* stream);
+
 /* BatchNorm (eval mode, packages/fastdvdnet/models.py:21-26) folded to per-column scale/shift:
  * scale = gamma*rsqrt(var+eps), shift = beta - mean*scale; columns >= C are zeroed up to C_pad. */
 int sci_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps,

@@ -120,7 +120,7 @@ def test_conv_layer_fwd_bwd(cuda, impl, case):
         # the dgrad / wgrad kernels (the end-to-end fine-tune tests cover the real mask)
         ystore = torch.zeros(N, oh, ow, och, device=cuda)
         ystore[..., :cout_valid] = yref.detach().permute(0, 2, 3, 1).to(cuda)
-    eng.dw_flat.zero_()
+    eng.begin_backward()                               # zero the packed-gradient accumulators and the column sums
     dz = eng.act_bwd(L, dyd, ystore, N * Ho * Wo, L.Co_pad)
     eng.wgrad(L, xd, dz, N, H, W)
     dx = torch.empty(N, H, W, L.Ci_pad, device=cuda)
@@ -142,6 +142,7 @@ def test_conv_layer_fwd_bwd(cuda, impl, case):
     else:
         eng.dgrad(L, dz, N, Ho, Wo, dx)
     eng.param_grads(L)
+    eng.finish_param_grads()                           # batched mode: unpack / BatchNorm / bias gradients of all layers in one launch
     btol = tol * 3
     errs = dict(dx=_rel(dx[..., :Ci].permute(0, 3, 1, 2).cpu(), xr.grad),
                 dw=_rel(eng.bucket.grad_view(cconv.weight).cpu(), conv.weight.grad))
