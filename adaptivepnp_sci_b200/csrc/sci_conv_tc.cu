@@ -397,6 +397,9 @@ struct Fwd2Params {
     // (64, or 32 when the layer / its PixelShuffle sub-pixel group has 32 real channels) -> ONE 64-channel fp16 pixel row of
     // the stored tensor (the missing half is written as zeros); Cstore = channels per pixel of the stored output tensor
     int ucols, Cstore;
+    // MODE 4 (data gradient + activation backward of the layer that PRODUCED this tensor, fused): dz = (conv [+ residual]) *
+    // (mask_y > 0); col_s1[c] += sum dz, col_s2[c] += sum dz * mask_y  (bias / BatchNorm gradients), see the epilogue
+    const float* mask_y; float* col_s1; float* col_s2; int mask_relu;
 };
 
 __device__ __forceinline__ uint64_t umma_desc_off(uint32_t saddr, int mode) {
@@ -431,8 +434,12 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2], w_bar;
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) float s_scale[128], s_shift[128];
+    __shared__ float s_cs1[MODE == 4 ? 128 : 1], s_cs2[MODE == 4 ? 128 : 1];      // CTA partial column sums (MODE 4)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (MODE == 4) {
+        for (int i = threadIdx.x; i < 128; i += 128 + 128 * EPI_WG) { s_cs1[i] = 0.f; s_cs2[i] = 0.f; }
+    }
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t b_bytes = (uint32_t)p.Cout * KCH * 4;
     const uint32_t w_bytes = p.resident ? 9u * (uint32_t)p.k_chunks * b_bytes : 0u;
@@ -809,6 +816,92 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const int t = u / nch, c0 = (u - t * nch) << 5;
                     const int ho = y0 + t;
                     float v[32];
+                    if (MODE == 4) {
+                        // ---- data gradient + activation backward, fused (replaces a separate pass over dy, y and dz) ----
+                        // operands of this unit from global memory first (the other warpgroup hides their latency)
+                        float4 yy[8], ra[8];
+                        const long eo = out_offset(ho, c0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { yy[j] = make_float4(0.f, 0.f, 0.f, 0.f); ra[j] = yy[j]; }
+                        if (valid) {
+                            const float4* yp = reinterpret_cast<const float4*>(p.mask_y + eo);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) yy[j] = __ldg(yp + j);
+                            if (p.residual) {
+                                const float4* rp = reinterpret_cast<const float4*>(p.residual + eo);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) ra[j] = __ldg(rp + j);
+                            }
+                        }
+                        unit(t, c0, v);
+                        const uint32_t sbuf = sbuf0;
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous store has read the tile
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float ya[4] = {yy[j].x, yy[j].y, yy[j].z, yy[j].w};
+                            const float rv[4] = {ra[j].x, ra[j].y, ra[j].z, ra[j].w};
+                            float pz[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                float d = v[4 * j + e] + rv[e];
+                                if (p.round_tf32) d = rna_tf32(d);
+                                if (!valid || (p.mask_relu && !(ya[e] > 0.f))) d = 0.f;
+                                v[4 * j + e] = d;
+                                pz[e] = d * ya[e];
+                            }
+                            // phase 1: dz * y into the staging tile (column sums for the BatchNorm scale gradient)
+                            const uint32_t a = sbuf + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(pz[0]), "f"(pz[1]), "f"(pz[2]), "f"(pz[3]) : "memory");
+                        }
+                        __syncwarp();
+                        // lane c sums column c of the 32 x 32 tile: element (row r, column c) sits in chunk (c >> 2) ^ (r & 7) of
+                        // row r - for a fixed r the 32 lanes hit 32 different banks
+                        float cs2 = 0.f;
+                        if (p.col_s2) {
+#pragma unroll 8
+                            for (int r = 0; r < 32; ++r) {
+                                float e;
+                                const uint32_t a = sbuf + (uint32_t)r * 128u + (uint32_t)((((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2));
+                                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(e) : "r"(a) : "memory");
+                                cs2 += e;
+                            }
+                        }
+                        __syncwarp();
+                        // phase 2: dz itself -> column sums (bias / BatchNorm shift gradient) and the TMA store
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const uint32_t a = sbuf + (uint32_t)lane * 128u + (uint32_t)(((j >> 2) ^ (lane & 7)) << 4);
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) {
+                            const int cg = p.col0 + c0;
+                            int cx = cg, cw = wt * 128 + q * 32, chh = ho;
+                            if (p.ps) { const int qq = cg / Cq; cx = cg % Cq; cw = 2 * cw + (qq & 1); chh = 2 * ho + (qq >> 1); }
+                            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                                         ::"l"(&tmY), "r"(sbuf), "r"(cx), "r"(cw), "r"(chh), "r"(n) : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                        if (p.col_s1) {
+                            float cs1 = 0.f;
+#pragma unroll 8
+                            for (int r = 0; r < 32; ++r) {
+                                float e;
+                                const uint32_t a = sbuf + (uint32_t)r * 128u + (uint32_t)((((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2));
+                                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(e) : "r"(a) : "memory");
+                                cs1 += e;
+                            }
+                            // column of the stored tensor this lane summed (PixelShuffle: the sub-pixel groups share the channels)
+                            const int cg = p.col0 + c0;
+                            const int cc = (p.ps ? cg % Cq : cg) + lane;
+                            atomicAdd(&s_cs1[cc], cs1);
+                            if (p.col_s2) atomicAdd(&s_cs2[cc], cs2);
+                        }
+                        __syncwarp();
+                        continue;
+                    }
                     unit(t, c0, v);
                     if (MODE == 1 || MODE == 3) {
                         float4 rn[8];
@@ -874,6 +967,16 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");    // TMA stores (if any) have landed
+        if (MODE == 4 && p.col_s1) {
+            // all epilogue warps of the CTA have added their partial sums: one global atomic per column and CTA
+            asm volatile("bar.sync 1, %0;" ::"r"(128 * EPI_WG) : "memory");
+            const int e = threadIdx.x - 128;
+            const int ncol = p.ps ? Cq : p.Ctot;
+            if (e < min(ncol, 128)) {
+                atomicAdd(p.col_s1 + e, s_cs1[e]);
+                if (p.col_s2) atomicAdd(p.col_s2 + e, s_cs2[e]);
+            }
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -1040,7 +1143,13 @@ int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream, int col0, int ncol
         p.ucols = (cq % 64 == 0 || cq > 64) ? 64 : 32;
         if (p.ps && cq != 32 && cq % 64 != 0) return sci_fail(SCI_EUNSUPPORTED, "conv tc v2 fp16: PixelShuffle groups of 32 or k*64 columns");
     }
-    const int mode = p.planar_out ? 2 : (!p.tma_store ? 3 : (d->residual ? 1 : 0));
+    int mode = p.planar_out ? 2 : (!p.tma_store ? 3 : (d->residual ? 1 : 0));
+    p.mask_y = d->mask_y; p.col_s1 = d->col_s1; p.col_s2 = d->col_s2; p.mask_relu = d->mask_relu;
+    if (d->mask_y) {
+        if (half || p.planar_out || !p.tma_store || (d->pixel_shuffle ? d->Cout / 4 : d->Cout) > 128 || (d->col_s2 && !d->col_s1))
+            return sci_fail(SCI_EUNSUPPORTED, "conv tc v2: fused activation backward needs the fp32 TMA-store path and <= 128 stored channels");
+        mode = 4;
+    }
     const int w_bytes = 9 * p.k_chunks * b_bytes;
     // shared-memory plan: [resident weights] [pipeline stages] [store staging: 4 * epi_wg warps x out_bufs x 4 KB].
     // Two epilogue warpgroups (see the kernel comment) unless their extra staging would cost the weights their residency.
@@ -1050,9 +1159,9 @@ int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream, int col0, int ncol
     // measured per layer (tools/pass_layers.py): the second warpgroup pays where the epilogue work per MMA is high (K <= 32:
     // 12->90 0.270 -> 0.255 ms, or a skip-add: 64->128+PS 0.251 -> 0.178 ms) and costs where the MMA-issuing warp is the
     // critical path and now shares its scheduler with two epilogue warps (128->128: 0.067 -> 0.078 ms)
-    const int epi_first = epi_env ? (epi_env == 1 ? 1 : 2) : ((half || p.k_chunks <= 1 || d->residual) ? 2 : 1);
+    const int epi_first = epi_env ? (epi_env == 1 ? 1 : 2) : ((half || p.k_chunks <= 1 || d->residual || d->mask_y) ? 2 : 1);
     for (epi_wg = epi_first; epi_wg >= 1; --epi_wg) {
-        for (p.out_bufs = (epi_wg == 2 ? 1 : 2); p.out_bufs >= 1; --p.out_bufs) {
+        for (p.out_bufs = ((epi_wg == 2 || d->mask_y) ? 1 : 2); p.out_bufs >= 1; --p.out_bufs) {
             out_stage = p.tma_store ? 4 * epi_wg * p.out_bufs * 4096 : 0;
             budget = total_budget - out_stage;
             p.resident = (w_bytes + 3 * A2_STAGE <= budget) ? 1 : 0;
@@ -1123,14 +1232,16 @@ int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream, int col0, int ncol
     const size_t smem = (size_t)(p.resident ? w_bytes : 0) + (size_t)p.stages * stage_bytes + out_stage + 1024;
     if (smem > 220 * 1024) return sci_fail(SCI_EUNSUPPORTED, "conv tc v2: shared memory budget exceeded");
     typedef void (*Fwd2Kernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const Fwd2Params);
-    static const Fwd2Kernel kernels[2][2][4] = {
-        {{conv_fwd2_tc_kernel<1, 0, false>, conv_fwd2_tc_kernel<1, 1, false>, conv_fwd2_tc_kernel<1, 2, false>, conv_fwd2_tc_kernel<1, 3, false>},
-         {conv_fwd2_tc_kernel<2, 0, false>, conv_fwd2_tc_kernel<2, 1, false>, conv_fwd2_tc_kernel<2, 2, false>, conv_fwd2_tc_kernel<2, 3, false>}},
-        {{conv_fwd2_tc_kernel<1, 0, true>, conv_fwd2_tc_kernel<1, 1, true>, conv_fwd2_tc_kernel<1, 2, true>, nullptr},
-         {conv_fwd2_tc_kernel<2, 0, true>, conv_fwd2_tc_kernel<2, 1, true>, conv_fwd2_tc_kernel<2, 2, true>, nullptr}}};
+    static const Fwd2Kernel kernels[2][2][5] = {
+        {{conv_fwd2_tc_kernel<1, 0, false>, conv_fwd2_tc_kernel<1, 1, false>, conv_fwd2_tc_kernel<1, 2, false>, conv_fwd2_tc_kernel<1, 3, false>,
+          conv_fwd2_tc_kernel<1, 4, false>},
+         {conv_fwd2_tc_kernel<2, 0, false>, conv_fwd2_tc_kernel<2, 1, false>, conv_fwd2_tc_kernel<2, 2, false>, conv_fwd2_tc_kernel<2, 3, false>,
+          conv_fwd2_tc_kernel<2, 4, false>}},
+        {{conv_fwd2_tc_kernel<1, 0, true>, conv_fwd2_tc_kernel<1, 1, true>, conv_fwd2_tc_kernel<1, 2, true>, nullptr, nullptr},
+         {conv_fwd2_tc_kernel<2, 0, true>, conv_fwd2_tc_kernel<2, 1, true>, conv_fwd2_tc_kernel<2, 2, true>, nullptr, nullptr}}};
     const Fwd2Kernel kern = kernels[half ? 1 : 0][epi_wg - 1][mode];
     if (!kern) return sci_fail(SCI_EUNSUPPORTED, "conv tc v2 fp16: direct-store epilogue not built");
-    static bool attr_set[64][2][2][4] = {};
+    static bool attr_set[64][2][2][5] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !attr_set[dev][half ? 1 : 0][epi_wg - 1][mode]) {

@@ -35,7 +35,8 @@ class ConvDesc(ctypes.Structure):
                 ("Cout", ctypes.c_int), ("stride", ctypes.c_int), ("relu", ctypes.c_int),
                 ("pixel_shuffle", ctypes.c_int), ("round_tf32", ctypes.c_int), ("w_split", ctypes.c_int), ("emit_lo", ctypes.c_int),
                 ("planar_in1", _f32p), ("planar_out", _f32p), ("pdl", ctypes.c_int),
-                ("half_io", ctypes.c_int), ("Cin_store", ctypes.c_int), ("Cout_store", ctypes.c_int)]
+                ("half_io", ctypes.c_int), ("Cin_store", ctypes.c_int), ("Cout_store", ctypes.c_int),
+                ("mask_y", _f32p), ("col_s1", _f32p), ("col_s2", _f32p), ("mask_relu", ctypes.c_int)]
 
 
 class WgradDesc(ctypes.Structure):
@@ -304,6 +305,7 @@ class _EngineBase:
         self.dirty = True
         self.n_launch = 0
         self.batch = os.environ.get("SCI_BATCH_OPS", "1") != "0"
+        self.fuse_act = os.environ.get("SCI_FUSE_ACT_BWD", "1") != "0"      # activation backward in the dgrad epilogue
         self._tables = None
         self.s12_flat = None
         self.pdl_chain = False   # True inside an inference chain: weights are packed, consecutive convs may overlap (PDL)
@@ -417,17 +419,32 @@ class _EngineBase:
                                  "fwd %dx%d %d->%d s%d" % (H, W, b.Ci, b.Co, Lh.stride)))
         self.n_launch += 1
 
-    def dgrad_s2(self, L, dz, N, Ho, Wo, dx, residual=None):
+    def _mask_args(self, d, mask):
+        """mask = (y_prev, L_prev): fuse the activation backward of the layer that produced this dgrad's output tensor."""
+        if mask is not None:
+            y_prev, Lp = mask
+            d.mask_y = _dp(y_prev)
+            d.col_s1 = _dp(Lp.s1) if Lp.has_affine else None
+            d.col_s2 = _dp(Lp.s2) if Lp.bn is not None else None
+            d.mask_relu = int(Lp.relu)
+
+    def can_fuse_act_bwd(self, Lp, out_channels):
+        """The data-gradient kernel can apply layer Lp's activation backward in its epilogue (tensor-core fp32 path)."""
+        return (self.fuse_act and self.impl == IMPL_TC and self.batch and (Lp.relu or Lp.has_affine) and out_channels <= 128)
+
+    def dgrad_s2(self, L, dz, N, Ho, Wo, dx, residual=None, mask=None):
         """Stride-2 layer: dx[N,2Ho,2Wo,Ci_pad] = PixelShuffle(conv(dz[N,Ho,Wo,Co_pad], sub-pixel weights)) [+ residual]."""
         d = ConvDesc(_dp(dz), _dp(L.wpk_t), None, None, _dp(residual), _dp(dx), N, Ho, Wo, L.Co_pad, 4 * L.Ci_pad, 1, 0, 1,
                      int(self.tf32), 0, 0)
+        self._mask_args(d, mask)
         call("sci_conv3x3_dgrad", ctypes.byref(d), self.impl, stream())
         self.n_launch += 1
 
-    def dgrad(self, L, dz, N, Ho, Wo, dx, residual=None):
+    def dgrad(self, L, dz, N, Ho, Wo, dx, residual=None, mask=None):
         """dx[N,Ho,Wo,Ci_pad] = conv(dz, packed transposed+flipped (and BN-scaled) weights) [+ residual]."""
         d = ConvDesc(_dp(dz), _dp(L.wpk_t), None, None, _dp(residual), _dp(dx), N, Ho, Wo, L.Co_pad, L.Ci_pad, 1, 0, 0,
                      int(self.tf32), 0, 0)
+        self._mask_args(d, mask)
         call("sci_conv3x3_dgrad", ctypes.byref(d), self.impl, stream())
         self.n_launch += 1
 
@@ -737,50 +754,61 @@ class FastDVDnetEngine(_EngineBase):
         h2, w2, h4, w4 = H // 2, W // 2, H // 4, W // 4
         nf, nh, nq = B * H * W, B * h2 * w2, B * h4 * w4
 
-        def layer_bwd(i, dy, y, x_in, N, Hin, Win, n_out_pix, dx_name, dx_shape, residual=None, want_dx=True):
-            """Backward of layer i given dy wrt its stored output y; returns dx (grad wrt its input)."""
+        Y = {0: "a0", 1: "x0", 2: "d0a", 3: "d0b", 4: "x1", 5: "d1a", 6: "d1b", 7: "x2", 8: "u2a", 9: "u2b", 11: "u1a", 12: "u1b", 14: "o0"}
+        fused = set()        # layers whose dz was already produced by the data-gradient kernel of the layer after them
+
+        def layer_bwd(i, dy, y, x_in, N, Hin, Win, n_out_pix, dx_name, dx_shape, residual=None, want_dx=True, prev=None):
+            """Backward of layer i given dy wrt its stored output y; returns dx (grad wrt its input).  prev = index of the layer
+            whose stored output IS this layer's input tensor: its activation backward is fused into this layer's data gradient
+            (dx then already is that layer's dz)."""
             Li = L[i]
-            dz = self.act_bwd(Li, dy, y, n_out_pix, Li.Co_pad)
+            dz = dy if i in fused else self.act_bwd(Li, dy, y, n_out_pix, Li.Co_pad)
             self.wgrad(Li, x_in, dz, N, Hin, Win)
             dx = None
             if want_dx:
                 dx = g(dx_name, dx_shape, dev)
+                mask = None
+                if prev is not None and self.can_fuse_act_bwd(L[prev], dx_shape[-1]):
+                    mask = (S[Y[prev]], L[prev])
+                    fused.add(prev)
                 if Li.stride == 2 and getattr(Li, "s2t", False):
-                    self.dgrad_s2(Li, dz, N, Hin // 2, Win // 2, dx, residual)
+                    self.dgrad_s2(Li, dz, N, Hin // 2, Win // 2, dx, residual, mask=mask)
                 elif Li.stride == 2:
+                    if mask is not None:
+                        fused.discard(prev)
                     dil = g("g_dil", (N, Hin, Win, Li.Co_pad), dev)
                     call("sci_nhwc_dilate2", ptr(dz), ptr(dil), N, Hin // 2, Win // 2, Li.Co_pad, stream())
                     self.dgrad(Li, dil, N, Hin, Win, dx, residual)
                 else:
                     Ho, Wo = Hin, Win
-                    self.dgrad(Li, dz, N, Ho, Wo, dx, residual)
+                    self.dgrad(Li, dz, N, Ho, Wo, dx, residual, mask=mask)
             self.param_grads(Li)
             return dx
 
         # out = in1 - xo  ->  d xo = -dout (padded columns 0)
         d_xo = g("g_xo", (B, H, W, L[15].Co_pad), dev)
         call("sci_fastdvd_output_grad", ptr(dout), ptr(d_xo), B, H, W, L[15].Co_pad, stream())
-        d_o0 = layer_bwd(15, d_xo, S["xo"], S["o0"], B, H, W, nf, "g_f32a", (B, H, W, 32))
+        d_o0 = layer_bwd(15, d_xo, S["xo"], S["o0"], B, H, W, nf, "g_f32a", (B, H, W, 32), prev=14)
         d_s0 = layer_bwd(14, d_o0, S["o0"], S["s0"], B, H, W, nf, "g_f32b", (B, H, W, 32))
         # s0 = x0 + PS(conv13(u1b)): gradient of the GEMM output is the pixel-unshuffle of d_s0
         d_c13 = g("g_h128", (B, h2, w2, 128), dev)
         call("sci_nhwc_pixel_unshuffle", ptr(d_s0), ptr(d_c13), B, h2, w2, 32, stream())
-        d_u1b = layer_bwd(13, d_c13, None, S["u1b"], B, h2, w2, nh, "g_h64a", (B, h2, w2, 64))
-        d_u1a = layer_bwd(12, d_u1b, S["u1b"], S["u1a"], B, h2, w2, nh, "g_h64b", (B, h2, w2, 64))
+        d_u1b = layer_bwd(13, d_c13, None, S["u1b"], B, h2, w2, nh, "g_h64a", (B, h2, w2, 64), prev=12)
+        d_u1a = layer_bwd(12, d_u1b, S["u1b"], S["u1a"], B, h2, w2, nh, "g_h64b", (B, h2, w2, 64), prev=11)
         d_s1 = layer_bwd(11, d_u1a, S["u1a"], S["s1"], B, h2, w2, nh, "g_h64a", (B, h2, w2, 64))
         d_c10 = g("g_q256", (B, h4, w4, 256), dev)
         call("sci_nhwc_pixel_unshuffle", ptr(d_s1), ptr(d_c10), B, h4, w4, 64, stream())
-        d_u2b = layer_bwd(10, d_c10, None, S["u2b"], B, h4, w4, nq, "g_q128a", (B, h4, w4, 128))
-        d_u2a = layer_bwd(9, d_u2b, S["u2b"], S["u2a"], B, h4, w4, nq, "g_q128b", (B, h4, w4, 128))
-        d_x2 = layer_bwd(8, d_u2a, S["u2a"], S["x2"], B, h4, w4, nq, "g_q128a", (B, h4, w4, 128))
-        d_d1b = layer_bwd(7, d_x2, S["x2"], S["d1b"], B, h4, w4, nq, "g_q128b", (B, h4, w4, 128))
-        d_d1a = layer_bwd(6, d_d1b, S["d1b"], S["d1a"], B, h4, w4, nq, "g_q128a", (B, h4, w4, 128))
+        d_u2b = layer_bwd(10, d_c10, None, S["u2b"], B, h4, w4, nq, "g_q128a", (B, h4, w4, 128), prev=9)
+        d_u2a = layer_bwd(9, d_u2b, S["u2b"], S["u2a"], B, h4, w4, nq, "g_q128b", (B, h4, w4, 128), prev=8)
+        d_x2 = layer_bwd(8, d_u2a, S["u2a"], S["x2"], B, h4, w4, nq, "g_q128a", (B, h4, w4, 128), prev=7)
+        d_d1b = layer_bwd(7, d_x2, S["x2"], S["d1b"], B, h4, w4, nq, "g_q128b", (B, h4, w4, 128), prev=6)
+        d_d1a = layer_bwd(6, d_d1b, S["d1b"], S["d1a"], B, h4, w4, nq, "g_q128a", (B, h4, w4, 128), prev=5)
         # x1 feeds conv5 (stride 2) and the skip into s1: total gradient = dgrad + d_s1
-        d_x1 = layer_bwd(5, d_d1a, S["d1a"], S["x1"], B, h2, w2, nq, "g_h64b", (B, h2, w2, 64), residual=d_s1)
-        d_d0b = layer_bwd(4, d_x1, S["x1"], S["d0b"], B, h2, w2, nh, "g_h64a", (B, h2, w2, 64))
-        d_d0a = layer_bwd(3, d_d0b, S["d0b"], S["d0a"], B, h2, w2, nh, "g_h64b", (B, h2, w2, 64))
-        d_x0 = layer_bwd(2, d_d0a, S["d0a"], S["x0"], B, H, W, nh, "g_f32a", (B, H, W, 32), residual=d_s0)
-        d_a0 = layer_bwd(1, d_x0, S["x0"], S["a0"], B, H, W, nf, "g_f96", (B, H, W, L[0].Co_pad))
+        d_x1 = layer_bwd(5, d_d1a, S["d1a"], S["x1"], B, h2, w2, nq, "g_h64b", (B, h2, w2, 64), residual=d_s1, prev=4)
+        d_d0b = layer_bwd(4, d_x1, S["x1"], S["d0b"], B, h2, w2, nh, "g_h64a", (B, h2, w2, 64), prev=3)
+        d_d0a = layer_bwd(3, d_d0b, S["d0b"], S["d0a"], B, h2, w2, nh, "g_h64b", (B, h2, w2, 64), prev=2)
+        d_x0 = layer_bwd(2, d_d0a, S["d0a"], S["x0"], B, H, W, nh, "g_f32a", (B, H, W, 32), residual=d_s0, prev=1)
+        d_a0 = layer_bwd(1, d_x0, S["x0"], S["a0"], B, H, W, nf, "g_f96", (B, H, W, L[0].Co_pad), prev=0)
         return layer_bwd(0, d_a0, S["a0"], S["a_in"], B, H, W, nf, "g_fin", (B, H, W, L[0].Ci_pad),
                          want_dx=need_input_grad)
 

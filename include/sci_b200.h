@@ -221,6 +221,15 @@ typedef struct sci_conv_desc {
     int Cout_store;         /* half_io: channels per pixel of the stored output tensor (every pixel row written is 64 channels:
                                real columns, then zeros; rows sticking out of the tensor are clipped); 0 = Cout (Cout/4 with
                                pixel_shuffle) */
+    const float* mask_y;    /* TC only (fp32, stride-1 kernel). non-NULL: this call is a DATA GRADIENT whose output is the gradient
+                               w.r.t. the stored output `mask_y` (same layout as y) of the PRECEDING layer, and that layer's
+                               activation backward is fused into the epilogue: y = (conv [+ residual]) * (mask_y > 0 if mask_relu),
+                               col_s1[c] += sum y, col_s2[c] += sum y * mask_y over all pixels (either may be NULL; the sums the
+                               bias / BatchNorm parameter gradients need, see sci_act_bwd / sci_bn_param_grad).  Replaces the
+                               separate sci_act_bwd pass over dy, y and dz */
+    float* col_s1;
+    float* col_s2;
+    int mask_relu;
 } sci_conv_desc;
 
 /* 1 if this build contains the tcgen05 tensor-core convolution kernels. */
