@@ -37,6 +37,7 @@ struct FwdParams {
     int N, H, W, Ho, Wo, Cin, Cout, stride, relu, ps, round_tf32, wsplit, emit_lo;
     int tiles_w, tiles_h, num_tiles, k_chunks, stages, acc_stride, tmem_cols;
     int Cstore;       // fp16 storage: channels per pixel of the stored output tensor
+    int ks_last;      // see Fwd2Params
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -268,10 +269,12 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
                 const uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes, b_addr = a_addr + A_BYTES;
+                const int ksn = ((ks % p.k_chunks) == p.k_chunks - 1) ? p.ks_last : KCH / 8;
 #pragma unroll
                 for (int k = 0; k < KCH / 8; ++k) {
-                    tc_mma_elect<HALF>(d_tmem, desc_hi | (uint64_t)(((a_addr + k * 32) & 0x3FFFFu) >> 4),
-                                      desc_hi | (uint64_t)(((b_addr + k * 32) & 0x3FFFFu) >> 4), idesc, (uint32_t)((ks | k) != 0));
+                    if (k < ksn)
+                        tc_mma_elect<HALF>(d_tmem, desc_hi | (uint64_t)(((a_addr + k * 32) & 0x3FFFFu) >> 4),
+                                           desc_hi | (uint64_t)(((b_addr + k * 32) & 0x3FFFFu) >> 4), idesc, (uint32_t)((ks | k) != 0));
                 }
                 if (p.wsplit) {
 #pragma unroll
@@ -400,6 +403,8 @@ struct Fwd2Params {
     // MODE 4 (data gradient + activation backward of the layer that PRODUCED this tensor, fused): dz = (conv [+ residual]) *
     // (mask_y > 0); col_s1[c] += sum dz, col_s2[c] += sum dz * mask_y  (bias / BatchNorm gradients), see the epilogue
     const float* mask_y; float* col_s1; float* col_s2; int mask_relu;
+    int ks_last;      // K steps (8 fp32 / 16 fp16 channels each) of the LAST channel chunk that can hold non-zero channels (1..4):
+                      // zero-padded K columns are not multiplied (12 -> 90: 28 of 64 fp16 channels used -> 2 of 4 steps)
 };
 
 __device__ __forceinline__ uint64_t umma_desc_off(uint32_t saddr, int mode) {
@@ -543,6 +548,7 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         if (leader) {
                             const uint32_t a_addr = ring_base + (uint32_t)stage * stage_bytes;
                             const uint32_t a_lo = desc_lo(a_addr);
+                            const int ksn = (kc == p.k_chunks - 1) ? p.ks_last : KCH / 8;     // K steps that can hold non-zero channels
                             const uint32_t b_lo = desc_lo(p.resident ? smem_base + (uint32_t)(r * 3 * p.k_chunks + kc) * b_bytes : a_addr + A2_STAGE);
                             const uint32_t b_step = p.resident ? (uint32_t)p.k_chunks * b_tile_lo : b_tile_lo;
                             const uint32_t first = (uint32_t)((r | kc) != 0);
@@ -551,7 +557,7 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                 for (int s = 0; s < 3; ++s) {
 #pragma unroll
                                     for (int k = 0; k < KCH / 8; ++k)
-                                        mma_lo<HALF>(d_base, a_lo + s * 8 + k * 2, b_lo + s * b_step + k * 2, idesc, (s | k) ? 1u : first);
+                                        if (k < ksn) mma_lo<HALF>(d_base, a_lo + s * 8 + k * 2, b_lo + s * b_step + k * 2, idesc, (s | k) ? 1u : first);
                                 }
                             }
                             tc_commit(&empty_bar[stage]);
@@ -577,6 +583,7 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         tc_fence_after();
                         if (leader) {
                             const uint32_t a_lo = desc_lo(ring_base + (uint32_t)stage * stage_bytes);
+                            const int ksn = (kc == p.k_chunks - 1) ? p.ks_last : KCH / 8;
                             // weight tiles ordered [s][kc][r]: the three filter rows of tap s are consecutive
                             const uint32_t b_lo = desc_lo(smem_base + (uint32_t)(kc * 3 + r_lo) * b_bytes);
                             const uint32_t b_step = (uint32_t)(3 * p.k_chunks) * b_tile_lo;
@@ -588,14 +595,14 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                                 for (int sk = 1; sk < 3 * (KCH / 8); ++sk) {
                                     const int s = sk / (KCH / 8), k = sk % (KCH / 8);
-                                    mma_lo<HALF>(d_col, a_lo + s * 8 + k * 2, b_lo + s * b_step + k * 2, idesc_n, 1u);
+                                    if (k < ksn) mma_lo<HALF>(d_col, a_lo + s * 8 + k * 2, b_lo + s * b_step + k * 2, idesc_n, 1u);
                                 }
                             } else {
 #pragma unroll
                                 for (int s = 0; s < 3; ++s) {
 #pragma unroll
                                     for (int k = 0; k < KCH / 8; ++k)
-                                        mma_lo<HALF>(d_col, a_lo + s * 8 + k * 2, b_lo + s * b_step + k * 2, idesc_n, 1u);
+                                        if (k < ksn) mma_lo<HALF>(d_col, a_lo + s * 8 + k * 2, b_lo + s * b_step + k * 2, idesc_n, 1u);
                                 }
                             }
                             tc_commit(&empty_bar[stage]);
@@ -612,6 +619,7 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         if (leader) {
                             const uint32_t a_addr = ring_base + (uint32_t)stage * stage_bytes;
                             const uint32_t a_lo = desc_lo(a_addr);
+                            const int ksn = (kc == p.k_chunks - 1) ? p.ks_last : KCH / 8;
                             // the loaded input row is filter row r = j - t of every output row t of the super-tile it touches
                             for (int t = max(0, j - 2); t <= min(rows - 1, j); ++t) {
                                 const int r = j - t;
@@ -624,7 +632,7 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                     for (int s = 0; s < 3; ++s) {
 #pragma unroll
                                         for (int k = 0; k < KCH / 8; ++k)
-                                            mma_lo<HALF>(d_tmem, a_lo + s * 8 + k * 2, b_lo + s * b_step + k * 2, idesc, (s | k) ? 1u : first);
+                                            if (k < ksn) mma_lo<HALF>(d_tmem, a_lo + s * 8 + k * 2, b_lo + s * b_step + k * 2, idesc, (s | k) ? 1u : first);
                                     }
                                 }
                             }
@@ -1066,6 +1074,11 @@ int conv_fwd_tc_launch(const sci_conv_desc* d, void* stream) {
     p.wsplit = d->w_split ? 1 : 0;
     p.emit_lo = d->emit_lo ? 1 : 0;
     p.Cstore = (half && d->Cout_store) ? d->Cout_store : d->Cout;
+    {
+        const int step = half ? 16 : 8, used = (d->K_used > 0 && d->K_used <= d->Cin && !d->w_split) ? d->K_used : d->Cin;
+        p.ks_last = min(4, max(1, (used - (d->Cin / kch - 1) * kch + step - 1) / step));
+        if (used <= (d->Cin / kch - 1) * kch) p.ks_last = 4;      // K_used must reach into the last chunk to shorten it
+    }
     if (p.emit_lo && (d->pixel_shuffle || d->residual || !d->round_tf32))
         return sci_fail(SCI_EUNSUPPORTED, "conv tc: emit_lo needs round_tf32 and no pixel_shuffle / residual");
     p.tiles_w = (p.Wo + TILE_W - 1) / TILE_W; p.tiles_h = (p.Ho + TILE_H - 1) / TILE_H;
@@ -1136,6 +1149,11 @@ int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream, int col0, int ncol
     const int b_bytes = p.Cout * 128;
     p.tma_store = ((half || env_int("SCI_CONV_TMA_STORE", 1)) && !p.planar_out) ? 1 : 0;
     p.Cstore = cout_store;
+    {
+        const int step = half ? 16 : 8, used = (d->K_used > 0 && d->K_used <= d->Cin) ? d->K_used : d->Cin;
+        p.ks_last = min(4, max(1, (used - (p.k_chunks - 1) * kch + step - 1) / step));
+        if (used <= (p.k_chunks - 1) * kch) p.ks_last = 4;
+    }
     p.ucols = 32;
     if (half) {
         const int cq = p.ps ? d->Cout / 4 : ncols;             // columns that belong to one stored pixel row

@@ -36,7 +36,7 @@ class ConvDesc(ctypes.Structure):
                 ("pixel_shuffle", ctypes.c_int), ("round_tf32", ctypes.c_int), ("w_split", ctypes.c_int), ("emit_lo", ctypes.c_int),
                 ("planar_in1", _f32p), ("planar_out", _f32p), ("pdl", ctypes.c_int),
                 ("half_io", ctypes.c_int), ("Cin_store", ctypes.c_int), ("Cout_store", ctypes.c_int),
-                ("mask_y", _f32p), ("col_s1", _f32p), ("col_s2", _f32p), ("mask_relu", ctypes.c_int)]
+                ("mask_y", _f32p), ("col_s1", _f32p), ("col_s2", _f32p), ("mask_relu", ctypes.c_int), ("K_used", ctypes.c_int)]
 
 
 class WgradDesc(ctypes.Structure):
@@ -259,6 +259,7 @@ class HalfLayer:
         self.base = base
         self.cin_store, self.cout_store, self.ci_dup = cin_store, cout_store, ci_dup
         self.K = _pad(cin_store, 64)
+        self.k_used = (ci_dup + base.Ci) if ci_dup else base.Ci        # leading K columns that can be non-zero
         self.N = base.Co_pad
         self.stride, self.relu, self.ps = base.stride, base.relu, base.ps
         self.wpk = torch.empty(9 * self.N * self.K, dtype=torch.float16, device=base.conv.weight.device)
@@ -408,6 +409,7 @@ class _EngineBase:
         d = ConvDesc(_dp(x), _dp(Lh.wpk), _dp(b.scale), _dp(b.shift), _dp(residual), _dp(y), N, H, W, Lh.K, Lh.N,
                      Lh.stride, int(Lh.relu), int(Lh.ps), 0, 0, 0, _dp(planar[0]) if planar else None,
                      _dp(planar[1]) if planar else None, int(self.pdl_chain), 1, Lh.cin_store, Lh.cout_store)
+        d.K_used = Lh.k_used                         # zero-padded channels of the last 64-channel chunk are not multiplied
         if self.profile is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()

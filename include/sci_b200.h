@@ -230,6 +230,9 @@ typedef struct sci_conv_desc {
     float* col_s1;
     float* col_s2;
     int mask_relu;
+    int K_used;             /* TC only. > 0: only the first K_used input channels (K columns of the packed weights) can be non-zero;
+                               the MMAs over the all-zero tail of the last 128-byte channel chunk are skipped (results unchanged).
+                               0 = Cin */
 } sci_conv_desc;
 
 /* 1 if this build contains the tcgen05 tensor-core convolution kernels. */
