@@ -68,7 +68,7 @@ PROTOTYPES = {
     "sci_p2p_close_handle": [_p],
     "sci_halo_send": [_p, _i, _i, _i, _i, _p, _p, _p, _p, ctypes.c_uint, _p, _p],
     "sci_halo_assemble": [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, ctypes.c_uint, _p, _p, _p],
-    "sci_fastdvd_pack_input_half": [_p, _f, _p, _i, _i, _i, _p],
+    "sci_fastdvd_pack_input_half": [_p, _f, _p, _i, _i, _i, _i, _p],
     "sci_conv_unpack_wgrad": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "sci_bn_fold": [_p, _p, _p, _p, _f, _p, _p, _i, _i, _p],
     "sci_act_bwd": [_p, _p, _p, _l, _i, _i, _p, _p, _p],

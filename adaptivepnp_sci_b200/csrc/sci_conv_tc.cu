@@ -38,6 +38,7 @@ struct FwdParams {
     int tiles_w, tiles_h, num_tiles, k_chunks, stages, acc_stride, tmem_cols;
     int Cstore;       // fp16 storage: channels per pixel of the stored output tensor
     int ks_last;      // see Fwd2Params
+    int rb_in, a_bytes;   // bytes per operand row (64: 32 fp16 channels, SWIZZLE_64B; else 128) and per 128-pixel A tile
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -122,16 +123,19 @@ __device__ __forceinline__ void tc_mma_elect(uint32_t d_tmem, uint64_t adesc, ui
 // LBO = 16 B, the high word (SBO = 1024 B, version 1, layout SWIZZLE_128B) never changes.  Advancing an operand by whole
 // 16-byte units inside the tile is then ONE 32-bit add on the low word.
 constexpr uint32_t DESC_HI_K128 = 0x40004040u;
+// K-major SWIZZLE_64B (64-byte operand rows = 32 fp16 channels): SBO = 8 rows x 64 B = 512 B, layout type 4
+constexpr uint32_t DESC_HI_K64 = 0x80004020u;
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | 0x10000u; }
 template <bool HALF>
-__device__ __forceinline__ void mma_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accum) {
+__device__ __forceinline__ void mma_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accum,
+                                       uint32_t desc_hi = DESC_HI_K128) {
     if (HALF) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
             "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
             "setp.ne.b32 p, %4, 0;\n\t"
             "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
-            ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accum), "r"(DESC_HI_K128) : "memory");
+            ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accum), "r"(desc_hi) : "memory");
     } else {
         asm volatile(
             "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
@@ -205,8 +209,9 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t b_bytes = (uint32_t)p.Cout * KCH * 4;
-    const uint32_t stage_bytes = A_BYTES + b_bytes * (1u + (uint32_t)p.wsplit);   // wsplit: tf32 hi + remainder weights
+    const uint32_t b_bytes = (uint32_t)p.Cout * (uint32_t)p.rb_in;
+    const uint32_t a_bytes = (uint32_t)p.a_bytes;
+    const uint32_t stage_bytes = a_bytes + b_bytes * (1u + (uint32_t)p.wsplit);   // wsplit: tf32 hi + remainder weights
 
     for (int i = threadIdx.x; i < p.Cout; i += TC_THREADS) {
         s_scale[i] = p.scale ? p.scale[i] : 1.f;
@@ -245,9 +250,9 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     if (elect_one()) {
                         mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
                         const uint32_t a_dst = smem_base + (uint32_t)stage * stage_bytes;
-                        tma_load_4d(a_dst, &tmA, &full_bar[stage], kc * (HALF ? 64 : KCH), iw0 + s, ih0 + r, n);
-                        tma_load_3d(a_dst + A_BYTES, &tmB, &full_bar[stage], kc * (HALF ? 64 : KCH), 0, tap);
-                        if (p.wsplit) tma_load_3d(a_dst + A_BYTES + b_bytes, &tmB, &full_bar[stage], kc * (HALF ? 64 : KCH), 0, tap + 9);
+                        tma_load_4d(a_dst, &tmA, &full_bar[stage], kc * (HALF ? (p.rb_in >> 1) : KCH), iw0 + s, ih0 + r, n);
+                        tma_load_3d(a_dst + a_bytes, &tmB, &full_bar[stage], kc * (HALF ? (p.rb_in >> 1) : KCH), 0, tap);
+                        if (p.wsplit) tma_load_3d(a_dst + a_bytes + b_bytes, &tmB, &full_bar[stage], kc * (HALF ? (p.rb_in >> 1) : KCH), 0, tap + 9);
                     }
                     __syncwarp();
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -259,7 +264,8 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // instruction descriptor: D=f32, A=B=tf32, K-major both, N = Cout, M = 128
         const uint32_t fmt = HALF ? 0u : 2u;
         const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.Cout >> 3) << 17) | ((128u >> 4) << 24);
-        const uint64_t desc_hi = umma_desc(0, 16, 1024);
+        const uint64_t desc_hi = p.rb_in == 64 ? umma_desc(0, 16, 512, 4) : umma_desc(0, 16, 1024);
+        const int ks_full = p.rb_in >> 5;
         int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
@@ -268,8 +274,8 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             for (int ks = 0; ks < k_steps; ++ks) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes, b_addr = a_addr + A_BYTES;
-                const int ksn = ((ks % p.k_chunks) == p.k_chunks - 1) ? p.ks_last : KCH / 8;
+                const uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes, b_addr = a_addr + a_bytes;
+                const int ksn = ((ks % p.k_chunks) == p.k_chunks - 1) ? p.ks_last : ks_full;
 #pragma unroll
                 for (int k = 0; k < KCH / 8; ++k) {
                     if (k < ksn)
@@ -405,6 +411,10 @@ struct Fwd2Params {
     const float* mask_y; float* col_s1; float* col_s2; int mask_relu;
     int ks_last;      // K steps (8 fp32 / 16 fp16 channels each) of the LAST channel chunk that can hold non-zero channels (1..4):
                       // zero-padded K columns are not multiplied (12 -> 90: 28 of 64 fp16 channels used -> 2 of 4 steps)
+    // fp16 tensors with 32 channels are stored as 64-byte pixel rows (no zero half): operand rows / staging rows of 64 bytes use the
+    // SWIZZLE_64B layouts.  rb_in / rb_out = bytes per pixel row of the input operand / of the stored output (64 or 128)
+    int rb_in, rb_out, a_stage, row_bytes;
+    uint32_t desc_hi;
 };
 
 __device__ __forceinline__ uint64_t umma_desc_off(uint32_t saddr, int mode) {
@@ -446,9 +456,9 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int i = threadIdx.x; i < 128; i += 128 + 128 * EPI_WG) { s_cs1[i] = 0.f; s_cs2[i] = 0.f; }
     }
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t b_bytes = (uint32_t)p.Cout * KCH * 4;
+    const uint32_t b_bytes = (uint32_t)p.Cout * (uint32_t)p.rb_in;
     const uint32_t w_bytes = p.resident ? 9u * (uint32_t)p.k_chunks * b_bytes : 0u;
-    const uint32_t stage_bytes = A2_STAGE + (p.resident ? 0u : 3u * b_bytes);
+    const uint32_t stage_bytes = (uint32_t)p.a_stage + (p.resident ? 0u : 3u * b_bytes);
     const uint32_t ring_base = smem_base + w_bytes;
     const uint32_t stage_out_base = ring_base + (uint32_t)p.stages * stage_bytes;   // 4 EPI_WG warps x out_bufs x 4 KB store staging
 
@@ -489,7 +499,7 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         // horizontal tap form ONE K-major B matrix of 3*Cout rows
                         const uint32_t slot = p.stack ? (uint32_t)(((tap % 3) * p.k_chunks + kc) * 3 + tap / 3)
                                                       : (uint32_t)(tap * p.k_chunks + kc);
-                        tma_load_3d(smem_base + slot * b_bytes, &tmB, &w_bar, kc * (HALF ? 64 : KCH), p.col0, tap);
+                        tma_load_3d(smem_base + slot * b_bytes, &tmB, &w_bar, kc * (HALF ? (p.rb_in >> 1) : KCH), p.col0, tap);
                     }
             }
             __syncwarp();
@@ -508,12 +518,12 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
                     if (elect_one()) {
                         const bool skip_a = (p.dbg & 2) != 0;
-                        mbar_arrive_expect_tx(&full_bar[stage], (skip_a ? 0u : ROW_BYTES) + (p.resident ? 0u : 3u * b_bytes));
+                        mbar_arrive_expect_tx(&full_bar[stage], (skip_a ? 0u : (uint32_t)p.row_bytes) + (p.resident ? 0u : 3u * b_bytes));
                         const uint32_t a_dst = ring_base + (uint32_t)stage * stage_bytes;
-                        if (!skip_a) tma_load_4d(a_dst, &tmA, &full_bar[stage], kc * (HALF ? 64 : KCH), wt * 128 - 1, y0 + j - 1, n);
+                        if (!skip_a) tma_load_4d(a_dst, &tmA, &full_bar[stage], kc * (HALF ? (p.rb_in >> 1) : KCH), wt * 128 - 1, y0 + j - 1, n);
                         if (!p.resident) {       // streamed weights: R == 1, j is the filter row
                             for (int s = 0; s < 3; ++s)
-                                tma_load_3d(a_dst + A2_STAGE + (uint32_t)s * b_bytes, &tmB, &full_bar[stage], kc * (HALF ? 64 : KCH), p.col0, j * 3 + s);
+                                tma_load_3d(a_dst + (uint32_t)p.a_stage + (uint32_t)s * b_bytes, &tmB, &full_bar[stage], kc * (HALF ? (p.rb_in >> 1) : KCH), p.col0, j * 3 + s);
                         }
                     }
                     __syncwarp();
@@ -533,6 +543,8 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (p.resident) { mbar_wait(&w_bar, 0); tc_fence_after(); }
         int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
         const uint32_t b_tile_lo = b_bytes >> 4;                  // one [Cout][32 ch] weight tile, in descriptor units
+        const uint32_t tapu = (uint32_t)p.rb_in >> 4;             // one pixel (= one horizontal tap) in 16-byte descriptor units
+        const int ks_full = p.rb_in >> 5;                         // 32-byte K steps per operand row
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
             tc_fence_after();
@@ -548,8 +560,8 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         if (leader) {
                             const uint32_t a_addr = ring_base + (uint32_t)stage * stage_bytes;
                             const uint32_t a_lo = desc_lo(a_addr);
-                            const int ksn = (kc == p.k_chunks - 1) ? p.ks_last : KCH / 8;     // K steps that can hold non-zero channels
-                            const uint32_t b_lo = desc_lo(p.resident ? smem_base + (uint32_t)(r * 3 * p.k_chunks + kc) * b_bytes : a_addr + A2_STAGE);
+                            const int ksn = (kc == p.k_chunks - 1) ? p.ks_last : ks_full;     // K steps that can hold non-zero channels
+                            const uint32_t b_lo = desc_lo(p.resident ? smem_base + (uint32_t)(r * 3 * p.k_chunks + kc) * b_bytes : a_addr + (uint32_t)p.a_stage);
                             const uint32_t b_step = p.resident ? (uint32_t)p.k_chunks * b_tile_lo : b_tile_lo;
                             const uint32_t first = (uint32_t)((r | kc) != 0);
                             if (!(p.dbg & 1)) {
@@ -557,7 +569,7 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                 for (int s = 0; s < 3; ++s) {
 #pragma unroll
                                     for (int k = 0; k < KCH / 8; ++k)
-                                        if (k < ksn) mma_lo<HALF>(d_base, a_lo + s * 8 + k * 2, b_lo + s * b_step + k * 2, idesc, (s | k) ? 1u : first);
+                                        if (k < ksn) mma_lo<HALF>(d_base, a_lo + s * tapu + k * 2, b_lo + s * b_step + k * 2, idesc, (s | k) ? 1u : first, p.desc_hi);
                                 }
                             }
                             tc_commit(&empty_bar[stage]);
@@ -583,26 +595,26 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         tc_fence_after();
                         if (leader) {
                             const uint32_t a_lo = desc_lo(ring_base + (uint32_t)stage * stage_bytes);
-                            const int ksn = (kc == p.k_chunks - 1) ? p.ks_last : KCH / 8;
+                            const int ksn = (kc == p.k_chunks - 1) ? p.ks_last : ks_full;
                             // weight tiles ordered [s][kc][r]: the three filter rows of tap s are consecutive
                             const uint32_t b_lo = desc_lo(smem_base + (uint32_t)(kc * 3 + r_lo) * b_bytes);
                             const uint32_t b_step = (uint32_t)(3 * p.k_chunks) * b_tile_lo;
                             if (p.dbg & 1) {
                             } else if (r_lo == 0 && kc == 0) {
                                 // this row opens the accumulator of output row t = j (r = 0): that slice must overwrite
-                                mma_lo<HALF>(d_col, a_lo, b_lo, idesc, 0u);
-                                if (nr > 1) mma_lo<HALF>(d_col + (uint32_t)p.acc_stride, a_lo, b_lo + b_tile_lo, idesc_m, 1u);
+                                mma_lo<HALF>(d_col, a_lo, b_lo, idesc, 0u, p.desc_hi);
+                                if (nr > 1) mma_lo<HALF>(d_col + (uint32_t)p.acc_stride, a_lo, b_lo + b_tile_lo, idesc_m, 1u, p.desc_hi);
 #pragma unroll
                                 for (int sk = 1; sk < 3 * (KCH / 8); ++sk) {
                                     const int s = sk / (KCH / 8), k = sk % (KCH / 8);
-                                    if (k < ksn) mma_lo<HALF>(d_col, a_lo + s * 8 + k * 2, b_lo + s * b_step + k * 2, idesc_n, 1u);
+                                    if (k < ksn) mma_lo<HALF>(d_col, a_lo + s * tapu + k * 2, b_lo + s * b_step + k * 2, idesc_n, 1u, p.desc_hi);
                                 }
                             } else {
 #pragma unroll
                                 for (int s = 0; s < 3; ++s) {
 #pragma unroll
                                     for (int k = 0; k < KCH / 8; ++k)
-                                        if (k < ksn) mma_lo<HALF>(d_col, a_lo + s * 8 + k * 2, b_lo + s * b_step + k * 2, idesc_n, 1u);
+                                        if (k < ksn) mma_lo<HALF>(d_col, a_lo + s * tapu + k * 2, b_lo + s * b_step + k * 2, idesc_n, 1u, p.desc_hi);
                                 }
                             }
                             tc_commit(&empty_bar[stage]);
@@ -619,12 +631,12 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         if (leader) {
                             const uint32_t a_addr = ring_base + (uint32_t)stage * stage_bytes;
                             const uint32_t a_lo = desc_lo(a_addr);
-                            const int ksn = (kc == p.k_chunks - 1) ? p.ks_last : KCH / 8;
+                            const int ksn = (kc == p.k_chunks - 1) ? p.ks_last : ks_full;
                             // the loaded input row is filter row r = j - t of every output row t of the super-tile it touches
                             for (int t = max(0, j - 2); t <= min(rows - 1, j); ++t) {
                                 const int r = j - t;
                                 const uint32_t d_tmem = d_base + (uint32_t)(t * p.acc_stride);
-                                const uint32_t b_lo = desc_lo(p.resident ? smem_base + (uint32_t)(r * 3 * p.k_chunks + kc) * b_bytes : a_addr + A2_STAGE);
+                                const uint32_t b_lo = desc_lo(p.resident ? smem_base + (uint32_t)(r * 3 * p.k_chunks + kc) * b_bytes : a_addr + (uint32_t)p.a_stage);
                                 const uint32_t b_step = p.resident ? (uint32_t)p.k_chunks * b_tile_lo : b_tile_lo;
                                 const uint32_t first = (uint32_t)((r | kc) != 0);
                                 if (!(p.dbg & 1)) {
@@ -632,7 +644,7 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                     for (int s = 0; s < 3; ++s) {
 #pragma unroll
                                         for (int k = 0; k < KCH / 8; ++k)
-                                            if (k < ksn) mma_lo<HALF>(d_tmem, a_lo + s * 8 + k * 2, b_lo + s * b_step + k * 2, idesc, (s | k) ? 1u : first);
+                                            if (k < ksn) mma_lo<HALF>(d_tmem, a_lo + s * tapu + k * 2, b_lo + s * b_step + k * 2, idesc, (s | k) ? 1u : first, p.desc_hi);
                                     }
                                 }
                             }
@@ -768,10 +780,19 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         else                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     }
                     __syncwarp();
+                    if (p.rb_out == 64) {
+                        // 32-channel tensor: 64-byte pixel rows, SWIZZLE_64B (16-byte chunk j of row l at j ^ ((l >> 1) & 3))
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const uint32_t a = sbuf + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(hv[4 * j]), "r"(hv[4 * j + 1]), "r"(hv[4 * j + 2]), "r"(hv[4 * j + 3]) : "memory");
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t a = sbuf + (uint32_t)lane * 64u + (uint32_t)((j ^ ((lane >> 1) & 3)) << 4);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(hv[4 * j]), "r"(hv[4 * j + 1]), "r"(hv[4 * j + 2]), "r"(hv[4 * j + 3]) : "memory");
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const uint32_t a = sbuf + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(hv[4 * j]), "r"(hv[4 * j + 1]), "r"(hv[4 * j + 2]), "r"(hv[4 * j + 3]) : "memory");
+                        }
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
@@ -1015,13 +1036,13 @@ EncodeTiledFn get_encode_fn() {
 
 // NHWC activation tensor [N][H][W][C], box = {32 ch, TILE_W*stride, TILE_H*stride, 1} traversed with element stride `stride`
 int make_act_map(CUtensorMap* tm, const float* x, int N, int H, int W, int C, int stride, int box_w, int box_h,
-                 CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, bool half = false) {
+                 CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, bool half = false, bool row64 = false) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return sci_fail(SCI_ELAUNCH, "cuTensorMapEncodeTiled entry point not available");
     const cuuint64_t esz = half ? 2 : 4;
     const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     const cuuint64_t strides[3] = {(cuuint64_t)C * esz, (cuuint64_t)W * C * esz, (cuuint64_t)H * W * C * esz};
-    const cuuint32_t box[4] = {(cuuint32_t)(half ? 64 : KCH), (cuuint32_t)(box_w * stride), (cuuint32_t)(box_h * stride), 1};
+    const cuuint32_t box[4] = {(cuuint32_t)(row64 ? 32 : (half ? 64 : KCH)), (cuuint32_t)(box_w * stride), (cuuint32_t)(box_h * stride), 1};
     const cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     CUresult r = fn(tm, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1034,16 +1055,17 @@ int make_act_map(CUtensorMap* tm, const float* x, int N, int H, int W, int C, in
 }
 
 // packed weights [taps][Cout][Cin] (taps = 9, or 18 with the hi/remainder split), box = {32 ch, Cout, 1}
-int make_weight_map(CUtensorMap* tm, const float* w, int Cout, int Cin, int taps, int box_rows = 0, bool half = false) {
+int make_weight_map(CUtensorMap* tm, const float* w, int Cout, int Cin, int taps, int box_rows = 0, bool half = false,
+                    bool row64 = false) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return sci_fail(SCI_ELAUNCH, "cuTensorMapEncodeTiled entry point not available");
     const cuuint64_t esz = half ? 2 : 4;
     const cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)taps};
     const cuuint64_t strides[2] = {(cuuint64_t)Cin * esz, (cuuint64_t)Cout * Cin * esz};
-    const cuuint32_t box[3] = {(cuuint32_t)(half ? 64 : KCH), (cuuint32_t)(box_rows ? box_rows : Cout), 1};
+    const cuuint32_t box[3] = {(cuuint32_t)(row64 ? 32 : (half ? 64 : KCH)), (cuuint32_t)(box_rows ? box_rows : Cout), 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(tm, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(w), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, row64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         char msg[96];
@@ -1055,9 +1077,16 @@ int make_weight_map(CUtensorMap* tm, const float* w, int Cout, int Cin, int taps
 
 int next_pow2_cols(int c) { int v = 32; while (v < c) v <<= 1; return v; }
 
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
 int conv_fwd_tc_launch(const sci_conv_desc* d, void* stream) {
     const bool half = d->half_io != 0;
-    const int kch = half ? 64 : KCH, esz = half ? 2 : 4;
+    const int esz = half ? 2 : 4;
+    const int rb_in = (half && d->Cin == 32 && env_int("SCI_CONV_SW64", 1)) ? 64 : 128;
+    const int kch = rb_in / esz;
     if (d->Cin % kch != 0 || d->Cout % 16 != 0 || d->Cout > 256)
         return sci_fail(SCI_EUNSUPPORTED, "conv tc: needs Cin % 32 == 0 (fp16: % 64), Cout % 16 == 0, Cout <= 256");
     if (((uintptr_t)d->x | (uintptr_t)d->w | (uintptr_t)d->y | (uintptr_t)d->residual) & 15)
@@ -1076,23 +1105,26 @@ int conv_fwd_tc_launch(const sci_conv_desc* d, void* stream) {
     p.Cstore = (half && d->Cout_store) ? d->Cout_store : d->Cout;
     {
         const int step = half ? 16 : 8, used = (d->K_used > 0 && d->K_used <= d->Cin && !d->w_split) ? d->K_used : d->Cin;
-        p.ks_last = min(4, max(1, (used - (d->Cin / kch - 1) * kch + step - 1) / step));
-        if (used <= (d->Cin / kch - 1) * kch) p.ks_last = 4;      // K_used must reach into the last chunk to shorten it
+        p.ks_last = min(rb_in / 32, max(1, (used - (d->Cin / kch - 1) * kch + step - 1) / step));
+        if (used <= (d->Cin / kch - 1) * kch) p.ks_last = rb_in / 32;      // K_used must reach into the last chunk to shorten it
     }
     if (p.emit_lo && (d->pixel_shuffle || d->residual || !d->round_tf32))
         return sci_fail(SCI_EUNSUPPORTED, "conv tc: emit_lo needs round_tf32 and no pixel_shuffle / residual");
     p.tiles_w = (p.Wo + TILE_W - 1) / TILE_W; p.tiles_h = (p.Ho + TILE_H - 1) / TILE_H;
     p.num_tiles = p.tiles_w * p.tiles_h * p.N;
     p.k_chunks = p.Cin / kch;
-    const int stage_bytes = A_BYTES + p.Cout * 128 * (1 + p.wsplit);
+    p.rb_in = rb_in;
+    p.a_bytes = TILE_W * TILE_H * rb_in;
+    const int stage_bytes = p.a_bytes + p.Cout * rb_in * (1 + p.wsplit);
     p.stages = min(MAX_STAGES, (216 * 1024) / stage_bytes);
     p.acc_stride = ((p.Cout + 31) / 32) * 32;
     p.tmem_cols = next_pow2_cols(2 * p.acc_stride);
     CUtensorMap tmA, tmB;
     const int cin_store = (half && d->Cin_store) ? d->Cin_store : d->Cin;
-    int rc = make_act_map(&tmA, d->x, d->N, d->H, d->W, cin_store, d->stride, TILE_W, TILE_H, CU_TENSOR_MAP_SWIZZLE_128B, half);
+    int rc = make_act_map(&tmA, d->x, d->N, d->H, d->W, cin_store, d->stride, TILE_W, TILE_H,
+                          rb_in == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, half, rb_in == 64);
     if (rc) return rc;
-    rc = make_weight_map(&tmB, d->w, d->Cout, d->Cin, 9 * (1 + p.wsplit), 0, half);
+    rc = make_weight_map(&tmB, d->w, d->Cout, d->Cin, 9 * (1 + p.wsplit), 0, half, rb_in == 64);
     if (rc) return rc;
     const size_t smem = (size_t)p.stages * stage_bytes + 1024;
     static bool attr_set[64][2] = {};
@@ -1113,10 +1145,6 @@ int conv_fwd_tc_launch(const sci_conv_desc* d, void* stream) {
 
 
 
-int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return v ? atoi(v) : dflt;
-}
 
 bool fwd2_eligible(const sci_conv_desc* d) {
     if (d->planar_out) return true;                      // fused planar output exists in the v2 kernel only
@@ -1128,9 +1156,11 @@ bool fwd2_eligible(const sci_conv_desc* d) {
 // columns [col0, col0 + ncols) of the layer
 int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream, int col0, int ncols) {
     const bool half = d->half_io != 0;
-    const int kch = half ? 64 : KCH;                 // channels per 128-byte operand row
     const int esz = half ? 2 : 4;
-    if (d->Cin % kch != 0) return sci_fail(SCI_EUNSUPPORTED, "conv tc v2: Cin % 32 (fp32) / % 64 (fp16)");
+    // fp16 tensors with 32 channels use 64-byte operand rows (SWIZZLE_64B); everything else one 128-byte row per pixel and chunk
+    const int rb_in = (half && d->Cin == 32 && env_int("SCI_CONV_SW64", 1)) ? 64 : 128;
+    const int kch = rb_in / esz;                     // channels per operand row
+    if (d->Cin % kch != 0) return sci_fail(SCI_EUNSUPPORTED, "conv tc v2: Cin % 32 (fp32) / % 64 or == 32 (fp16)");
     if (((uintptr_t)d->x | (uintptr_t)d->w | (uintptr_t)d->y | (uintptr_t)d->residual) & 15)
         return sci_fail(SCI_EINVAL, "conv tc: pointers must be 16-byte aligned");
     const int cin_store = (half && d->Cin_store) ? d->Cin_store : d->Cin;       // channels per pixel of the stored input
@@ -1146,19 +1176,26 @@ int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream, int col0, int ncol
         return sci_fail(SCI_EINVAL, "conv tc v2: planar output needs planar_in1, Cout == 32, no pixel_shuffle / residual");
     p.tiles_w = (p.W + 127) / 128;
     p.k_chunks = p.Cin / kch;
-    const int b_bytes = p.Cout * 128;
+    const int rb_out = (half && cout_store == 32 && !p.planar_out) ? 64 : 128;
+    p.rb_in = rb_in; p.rb_out = rb_out;
+    p.a_stage = rb_in == 64 ? 9 * 1024 : A2_STAGE;
+    p.row_bytes = ROW_PX * rb_in;
+    p.desc_hi = rb_in == 64 ? DESC_HI_K64 : DESC_HI_K128;
+    const int a_stage = p.a_stage;
+    const int b_bytes = p.Cout * rb_in;
     p.tma_store = ((half || env_int("SCI_CONV_TMA_STORE", 1)) && !p.planar_out) ? 1 : 0;
     p.Cstore = cout_store;
     {
         const int step = half ? 16 : 8, used = (d->K_used > 0 && d->K_used <= d->Cin) ? d->K_used : d->Cin;
-        p.ks_last = min(4, max(1, (used - (p.k_chunks - 1) * kch + step - 1) / step));
-        if (used <= (p.k_chunks - 1) * kch) p.ks_last = 4;
+        p.ks_last = min(rb_in / 32, max(1, (used - (p.k_chunks - 1) * kch + step - 1) / step));
+        if (used <= (p.k_chunks - 1) * kch) p.ks_last = rb_in / 32;
     }
     p.ucols = 32;
     if (half) {
         const int cq = p.ps ? d->Cout / 4 : ncols;             // columns that belong to one stored pixel row
         if (cq % 32 != 0) return sci_fail(SCI_EUNSUPPORTED, "conv tc v2 fp16: column groups of 32");
         p.ucols = (cq % 64 == 0 || cq > 64) ? 64 : 32;
+        if (rb_out == 64 && p.ucols != 32) return sci_fail(SCI_EUNSUPPORTED, "conv tc v2 fp16: a 32-channel output tensor needs 32-column units");
         if (p.ps && cq != 32 && cq % 64 != 0) return sci_fail(SCI_EUNSUPPORTED, "conv tc v2 fp16: PixelShuffle groups of 32 or k*64 columns");
     }
     int mode = p.planar_out ? 2 : (!p.tma_store ? 3 : (d->residual ? 1 : 0));
@@ -1182,20 +1219,20 @@ int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream, int col0, int ncol
         for (p.out_bufs = ((epi_wg == 2 || d->mask_y) ? 1 : 2); p.out_bufs >= 1; --p.out_bufs) {
             out_stage = p.tma_store ? 4 * epi_wg * p.out_bufs * 4096 : 0;
             budget = total_budget - out_stage;
-            p.resident = (w_bytes + 3 * A2_STAGE <= budget) ? 1 : 0;
-            const int sb = A2_STAGE + (p.resident ? 0 : 3 * b_bytes);
+            p.resident = (w_bytes + 3 * a_stage <= budget) ? 1 : 0;
+            const int sb = a_stage + (p.resident ? 0 : 3 * b_bytes);
             const int st = (budget - (p.resident ? w_bytes : 0)) / sb;
-            const bool would_be_resident = w_bytes + 3 * A2_STAGE <= total_budget - (p.tma_store ? 4 * epi_wg * 4096 : 0);
+            const bool would_be_resident = w_bytes + 3 * a_stage <= total_budget - (p.tma_store ? 4 * epi_wg * 4096 : 0);
             if ((p.resident || !would_be_resident) && st >= 3) break;
             if (p.out_bufs == 1) break;
         }
-        const bool resident_with_one = w_bytes + 3 * A2_STAGE <= total_budget - (p.tma_store ? 4 * 4096 : 0);
+        const bool resident_with_one = w_bytes + 3 * a_stage <= total_budget - (p.tma_store ? 4 * 4096 : 0);
         // fp16 chains: the MMAs are twice as fast, so the epilogue decides more often - two warpgroups even where that costs
         // the weights their residency (64->128 + PixelShuffle: 0.215 ms resident with one group, 0.135 ms streamed with two)
         if (epi_wg == 1 || epi_env == 2 || half || p.resident || !resident_with_one) break;
     }
     if (env_int("SCI_CONV_RESIDENT", 1) == 0) p.resident = 0;
-    const int stage_bytes = A2_STAGE + (p.resident ? 0 : 3 * b_bytes);
+    const int stage_bytes = a_stage + (p.resident ? 0 : 3 * b_bytes);
     p.stages = min(MAX_STAGES, (budget - (p.resident ? w_bytes : 0)) / stage_bytes);
     if (p.stages < 2) return sci_fail(SCI_EUNSUPPORTED, "conv tc v2: pipeline does not fit");
     p.acc_stride = p.Cout;
@@ -1226,11 +1263,11 @@ int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream, int col0, int ncol
         const cuuint32_t box[4] = {(cuuint32_t)kch, ROW_PX, 1, 1};
         const cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = fn(&tmA, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(d->x), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, rb_in == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return sci_fail(SCI_ELAUNCH, "cuTensorMapEncodeTiled(row box) failed");
     }
-    int rc = make_weight_map(&tmB, d->w, d->Cout, d->Cin, 9, ncols, half);
+    int rc = make_weight_map(&tmB, d->w, d->Cout, d->Cin, 9, ncols, half, rb_in == 64);
     if (rc) return rc;
     CUtensorMap tmY = tmA;
     if (p.tma_store) {
@@ -1241,10 +1278,10 @@ int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream, int col0, int ncol
         const cuuint64_t oc = (cuuint64_t)cout_store, ow = (cuuint64_t)(d->W << ps), oh = (cuuint64_t)(d->H << ps);
         const cuuint64_t dims[4] = {oc, ow, oh, (cuuint64_t)d->N};
         const cuuint64_t strides[3] = {oc * esz, ow * oc * esz, oh * ow * oc * esz};
-        const cuuint32_t box[4] = {(cuuint32_t)kch, (cuuint32_t)(32 << ps), 1, 1};
+        const cuuint32_t box[4] = {(cuuint32_t)(rb_out / esz), (cuuint32_t)(32 << ps), 1, 1};
         const cuuint32_t estr[4] = {1, (cuuint32_t)(1 << ps), 1, 1};
         CUresult r = fn(&tmY, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d->y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        rb_out == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return sci_fail(SCI_ELAUNCH, "cuTensorMapEncodeTiled(output) failed");
     }
     const size_t smem = (size_t)(p.resident ? w_bytes : 0) + (size_t)p.stages * stage_bytes + out_stage + 1024;
@@ -1846,7 +1883,7 @@ int check_conv_desc(const sci_conv_desc* d) {
     SCI_REQUIRE(!d->planar_out || (d->stride == 1 && !d->w_split && !d->emit_lo), "conv: planar output options");
     SCI_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "conv: shape");
     SCI_REQUIRE(d->Cin % 8 == 0 && d->Cout % 4 == 0, "conv: Cin % 8, Cout % 4");
-    SCI_REQUIRE(!d->half_io || (d->Cin % 64 == 0 && d->Cout % 32 == 0 && !d->w_split && !d->emit_lo), "conv fp16: Cin % 64, Cout % 32, no split options");
+    SCI_REQUIRE(!d->half_io || ((d->Cin % 64 == 0 || d->Cin == 32) && d->Cout % 32 == 0 && !d->w_split && !d->emit_lo), "conv fp16: Cin % 64 (or 32), Cout % 32, no split options");
     SCI_REQUIRE(d->stride == 1 || d->stride == 2, "conv: stride");
     SCI_REQUIRE(!d->pixel_shuffle || d->stride == 1, "conv: pixel_shuffle with stride 2");
     return SCI_OK;

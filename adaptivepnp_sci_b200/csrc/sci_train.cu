@@ -409,9 +409,11 @@ __device__ __forceinline__ uint4 pack8(const __half* v) {
     auto pk = [](__half a, __half b) -> uint32_t { return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16); };
     return make_uint4(pk(v[0], v[1]), pk(v[2], v[3]), pk(v[4], v[5]), pk(v[6], v[7]));
 }
+// NCH = 16-byte chunks per pixel row: 8 (64 channels, the upper 36 zero) or 4 (32 channels = 64-byte rows)
+template <int NCH>
 __global__ void __launch_bounds__(256) fastdvd_pack_half_kernel(const float* __restrict__ frames, float sigma,
                                                                 __half* __restrict__ out, int B, int H, int W) {
-    __shared__ uint4 tile[8][32 * 8];                 // per warp: 32 pixels x 8 chunks of 16 bytes, XOR-swizzled
+    __shared__ uint4 tile[8][32 * NCH];               // per warp: 32 pixels x NCH chunks of 16 bytes, XOR-swizzled
     const long plane = (long)H * W;
     const int f = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -433,22 +435,23 @@ __global__ void __launch_bounds__(256) fastdvd_pack_half_kernel(const float* __r
             }
         }
     }
-    // stage the warp's 32 rows of 128 bytes (chunk j of pixel l at slot l*8 + (j ^ (l & 7)): conflict-free both ways) ...
+    // stage the warp's 32 pixel rows (chunk j of pixel l at slot l*NCH + (j ^ (l & (NCH-1))): conflict-free both ways) ...
     uint4* t = tile[warp];
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    t[lane * 8 + (0 ^ (lane & 7))] = pack8(hi);
-    t[lane * 8 + (1 ^ (lane & 7))] = pack8(hi + 8);
-    t[lane * 8 + (2 ^ (lane & 7))] = pack8(lo);
-    t[lane * 8 + (3 ^ (lane & 7))] = pack8(lo + 8);
+    const int sw = lane & (NCH - 1);
+    t[lane * NCH + (0 ^ sw)] = pack8(hi);
+    t[lane * NCH + (1 ^ sw)] = pack8(hi + 8);
+    t[lane * NCH + (2 ^ sw)] = pack8(lo);
+    t[lane * NCH + (3 ^ sw)] = pack8(lo + 8);
 #pragma unroll
-    for (int j = 4; j < 8; ++j) t[lane * 8 + (j ^ (lane & 7))] = z;
+    for (int j = 4; j < NCH; ++j) t[lane * NCH + (j ^ sw)] = z;
     __syncwarp();
-    // ... and write them as 8 fully coalesced 512-byte warp stores
-    uint4* dst = reinterpret_cast<uint4*>(out + ((long)f * plane + p0) * 64);
+    // ... and write them as fully coalesced 512-byte warp stores
+    uint4* dst = reinterpret_cast<uint4*>(out + ((long)f * plane + p0) * (NCH * 8));
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int o = i * 32 + lane, px = o >> 3, j = o & 7;
-        if (p0 + px < plane) dst[o] = t[px * 8 + (j ^ (px & 7))];
+    for (int i = 0; i < NCH; ++i) {
+        const int o = i * 32 + lane, px = o / NCH, j = o % NCH;
+        if (p0 + px < plane) dst[o] = t[px * NCH + (j ^ (px & (NCH - 1)))];
     }
 }
 
@@ -591,7 +594,7 @@ extern "C" int sci_conv_pack_weights(const float* w, float* packed, int Co, int 
 extern "C" int sci_conv_pack_weights_half(const float* w, void* packed, int Co, int Ci, int groups, int Co_pad, int Ci_pad,
                                           int ps, int ci_dup, void* stream) {
     SCI_REQUIRE(w && packed && Co > 0 && Ci > 0 && groups > 0 && Co % groups == 0 && Ci % groups == 0, "pack_weights_half");
-    SCI_REQUIRE(Co_pad >= Co && Ci_pad >= Ci && Ci_pad % 64 == 0 && (!ps || (Co % 4 == 0 && Co_pad % 4 == 0)), "pack_weights_half: padding");
+    SCI_REQUIRE(Co_pad >= Co && Ci_pad >= Ci && Ci_pad % 32 == 0 && (!ps || (Co % 4 == 0 && Co_pad % 4 == 0)), "pack_weights_half: padding");
     SCI_REQUIRE(ci_dup == 0 || (ci_dup >= Ci && ci_dup + Ci <= Ci_pad), "pack_weights_half: ci_dup block does not fit");
     const long total = (long)9 * Co_pad * Ci_pad;
     pack_weights_half_kernel<<<grid1d(total), 256, 0, sci_stream(stream)>>>(w, reinterpret_cast<__half*>(packed), Co, Ci, groups,
@@ -600,10 +603,11 @@ extern "C" int sci_conv_pack_weights_half(const float* w, void* packed, int Co, 
     return SCI_OK;
 }
 
-extern "C" int sci_fastdvd_pack_input_half(const float* frames, float sigma, void* out, int B, int H, int W, void* stream) {
-    SCI_REQUIRE(frames && out && B > 0 && H > 0 && W > 0 && B <= 65535, "fastdvd_pack_input_half");
-    fastdvd_pack_half_kernel<<<dim3(grid1d((long)H * W, 256), B), 256, 0, sci_stream(stream)>>>(frames, sigma,
-                                                                                               reinterpret_cast<__half*>(out), B, H, W);
+extern "C" int sci_fastdvd_pack_input_half(const float* frames, float sigma, void* out, int B, int H, int W, int C, void* stream) {
+    SCI_REQUIRE(frames && out && B > 0 && H > 0 && W > 0 && B <= 65535 && (C == 32 || C == 64), "fastdvd_pack_input_half");
+    const dim3 grid(grid1d((long)H * W, 256), B);
+    if (C == 64) fastdvd_pack_half_kernel<8><<<grid, 256, 0, sci_stream(stream)>>>(frames, sigma, reinterpret_cast<__half*>(out), B, H, W);
+    else         fastdvd_pack_half_kernel<4><<<grid, 256, 0, sci_stream(stream)>>>(frames, sigma, reinterpret_cast<__half*>(out), B, H, W);
     SCI_CHECK_LAUNCH("fastdvd_pack_input_half");
     return SCI_OK;
 }

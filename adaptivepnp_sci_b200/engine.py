@@ -258,7 +258,7 @@ class HalfLayer:
     def __init__(self, base, cin_store, cout_store, ci_dup=0):
         self.base = base
         self.cin_store, self.cout_store, self.ci_dup = cin_store, cout_store, ci_dup
-        self.K = _pad(cin_store, 64)
+        self.K = 32 if cin_store == 32 else _pad(cin_store, 64)     # 32-channel tensors: 64-byte operand rows (SWIZZLE_64B)
         self.k_used = (ci_dup + base.Ci) if ci_dup else base.Ci        # leading K columns that can be non-zero
         self.N = base.Co_pad
         self.stride, self.relu, self.ps = base.stride, base.relu, base.ps
@@ -603,6 +603,9 @@ class FastDVDnetEngine(_EngineBase):
     # 32-channel tensors are stored as 64 (32 zeros) so that every pixel row is one 128-byte operand row
     _H_IN = [64, 96, 64, 64, 64, 64, 128, 128, 128, 128, 128, 64, 64, 64, 64, 64]
     _H_OUT = [96, 64, 64, 64, 64, 128, 128, 128, 128, 128, 64, 64, 64, 64, 64, 64]
+    # since the 64-byte-row (SWIZZLE_64B) kernels: tensors with 32 real channels (packed input, x0, s0, o0) are stored as 32
+    _H_IN32 = [32, 96, 32, 64, 64, 64, 128, 128, 128, 128, 128, 64, 64, 64, 32, 32]
+    _H_OUT32 = [96, 32, 64, 64, 64, 128, 128, 128, 128, 128, 64, 64, 64, 32, 32, 32]
 
     def __init__(self, module):
         self.t1 = _DenBlockLayers(module.temp1)
@@ -613,10 +616,10 @@ class FastDVDnetEngine(_EngineBase):
         self.half = self.impl == IMPL_TC and os.environ.get("SCI_CONV_HALF", "1") != "0"
         self.layers_inf = None
         if self.half:
-            self.t1h = [HalfLayer(L, ci, co, ci_dup=16 if i == 0 else 0)
-                        for i, (L, ci, co) in enumerate(zip(self.t1.L, self._H_IN, self._H_OUT))]
-            self.t2h = [HalfLayer(L, ci, co, ci_dup=16 if i == 0 else 0)
-                        for i, (L, ci, co) in enumerate(zip(self.t2.L, self._H_IN, self._H_OUT))]
+            self.sw64 = os.environ.get("SCI_CONV_SW64", "1") != "0"
+            hin, hout = (self._H_IN32, self._H_OUT32) if self.sw64 else (self._H_IN, self._H_OUT)
+            self.t1h = [HalfLayer(L, ci, co, ci_dup=16 if i == 0 else 0) for i, (L, ci, co) in enumerate(zip(self.t1.L, hin, hout))]
+            self.t2h = [HalfLayer(L, ci, co, ci_dup=16 if i == 0 else 0) for i, (L, ci, co) in enumerate(zip(self.t2.L, hin, hout))]
             self.layers_inf = self.t1h + self.t2h
 
     def _block_forward_h(self, Lh, frames, sigma, out):
@@ -626,10 +629,11 @@ class FastDVDnetEngine(_EngineBase):
         f16 = torch.float16
         g = lambda n, shape: self.ws.get("h_" + n, shape, dev, dtype=f16)
         h2, w2, h4, w4 = H // 2, W // 2, H // 4, W // 4
-        a_in = g("in", (B, H, W, 64))
-        call("sci_fastdvd_pack_input_half", ptr(frames), float(sigma), ptr(a_in), B, H, W, stream())
+        c32 = Lh[0].cin_store                # 32 (64-byte pixel rows) or 64: channels per pixel of the 32-channel tensors
+        a_in = g("in", (B, H, W, c32))
+        call("sci_fastdvd_pack_input_half", ptr(frames), float(sigma), ptr(a_in), B, H, W, c32, stream())
         a0 = g("a0", (B, H, W, 96));        self.conv_h(Lh[0], a_in, B, H, W, a0)
-        x0 = g("x0", (B, H, W, 64));        self.conv_h(Lh[1], a0, B, H, W, x0)
+        x0 = g("x0", (B, H, W, c32));       self.conv_h(Lh[1], a0, B, H, W, x0)
         d0a = g("d0a", (B, h2, w2, 64));    self.conv_h(Lh[2], x0, B, H, W, d0a)
         d0b = g("d0b", (B, h2, w2, 64));    self.conv_h(Lh[3], d0a, B, h2, w2, d0b)
         x1 = g("x1", (B, h2, w2, 64));      self.conv_h(Lh[4], d0b, B, h2, w2, x1)

@@ -264,14 +264,14 @@ int sci_conv3x3_wgrad(const sci_wgrad_desc* d, int impl, void* stream);
 int sci_conv_pack_weights(const float* w, float* packed, int Co, int Ci, int groups, int Co_pad, int Ci_pad,
                           int ps, const float* oscale, int transpose_flip, int round_tf32, int ci_dup, void* stream);
 /* fp16 form of the forward packing for sci_conv_desc.half_io layers: packed [9][Co_pad][Ci_pad] IEEE binary16, round to
- * nearest; Ci_pad % 64 == 0 (one 128-byte operand row = 64 channels).  Same grouped / PixelShuffle / ci_dup rules as above
+ * nearest; Ci_pad % 64 == 0 (one 128-byte operand row = 64 channels) or Ci_pad == 32 (64-byte rows).  Same grouped / PixelShuffle / ci_dup rules as above
  * (the fp16 network-boundary packer puts fp16(v) in channel k and fp16(v - fp16(v)) in channel k + ci_dup). */
 int sci_conv_pack_weights_half(const float* w, void* packed, int Co, int Ci, int groups, int Co_pad, int Ci_pad, int ps,
                                int ci_dup, void* stream);
 /* fp16 form of sci_fastdvd_pack_input (packages/fastdvdnet/models.py:185 input block, circular window fastdvdnet.py:115):
- * out [B][H][W][64] binary16, channels 0..11 = fp16 of [f0 RGB, sigma, f1 RGB, sigma, f2 RGB, sigma], 16..27 = the fp16
- * remainders, others zero. */
-int sci_fastdvd_pack_input_half(const float* frames, float sigma, void* out, int B, int H, int W, void* stream);
+ * out [B][H][W][C] binary16 (C = 32 or 64), channels 0..11 = fp16 of [f0 RGB, sigma, f1 RGB, sigma, f2 RGB, sigma], 16..27 =
+ * the fp16 remainders, others zero. */
+int sci_fastdvd_pack_input_half(const float* frames, float sigma, void* out, int B, int H, int W, int C, void* stream);
 /* Data-gradient weights of a STRIDE-2 layer (groups = 1) as a sub-pixel convolution over dz at the low resolution:
  * packed [9][4*Ci_pad][Co_pad]; run sci_conv3x3_dgrad with x = dz [N][Ho][Wo][Co_pad], Cin = Co_pad, Cout = 4*Ci_pad,
  * stride 1, pixel_shuffle = 1 -> dx [N][2Ho][2Wo][Ci_pad].  Replaces "zero-dilate dz, then convolve at full resolution"
