@@ -39,6 +39,7 @@ struct FwdParams {
     int Cstore;       // fp16 storage: channels per pixel of the stored output tensor
     int ks_last;      // see Fwd2Params
     int rb_in, a_bytes;   // bytes per operand row (64: 32 fp16 channels, SWIZZLE_64B; else 128) and per 128-pixel A tile
+    int lo_chunk0;        // > 0: first 32-channel chunk of the activations' remainder half (split accumulators, see the MMA issuer)
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -271,22 +272,35 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
+            // lo_chunk0 > 0 ("3xTF32" layers): the small products - weights' remainder x anything, weights x activations'
+            // remainder (channel chunks >= lo_chunk0) - go to a SECOND accumulator next to the main one and are added in the
+            // epilogue: the tensor core truncates when it accumulates, and 432 sequential accumulations into one fp32 value left
+            // an error floor that the 16 ADMM iterations of the FFDNet loop amplified to 1.2e-3 at 512x512x8
+            const uint32_t d_small = p.lo_chunk0 ? d_tmem + (uint32_t)(p.acc_stride >> 1) : d_tmem;
+            uint32_t small_started = p.lo_chunk0 ? 0u : 1u;
             for (int ks = 0; ks < k_steps; ++ks) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
                 const uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes, b_addr = a_addr + a_bytes;
-                const int ksn = ((ks % p.k_chunks) == p.k_chunks - 1) ? p.ks_last : ks_full;
+                const int kc = ks % p.k_chunks;
+                const int ksn = (kc == p.k_chunks - 1) ? p.ks_last : ks_full;
+                const bool lo_x = p.lo_chunk0 && kc >= p.lo_chunk0;
 #pragma unroll
                 for (int k = 0; k < KCH / 8; ++k) {
-                    if (k < ksn)
-                        tc_mma_elect<HALF>(d_tmem, desc_hi | (uint64_t)(((a_addr + k * 32) & 0x3FFFFu) >> 4),
-                                           desc_hi | (uint64_t)(((b_addr + k * 32) & 0x3FFFFu) >> 4), idesc, (uint32_t)((ks | k) != 0));
+                    if (k < ksn) {
+                        const uint32_t accum = lo_x ? (small_started | (uint32_t)(k != 0)) : (uint32_t)((ks | k) != 0);
+                        tc_mma_elect<HALF>(lo_x ? d_small : d_tmem, desc_hi | (uint64_t)(((a_addr + k * 32) & 0x3FFFFu) >> 4),
+                                           desc_hi | (uint64_t)(((b_addr + k * 32) & 0x3FFFFu) >> 4), idesc, accum);
+                    }
                 }
+                if (lo_x) small_started = 1u;
                 if (p.wsplit) {
 #pragma unroll
                     for (int k = 0; k < KCH / 8; ++k)
-                        tc_mma_elect<HALF>(d_tmem, desc_hi | (uint64_t)(((a_addr + k * 32) & 0x3FFFFu) >> 4),
-                                          desc_hi | (uint64_t)(((b_addr + b_bytes + k * 32) & 0x3FFFFu) >> 4), idesc, 1u);
+                        tc_mma_elect<HALF>(d_small, desc_hi | (uint64_t)(((a_addr + k * 32) & 0x3FFFFu) >> 4),
+                                          desc_hi | (uint64_t)(((b_addr + b_bytes + k * 32) & 0x3FFFFu) >> 4), idesc,
+                                          p.lo_chunk0 ? (small_started | (uint32_t)(k != 0)) : 1u);
+                    small_started = 1u;
                 }
                 tc_commit_elect(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -311,6 +325,12 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 float v[32];
                 const int nc = min(32, p.Cout - c0);
                 if (nc == 32) tmem_ld32(t_row + c0, v); else tmem_ld16(t_row + c0, v);
+                if (p.lo_chunk0) {                       // main + small-products accumulator
+                    float v2[32];
+                    if (nc == 32) tmem_ld32(t_row + (uint32_t)(p.acc_stride >> 1) + c0, v2); else tmem_ld16(t_row + (uint32_t)(p.acc_stride >> 1) + c0, v2);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += v2[j];
+                }
                 if (HALF) {
                     // fp16 storage: 32 columns = 64 bytes of this pixel's row (stride-2 layers: no residual / shuffle / split)
                     if (valid) {
@@ -1118,6 +1138,12 @@ int conv_fwd_tc_launch(const sci_conv_desc* d, void* stream) {
     const int stage_bytes = p.a_bytes + p.Cout * rb_in * (1 + p.wsplit);
     p.stages = min(MAX_STAGES, (216 * 1024) / stage_bytes);
     p.acc_stride = ((p.Cout + 31) / 32) * 32;
+    p.lo_chunk0 = 0;
+    if (p.wsplit && !half && d->lo_channel0 > 0 && d->lo_channel0 % KCH == 0 && d->lo_channel0 < d->Cin && 4 * p.acc_stride <= 512 &&
+        env_int("SCI_CONV_SPLIT_ACC", 1)) {
+        p.lo_chunk0 = d->lo_channel0 / KCH;
+        p.acc_stride *= 2;                               // [main | small products] per accumulator buffer
+    }
     p.tmem_cols = next_pow2_cols(2 * p.acc_stride);
     CUtensorMap tmA, tmB;
     const int cin_store = (half && d->Cin_store) ? d->Cin_store : d->Cin;

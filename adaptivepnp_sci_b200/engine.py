@@ -36,7 +36,8 @@ class ConvDesc(ctypes.Structure):
                 ("pixel_shuffle", ctypes.c_int), ("round_tf32", ctypes.c_int), ("w_split", ctypes.c_int), ("emit_lo", ctypes.c_int),
                 ("planar_in1", _f32p), ("planar_out", _f32p), ("pdl", ctypes.c_int),
                 ("half_io", ctypes.c_int), ("Cin_store", ctypes.c_int), ("Cout_store", ctypes.c_int),
-                ("mask_y", _f32p), ("col_s1", _f32p), ("col_s2", _f32p), ("mask_relu", ctypes.c_int), ("K_used", ctypes.c_int)]
+                ("mask_y", _f32p), ("col_s1", _f32p), ("col_s2", _f32p), ("mask_relu", ctypes.c_int), ("lo_channel0", ctypes.c_int),
+                ("K_used", ctypes.c_int)]
 
 
 class WgradDesc(ctypes.Structure):
@@ -392,6 +393,8 @@ class _EngineBase:
                      L.stride, int(L.relu), int(L.ps), int(self.tf32 and round_out), int(self.tf32 and L.wsplit),
                      int(emit_lo), _dp(planar[0]) if planar else None, _dp(planar[1]) if planar else None,
                      int(self.pdl_chain))
+        if L.dup_in and self.tf32 and L.wsplit:
+            d.lo_channel0 = L.ci_half                # "3xTF32": the remainder half of the input starts here (split accumulators)
         if self.profile is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()

@@ -230,6 +230,10 @@ typedef struct sci_conv_desc {
     float* col_s1;
     float* col_s2;
     int mask_relu;
+    int lo_channel0;        /* TC only, with w_split on an input written with emit_lo: first channel of the remainder half
+                               [tf32(v) | tf32(v - tf32(v))] (= the producing layer's Cout).  The small products then accumulate
+                               in their own TMEM accumulator and are added in the epilogue (fewer truncating accumulations into
+                               the main sum).  0 = one accumulator */
     int K_used;             /* TC only. > 0: only the first K_used input channels (K columns of the packed weights) can be non-zero;
                                the MMAs over the all-zero tail of the last 128-byte channel chunk are skipped (results unchanged).
                                0 = Cin */

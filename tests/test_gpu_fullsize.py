@@ -197,14 +197,11 @@ def test_config3_ffdnet_512_vs_reference(warm512, engine_impl, monkeypatch):
                                    x0_bayer=np2tch_cuda(r1[0]), X_orig=orig, model_denoise=m, model_demosaic=None,
                                    show_iqa=True, demosaic_method='malvar2004', lr_=2e-6, interval_iter=6,
                                    logf=io.StringIO(), update_=True, update_per_iter=2)
-    # MEASURED (tools/ffdnet_dev.py): fp32 engine vs the reference 1.2e-5; tensor-core engine 1.23e-3 max-abs (mean-abs 9e-5),
-    # of which 1.3e-3 already without any fine-tune.  FFDNet returns the image itself and the 16 ADMM iterations integrate its
-    # error through the dual variables (the loop amplifies even fp32 summation-order differences from 1e-7 to 1e-5), so the
-    # residual error of the "3xTF32" scheme - the truncating fp32 accumulation of the tensor core over 324 sequential MMAs per
-    # output, ~1e-5 per pass - ends 23 % ABOVE north_star's 1e-3 max-abs at this size (it is 3.4e-4 on the 64x64 / 7-iteration
-    # golden).  The PSNR criterion (0.05 dB, every iteration and every frame) holds with a wide margin.  The bound below is
-    # what the kernel delivers, not what north_star asks; DESIGN.md lists it as an open deviation.
-    tol = {"ref": 2e-4, "tc": 2e-3}[engine_impl]
+    # MEASURED (tools/ffdnet_dev.py): fp32 engine vs the reference 1.2e-5; tensor-core engine 2.6e-4.  (It was 1.23e-3 - above
+    # north_star's bound - while all products of the "3xTF32" scheme accumulated into ONE TMEM accumulator: the tensor core
+    # truncates when it accumulates, and FFDNet returns the image itself, so the 16 ADMM iterations integrate that bias through
+    # the dual variables.  The small products now have their own accumulator, sci_conv_desc.lo_channel0.)
+    tol = {"ref": 2e-4, "tc": 1e-3}[engine_impl]
     _check_against_gold(d, "c3", r[1], r[0], tol)
     assert np.max(np.abs(np.array(r[4]) - d["c3_psnr_all"])) < 0.05
     assert np.max(np.abs(np.array(r[2]) - d["c3_psnr"])) < 0.05 and np.max(np.abs(np.array(r[3]) - d["c3_ssim"])) < 1e-3
