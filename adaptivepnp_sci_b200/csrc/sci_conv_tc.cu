@@ -40,6 +40,7 @@ struct FwdParams {
     int ks_last;      // see Fwd2Params
     int rb_in, a_bytes;   // bytes per operand row (64: 32 fp16 channels, SWIZZLE_64B; else 128) and per 128-pixel A tile
     int lo_chunk0;        // > 0: first 32-channel chunk of the activations' remainder half (split accumulators, see the MMA issuer)
+    int pdl;              // launched with programmatic stream serialization
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -237,9 +238,13 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_slot, 0);
     const int k_steps = 9 * p.k_chunks;
+    // programmatic dependent launch inside inference chains (see conv_fwd2_tc_kernel): the next kernel may start its prologue
+    // now; this one touches its activations / outputs only after the previous kernel of the stream has completed
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0) {
         // ===== TMA producer (warp-uniform loop, one elected lane issues) =====
+        if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
         int stage = 0; uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, n = tile / (p.tiles_w * p.tiles_h);
@@ -314,6 +319,7 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int m = q * 32 + lane, hh = m / TILE_W, ww = m % TILE_W;
         const int Cq = p.Cout >> 2;
         int acc = 0; uint32_t acc_phase = 0;
+        if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");      // residual reads / output writes after the previous kernel
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, n = tile / (p.tiles_w * p.tiles_h);
             const int ho = th * TILE_H + hh, wo = tw * TILE_W + ww;
@@ -1163,6 +1169,19 @@ int conv_fwd_tc_launch(const sci_conv_desc* d, void* stream) {
         if (dev >= 0 && dev < 64) attr_set[dev][half ? 1 : 0] = true;
     }
     const int grid = min(p.num_tiles, SCI_NUM_SMS);
+    p.pdl = (d->pdl && env_int("SCI_CONV_PDL", 1)) ? 1 : 0;
+    if (p.pdl) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = sci_stream(stream);
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaError_t e = half ? cudaLaunchKernelEx(&cfg, conv_fwd_tc_kernel<true>, tmA, tmB, p)
+                             : cudaLaunchKernelEx(&cfg, conv_fwd_tc_kernel<false>, tmA, tmB, p);
+        if (e != cudaSuccess) return sci_fail(SCI_ELAUNCH, "conv tc fwd (PDL launch)", e);
+        return SCI_OK;
+    }
     if (half) conv_fwd_tc_kernel<true><<<grid, TC_THREADS, smem, sci_stream(stream)>>>(tmA, tmB, p);
     else      conv_fwd_tc_kernel<false><<<grid, TC_THREADS, smem, sci_stream(stream)>>>(tmA, tmB, p);
     SCI_CHECK_LAUNCH("conv tc fwd");
