@@ -484,7 +484,9 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t b_bytes = (uint32_t)p.Cout * (uint32_t)p.rb_in;
     const uint32_t w_bytes = p.resident ? 9u * (uint32_t)p.k_chunks * b_bytes : 0u;
-    const uint32_t stage_bytes = (uint32_t)p.a_stage + (p.resident ? 0u : 3u * b_bytes);
+    // streamed weights with two output rows per tile (wpair): a stage carries BOTH input rows a filter row needs
+    const bool wpair = !p.resident && p.R == 2;
+    const uint32_t stage_bytes = (uint32_t)p.a_stage * (wpair ? 2u : 1u) + (p.resident ? 0u : 3u * b_bytes);
     const uint32_t ring_base = smem_base + w_bytes;
     const uint32_t stage_out_base = ring_base + (uint32_t)p.stages * stage_bytes;   // 4 EPI_WG warps x out_bufs x 4 KB store staging
 
@@ -538,6 +540,28 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             const int wt = tile % p.tiles_w, hg = (tile / p.tiles_w) % p.tiles_h, n = tile / (p.tiles_w * p.tiles_h);
             const int y0 = hg * p.R, rows = min(p.R, p.H - y0);
+            if (wpair) {
+                // Streamed weights, two output rows per tile: per (filter row r, channel chunk) ONE stage holds the weight tiles of
+                // the three horizontal taps and the two input rows y0 + r - 1, y0 + r they multiply - the weight fill per output
+                // row halves (the 128-channel layers were bound by it: 390 KB per row tile at ~42 B/cycle/SM from L2)
+                for (int r = 0; r < 3; ++r) {
+                    for (int kc = 0; kc < p.k_chunks; ++kc) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1u);
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(&full_bar[stage], 2u * (uint32_t)p.row_bytes + 3u * b_bytes);
+                            const uint32_t a_dst = ring_base + (uint32_t)stage * stage_bytes;
+                            const int cc = kc * (HALF ? (p.rb_in >> 1) : KCH);
+                            tma_load_4d(a_dst, &tmA, &full_bar[stage], cc, wt * 128 - 1, y0 + r - 1, n);
+                            tma_load_4d(a_dst + (uint32_t)p.a_stage, &tmA, &full_bar[stage], cc, wt * 128 - 1, y0 + r, n);
+                            for (int s = 0; s < 3; ++s)
+                                tma_load_3d(a_dst + 2u * (uint32_t)p.a_stage + (uint32_t)s * b_bytes, &tmB, &full_bar[stage], cc, p.col0, r * 3 + s);
+                        }
+                        __syncwarp();
+                        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+                continue;
+            }
             // input rows y0-1 .. y0+rows: row j feeds output row t = j - r as filter row r (R = 1: j is the filter row)
             for (int j = 0; j < rows + 2; ++j) {
                 for (int kc = 0; kc < p.k_chunks; ++kc) {
@@ -596,6 +620,34 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                                     for (int k = 0; k < KCH / 8; ++k)
                                         if (k < ksn) mma_lo<HALF>(d_base, a_lo + s * tapu + k * 2, b_lo + s * b_step + k * 2, idesc, (s | k) ? 1u : first, p.desc_hi);
+                                }
+                            }
+                            tc_commit(&empty_bar[stage]);
+                        }
+                        __syncwarp();
+                        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            } else if (wpair) {
+                for (int r = 0; r < 3; ++r) {
+                    for (int kc = 0; kc < p.k_chunks; ++kc) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        if (leader) {
+                            const uint32_t a_addr = ring_base + (uint32_t)stage * stage_bytes;
+                            const int ksn = (kc == p.k_chunks - 1) ? p.ks_last : ks_full;
+                            const uint32_t b_lo = desc_lo(a_addr + 2u * (uint32_t)p.a_stage);
+                            const uint32_t first = (uint32_t)((r | kc) != 0);
+                            if (!(p.dbg & 1)) {
+                                for (int t = 0; t < rows; ++t) {        // input row y0 + r - 1 + t is filter row r of output row t
+                                    const uint32_t a_lo = desc_lo(a_addr + (uint32_t)t * (uint32_t)p.a_stage);
+                                    const uint32_t d_tmem = d_base + (uint32_t)(t * p.acc_stride);
+#pragma unroll
+                                    for (int s = 0; s < 3; ++s) {
+#pragma unroll
+                                        for (int k = 0; k < KCH / 8; ++k)
+                                            if (k < ksn) mma_lo<HALF>(d_tmem, a_lo + s * tapu + k * 2, b_lo + s * b_tile_lo + k * 2, idesc, (s | k) ? 1u : first, p.desc_hi);
+                                    }
                                 }
                             }
                             tc_commit(&empty_bar[stage]);
@@ -695,7 +747,8 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const float lower = p.relu ? 0.f : -INFINITY;
         const long pl_plane = (long)p.H * p.W;
         constexpr int PIN_ROWS = (8 + EPI_WG - 1) / EPI_WG;   // planar mode: rows of a super-tile (R <= 8) per warpgroup
-        const uint32_t sbuf0 = stage_out_base + (uint32_t)((g * 4 + q) * p.out_bufs) * 4096u;
+        const uint32_t tile_b = (uint32_t)p.rb_out * 32u;      // staging tile of a warp: 32 pixel rows of the stored output
+        const uint32_t sbuf0 = stage_out_base + (uint32_t)((g * 4 + q) * p.out_bufs) * tile_b;
         int acc = 0; uint32_t acc_phase = 0;
         uint32_t st_cnt = 0;
         if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");      // residual / in1 come from earlier kernels
@@ -800,7 +853,7 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             for (int j = 0; j < 16; ++j) hv[hb * 16 + j] = 0u;
                         }
                     }
-                    const uint32_t sbuf = sbuf0 + (p.out_bufs == 2 ? (st_cnt & 1) * 4096u : 0u);
+                    const uint32_t sbuf = sbuf0 + (p.out_bufs == 2 ? (st_cnt & 1) * tile_b : 0u);
                     if (lane == 0) {
                         if (p.out_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                         else                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -990,7 +1043,7 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         // coalesced path: the warp's 32 pixels x 32 channels go through a 128B-swizzled 4 KB staging tile and
                         // leave as ONE TMA store (box {32 ch, 32 px}; PixelShuffle = element stride 2 on the pixel axis of a map
                         // over the up-sampled tensor); out-of-image pixels are clipped by TMA
-                        const uint32_t sbuf = sbuf0 + (p.out_bufs == 2 ? (st_cnt & 1) * 4096u : 0u);
+                        const uint32_t sbuf = sbuf0 + (p.out_bufs == 2 ? (st_cnt & 1) * tile_b : 0u);
                         if (lane == 0) {
                             if (p.out_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                             else                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -1254,6 +1307,7 @@ int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream, int col0, int ncol
     // shared-memory plan: [resident weights] [pipeline stages] [store staging: 4 * epi_wg warps x out_bufs x 4 KB].
     // Two epilogue warpgroups (see the kernel comment) unless their extra staging would cost the weights their residency.
     const int total_budget = 214 * 1024;
+    const int tile_b = 32 * rb_out;                   // staging tile of one epilogue warp (fp32 path: rb_out = 128)
     int out_stage = 0, budget = 0, epi_wg = 2;
     const int epi_env = env_int("SCI_CONV_EPI_WG", 0);
     // measured per layer (tools/pass_layers.py): the second warpgroup pays where the epilogue work per MMA is high (K <= 32:
@@ -1262,22 +1316,22 @@ int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream, int col0, int ncol
     const int epi_first = epi_env ? (epi_env == 1 ? 1 : 2) : ((half || p.k_chunks <= 1 || d->residual || d->mask_y) ? 2 : 1);
     for (epi_wg = epi_first; epi_wg >= 1; --epi_wg) {
         for (p.out_bufs = ((epi_wg == 2 || d->mask_y) ? 1 : 2); p.out_bufs >= 1; --p.out_bufs) {
-            out_stage = p.tma_store ? 4 * epi_wg * p.out_bufs * 4096 : 0;
+            out_stage = p.tma_store ? 4 * epi_wg * p.out_bufs * tile_b : 0;
             budget = total_budget - out_stage;
             p.resident = (w_bytes + 3 * a_stage <= budget) ? 1 : 0;
             const int sb = a_stage + (p.resident ? 0 : 3 * b_bytes);
             const int st = (budget - (p.resident ? w_bytes : 0)) / sb;
-            const bool would_be_resident = w_bytes + 3 * a_stage <= total_budget - (p.tma_store ? 4 * epi_wg * 4096 : 0);
+            const bool would_be_resident = w_bytes + 3 * a_stage <= total_budget - (p.tma_store ? 4 * epi_wg * tile_b : 0);
             if ((p.resident || !would_be_resident) && st >= 3) break;
             if (p.out_bufs == 1) break;
         }
-        const bool resident_with_one = w_bytes + 3 * a_stage <= total_budget - (p.tma_store ? 4 * 4096 : 0);
+        const bool resident_with_one = w_bytes + 3 * a_stage <= total_budget - (p.tma_store ? 4 * tile_b : 0);
         // fp16 chains: the MMAs are twice as fast, so the epilogue decides more often - two warpgroups even where that costs
         // the weights their residency (64->128 + PixelShuffle: 0.215 ms resident with one group, 0.135 ms streamed with two)
         if (epi_wg == 1 || epi_env == 2 || half || p.resident || !resident_with_one) break;
     }
     if (env_int("SCI_CONV_RESIDENT", 1) == 0) p.resident = 0;
-    const int stage_bytes = a_stage + (p.resident ? 0 : 3 * b_bytes);
+    int stage_bytes = a_stage + (p.resident ? 0 : 3 * b_bytes);
     p.stages = min(MAX_STAGES, (budget - (p.resident ? w_bytes : 0)) / stage_bytes);
     if (p.stages < 2) return sci_fail(SCI_EUNSUPPORTED, "conv tc v2: pipeline does not fit");
     p.acc_stride = p.Cout;
@@ -1286,9 +1340,21 @@ int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream, int col0, int ncol
     // resident-weight layers are bound by ring_bytes / load round-trip latency, i.e. by bytes per output tile.
     // R accumulators x 2 buffers must fit the 512 TMEM columns; streamed weights keep R = 1 (their B tiles are per filter row).
     p.R = 1;
+    if (!p.resident && 2 * 2 * p.acc_stride <= 512 && p.H >= 2 && env_int("SCI_CONV_WPAIR", 1)) {
+        // streamed weights: two output rows per tile share every weight tile (a stage then carries two input rows)
+        // ... where the image is large enough that halving the tile count does not cost a wave of the 148 persistent CTAs
+        // (8x128x128: 1024 one-row tiles = 6.9 waves; 512 two-row tiles would be 3.5 -> 4 waves of twice the work)
+        const int sb2 = 2 * a_stage + 3 * b_bytes;
+        const long tiles2 = (long)p.tiles_w * ((p.H + 1) / 2) * p.N;
+        if (budget / sb2 >= 2 && tiles2 >= 8L * SCI_NUM_SMS) p.R = 2;
+    }
     if (p.resident) {
         const int rmax = env_int("SCI_CONV_ROWS", 8);
         while (p.R * 2 <= rmax && 2 * (p.R * 2) * p.acc_stride <= 512 && p.R * 2 <= p.H) p.R *= 2;
+    }
+    if (!p.resident && p.R == 2) {
+        stage_bytes = 2 * a_stage + 3 * b_bytes;
+        p.stages = min(MAX_STAGES, budget / stage_bytes);
     }
     p.stack = (p.resident && p.R >= 2 && 3 * p.Cout <= 256 && env_int("SCI_CONV_STACK", 1)) ? 1 : 0;
     p.tiles_h = (p.H + p.R - 1) / p.R;
@@ -1351,6 +1417,10 @@ int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream, int col0, int ncol
     }
     const int grid = min(p.num_tiles, SCI_NUM_SMS);
     const int threads = 128 + 128 * epi_wg;
+    if (env_int("SCI_CONV_VERBOSE", 0))
+        fprintf(stderr, "conv v2 plan: %dx%d Cin %d -> %d cols (+%d) half %d ps %d mode %d | resident %d stages %d R %d stack %d epi_wg %d out_bufs %d "
+                "rb %d/%d smem %zu KB tiles %d\n", d->H, d->W, d->Cin, ncols, col0, (int)half, p.ps, mode, p.resident, p.stages, p.R, p.stack,
+                epi_wg, p.out_bufs, rb_in, rb_out, smem / 1024, p.num_tiles);
     p.pdl = (d->pdl && env_int("SCI_CONV_PDL", 1)) ? 1 : 0;
     if (p.pdl) {
         cudaLaunchConfig_t cfg = {};
