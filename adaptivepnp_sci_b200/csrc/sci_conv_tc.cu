@@ -41,6 +41,9 @@ struct FwdParams {
     int rb_in, a_bytes;   // bytes per operand row (64: 32 fp16 channels, SWIZZLE_64B; else 128) and per 128-pixel A tile
     int lo_chunk0;        // > 0: first 32-channel chunk of the activations' remainder half (split accumulators, see the MMA issuer)
     int pdl;              // launched with programmatic stream serialization
+    int tps;              // filter taps per pipeline stage: 1, or 3 (one filter row) when three (A, B) tile pairs fit a stage -
+                          // the profile of the thin stride-2 layers showed both single-thread loops (producer, issuer)
+                          // instruction-bound at ~80-120 instructions per 12 KB stage
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -213,7 +216,8 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t b_bytes = (uint32_t)p.Cout * (uint32_t)p.rb_in;
     const uint32_t a_bytes = (uint32_t)p.a_bytes;
-    const uint32_t stage_bytes = a_bytes + b_bytes * (1u + (uint32_t)p.wsplit);   // wsplit: tf32 hi + remainder weights
+    const uint32_t b_tap = b_bytes * (1u + (uint32_t)p.wsplit);                   // wsplit: tf32 hi + remainder weights
+    const uint32_t stage_bytes = (uint32_t)p.tps * (a_bytes + b_tap);             // [A tiles of the stage's taps | their B tiles]
 
     for (int i = threadIdx.x; i < p.Cout; i += TC_THREADS) {
         s_scale[i] = p.scale ? p.scale[i] : 1.f;
@@ -237,7 +241,7 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_slot, 0);
-    const int k_steps = 9 * p.k_chunks;
+    const int k_steps = (9 / p.tps) * p.k_chunks;
     // programmatic dependent launch inside inference chains (see conv_fwd2_tc_kernel): the next kernel may start its prologue
     // now; this one touches its activations / outputs only after the previous kernel of the stream has completed
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -249,16 +253,20 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, n = tile / (p.tiles_w * p.tiles_h);
             const int iw0 = tw * TILE_W * p.stride - 1, ih0 = th * TILE_H * p.stride - 1;
-            for (int tap = 0; tap < 9; ++tap) {
-                const int r = tap / 3, s = tap % 3;
+            const int kstep_el = HALF ? (p.rb_in >> 1) : KCH;
+            for (int tap0 = 0; tap0 < 9; tap0 += p.tps) {
                 for (int kc = 0; kc < p.k_chunks; ++kc) {
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
                     if (elect_one()) {
                         mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
                         const uint32_t a_dst = smem_base + (uint32_t)stage * stage_bytes;
-                        tma_load_4d(a_dst, &tmA, &full_bar[stage], kc * (HALF ? (p.rb_in >> 1) : KCH), iw0 + s, ih0 + r, n);
-                        tma_load_3d(a_dst + a_bytes, &tmB, &full_bar[stage], kc * (HALF ? (p.rb_in >> 1) : KCH), 0, tap);
-                        if (p.wsplit) tma_load_3d(a_dst + a_bytes + b_bytes, &tmB, &full_bar[stage], kc * (HALF ? (p.rb_in >> 1) : KCH), 0, tap + 9);
+                        const uint32_t b_dst = a_dst + (uint32_t)p.tps * a_bytes;
+                        for (int t = 0; t < p.tps; ++t) {
+                            const int tap = tap0 + t, r = tap / 3, s = tap - 3 * r;
+                            tma_load_4d(a_dst + (uint32_t)t * a_bytes, &tmA, &full_bar[stage], kc * kstep_el, iw0 + s, ih0 + r, n);
+                            tma_load_3d(b_dst + (uint32_t)t * b_tap, &tmB, &full_bar[stage], kc * kstep_el, 0, tap);
+                            if (p.wsplit) tma_load_3d(b_dst + (uint32_t)t * b_tap + b_bytes, &tmB, &full_bar[stage], kc * kstep_el, 0, tap + 9);
+                        }
                     }
                     __syncwarp();
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -283,32 +291,36 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             // an error floor that the 16 ADMM iterations of the FFDNet loop amplified to 1.2e-3 at 512x512x8
             const uint32_t d_small = p.lo_chunk0 ? d_tmem + (uint32_t)(p.acc_stride >> 1) : d_tmem;
             uint32_t small_started = p.lo_chunk0 ? 0u : 1u;
+            int kc = 0;
             for (int ks = 0; ks < k_steps; ++ks) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes, b_addr = a_addr + a_bytes;
-                const int kc = ks % p.k_chunks;
+                const uint32_t a0 = smem_base + (uint32_t)stage * stage_bytes, b0 = a0 + (uint32_t)p.tps * a_bytes;
                 const int ksn = (kc == p.k_chunks - 1) ? p.ks_last : ks_full;
                 const bool lo_x = p.lo_chunk0 && kc >= p.lo_chunk0;
+                for (int t = 0; t < p.tps; ++t) {
+                    const uint32_t a_addr = a0 + (uint32_t)t * a_bytes, b_addr = b0 + (uint32_t)t * b_tap;
 #pragma unroll
-                for (int k = 0; k < KCH / 8; ++k) {
-                    if (k < ksn) {
-                        const uint32_t accum = lo_x ? (small_started | (uint32_t)(k != 0)) : (uint32_t)((ks | k) != 0);
-                        tc_mma_elect<HALF>(lo_x ? d_small : d_tmem, desc_hi | (uint64_t)(((a_addr + k * 32) & 0x3FFFFu) >> 4),
-                                           desc_hi | (uint64_t)(((b_addr + k * 32) & 0x3FFFFu) >> 4), idesc, accum);
+                    for (int k = 0; k < KCH / 8; ++k) {
+                        if (k < ksn) {
+                            const uint32_t accum = lo_x ? (small_started | (uint32_t)(k != 0)) : (uint32_t)((ks | t | k) != 0);
+                            tc_mma_elect<HALF>(lo_x ? d_small : d_tmem, desc_hi | (uint64_t)(((a_addr + k * 32) & 0x3FFFFu) >> 4),
+                                               desc_hi | (uint64_t)(((b_addr + k * 32) & 0x3FFFFu) >> 4), idesc, accum);
+                        }
                     }
-                }
-                if (lo_x) small_started = 1u;
-                if (p.wsplit) {
+                    if (lo_x) small_started = 1u;
+                    if (p.wsplit) {
 #pragma unroll
-                    for (int k = 0; k < KCH / 8; ++k)
-                        tc_mma_elect<HALF>(d_small, desc_hi | (uint64_t)(((a_addr + k * 32) & 0x3FFFFu) >> 4),
-                                          desc_hi | (uint64_t)(((b_addr + b_bytes + k * 32) & 0x3FFFFu) >> 4), idesc,
-                                          p.lo_chunk0 ? (small_started | (uint32_t)(k != 0)) : 1u);
-                    small_started = 1u;
+                        for (int k = 0; k < KCH / 8; ++k)
+                            tc_mma_elect<HALF>(d_small, desc_hi | (uint64_t)(((a_addr + k * 32) & 0x3FFFFu) >> 4),
+                                              desc_hi | (uint64_t)(((b_addr + b_bytes + k * 32) & 0x3FFFFu) >> 4), idesc,
+                                              p.lo_chunk0 ? (small_started | (uint32_t)(k != 0)) : 1u);
+                        small_started = 1u;
+                    }
                 }
                 tc_commit_elect(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                if (++kc == p.k_chunks) kc = 0;
             }
             tc_commit_elect(&tfull_bar[acc]);                // accumulator complete -> epilogue
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
@@ -1194,7 +1206,9 @@ int conv_fwd_tc_launch(const sci_conv_desc* d, void* stream) {
     p.k_chunks = p.Cin / kch;
     p.rb_in = rb_in;
     p.a_bytes = TILE_W * TILE_H * rb_in;
-    const int stage_bytes = p.a_bytes + p.Cout * rb_in * (1 + p.wsplit);
+    int stage_bytes = p.a_bytes + p.Cout * rb_in * (1 + p.wsplit);
+    p.tps = ((216 * 1024) / (3 * stage_bytes) >= 3 && env_int("SCI_CONV_TPS", 3) == 3) ? 3 : 1;
+    stage_bytes *= p.tps;
     p.stages = min(MAX_STAGES, (216 * 1024) / stage_bytes);
     p.acc_stride = ((p.Cout + 31) / 32) * 32;
     p.lo_chunk0 = 0;

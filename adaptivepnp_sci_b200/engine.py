@@ -493,16 +493,18 @@ class FFDNetEngine(_EngineBase):
     """models/network_ffdnet.py:54-69 on the native kernels, all frames of a cube as one batch."""
 
     def __init__(self, module):
-        convs = module.conv_layers()
+        # conv_layers(): convolutions in execution order, each a Conv2d or a (Conv2d, BatchNorm2d) pair (the IPOL flavour,
+        # ffdnet_ipol_models.py, has inference-mode BatchNorm between its inner layers)
+        convs = [c if isinstance(c, tuple) else (c, None) for c in module.conv_layers()]
         layers = []
-        for i, c in enumerate(convs):
+        for i, (c, bn) in enumerate(convs):
             last = i == len(convs) - 1
             # FFDNet returns the denoised image itself (no residual), so weight-rounding error reaches the output
             # undamped: on the TF32 path its weights are kept as tf32 hi + remainder (north_star 1e-3 max-abs bound).
             # This also holds for the TRAINING forward: with plain TF32 weights there (1.75 ms instead of 3.5 ms per pass at
             # 8x512x512, tools/time_ffdnet_train.py) the Adam-normalised updates change enough to move the final
             # reconstruction by 5e-3 on the golden online loop (3.4e-4 with the split), so the split stays on.
-            layers.append(ConvLayer(c, None, relu=not last, first=(i == 0), wsplit=(default_impl() == IMPL_TC)
+            layers.append(ConvLayer(c, bn, relu=not last, first=(i == 0), wsplit=(default_impl() == IMPL_TC)
                                     and os.environ.get("SCI_FFDNET_TRAIN_WSPLIT", "1") != "0"))
         super().__init__(module, layers)
         # inference on the TF32 path uses "3xTF32": every activation is stored as tf32 hi + remainder and every weight
@@ -510,8 +512,8 @@ class FFDNetEngine(_EngineBase):
         # plain TF32 rounding reaches the output undamped and is then integrated by the ADMM dual variables)
         self.layers_inf = None
         if self.tf32:
-            self.layers_inf = [ConvLayer(c, None, relu=(i < len(convs) - 1), first=(i == 0), wsplit=True, dup_in=(i > 0))
-                               for i, c in enumerate(convs)]
+            self.layers_inf = [ConvLayer(c, bn, relu=(i < len(convs) - 1), first=(i == 0), wsplit=True, dup_in=(i > 0))
+                               for i, (c, bn) in enumerate(convs)]
         self.in_nc, self.out_nc = module.in_nc, module.out_nc
         if (self.in_nc, self.out_nc) not in ((3, 3), (1, 1)):
             raise NotImplementedError("native FFDNet engine: colour (3->3) and gray (1->1) models")

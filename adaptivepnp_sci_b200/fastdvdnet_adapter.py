@@ -305,12 +305,23 @@ def denoise_planar(u, pb, sigma, model, lr, do_update, update_per_iter, grad_syn
 
 
 def fastdvdnet_seqdenoise(seq, noise_std, windsize, model, train=None):
-    """fastdvdnet.py:82-146 — seq [N,3,H,W] -> [N,3,H,W], circular 5-frame window."""
+    """fastdvdnet.py:82-146 — seq [N,C,H,W] -> [N,C,H,W], circular 5-frame window (C = 3, or 1 with the gray model, whose
+    frames travel as the first plane of a colour cube: fastdvdnet_models.FastDVDnet)."""
     if windsize != NUM_IN_FR_EXT:
         raise NotImplementedError("window size 5 only")
-    padded, H, W = ops.pad_to_multiple(seq.contiguous().float(), 4)                     # reflect pad to x4 (:119-127)
-    out = _unwrap(model).engine().forward(padded, float(noise_std.flatten()[0]), train=False)
-    out = ops.crop_to(out, H, W).clone()                                                # un-pad (:134-141)
+    net = _unwrap(model)
+    gray = net.num_color_channels == 1
+    if seq.shape[1] != net.num_color_channels:
+        raise SciError("sequence has %d channels, the model %d" % (seq.shape[1], net.num_color_channels))
+    seq = seq.contiguous().float()
+    if gray:
+        seq3 = seq.new_zeros((seq.shape[0], 3, seq.shape[2], seq.shape[3]))
+        seq3[:, 0:1] = seq
+        seq = seq3
+    padded, H, W = ops.pad_to_multiple(seq, 4)                                          # reflect pad to x4 (:119-127)
+    out = net.engine().forward(padded, float(noise_std.flatten()[0]), train=False)
+    out = ops.crop_to(out, H, W)                                                        # un-pad (:134-141)
+    out = out[:, 0:1].clone() if gray else out.clone()
     return (out, model) if train else out
 
 
@@ -320,7 +331,8 @@ def fastdvdnet_denoiser_full_tensor_v2(vnoisy, sigma, y_bayer=None, Phi=None, mo
     """vnoisy [H,W,3,B] CUDA, y_bayer [h,w,4], Phi [h,w,B,4] -> outv [H,W,3,B] (or ``(outv, model)``)."""
     from .utils_image import fourCh2OneCh
     if gray:
-        raise NotImplementedError("gray FastDVDnet: the 1-channel model class / model_gray.pth are absent from the reference")
+        raise NotImplementedError("the full-tensor adapter serves the Bayer solvers (colour cube [H,W,3,B]); the gray model "
+                                  "runs through the frame-wise fastdvdnet_denoiser(gray=True)")
     vnoisy = vnoisy.contiguous().float()
     H, W, _, B = vnoisy.shape
     v = ops.pixlast_to_planar(vnoisy, 3, B).view(B, 3, H, W)
@@ -339,19 +351,24 @@ def fastdvdnet_denoiser_full_tensor_v2(vnoisy, sigma, y_bayer=None, Phi=None, mo
 
 
 def fastdvdnet_denoiser(vnoisy, sigma, model=None, useGPU=True, lr_=0.000001, updata_=False, gray=False):
-    """packages/fastdvdnet/test_fastdvdnet.py:149-235 - frame-wise colour adapter: numpy ``vnoisy`` [H,W,F,3] in [0,1] ->
-    numpy [H,W,F,3], whole circular sequence through ``fastdvdnet_seqdenoise``.
+    """packages/fastdvdnet/test_fastdvdnet.py:149-235 - frame-wise adapter: numpy ``vnoisy`` [H,W,F,3] (``gray=True``:
+    [H,W,F], with the single-channel model ``FastDVDnet(num_color_channels=1)``) in [0,1] -> numpy of the same shape, the
+    whole circular sequence through ``fastdvdnet_seqdenoise``.
 
     Not on the hot path (the solvers call ``fastdvdnet_denoiser_full_tensor_v2``); kept for API parity.
-    ``gray=True`` needs the single-channel FastDVDnet whose class and weights (``model_gray.pth``) are absent from the
-    reference tree (.MISSING_LARGE_BLOBS), and ``updata_=True`` takes one Adam step on MSE(input, output) - a loss whose
-    backward is not built here; both raise."""
-    if gray:
-        raise NotImplementedError("gray FastDVDnet: the 1-channel model class / model_gray.pth are absent from the reference")
+    ``updata_=True`` takes one Adam step on MSE(input, output) - a self-loss no script uses and whose backward is not
+    built here; it raises."""
     if updata_:
         raise NotImplementedError("fastdvdnet_denoiser(updata_=True) (MSE(input, output) self-loss) is not on any script's path; "
                                   "the online adaptation of the solvers is fastdvdnet_denoiser_full_tensor_v2")
-    v = torch.from_numpy(np.ascontiguousarray(vnoisy, dtype=np.float32)).cuda()           # [H,W,F,3]
-    seq = v.permute(2, 3, 0, 1).contiguous()                                                # :215 -> [F,3,H,W]
+    if model is None:
+        raise SciError("model is required")
+    v = torch.from_numpy(np.ascontiguousarray(vnoisy, dtype=np.float32)).cuda()           # [H,W,F,3] / [H,W,F]
+    if gray:
+        v = v.unsqueeze(3)                                                                  # :212-213
+    seq = v.permute(2, 3, 0, 1).contiguous()                                                # :215 -> [F,C,H,W]
     out = fastdvdnet_seqdenoise(seq, torch.tensor([float(sigma)], device=seq.device), NUM_IN_FR_EXT, model)
-    return out.permute(2, 3, 0, 1).contiguous().cpu().numpy()                              # :226-230
+    out = out.permute(2, 3, 0, 1)                                                           # :226
+    if gray:
+        out = out.squeeze(3)                                                                # :227-228
+    return out.contiguous().cpu().numpy()

@@ -82,24 +82,65 @@ class DenBlock(nn.Module):
 
 
 class FastDVDnet(nn.Module):
+    """models.py:200-253.  ``num_color_channels=1`` (the grayscale model of ``fastdvdnet_denoiser(gray=True)``,
+    test_fastdvdnet.py:149-235) keeps the reference's parameter shapes (``inc`` 3 x (1+1) -> 90 in 3 groups, ``outc``
+    32 -> 1) and runs on the colour engine through an exact embedding: a colour-shaped twin holds the same weights with
+    zeros in the rows / columns of the two missing colour planes, the frames enter as its first plane, and its first
+    output plane is the result - the zero terms add nothing to any accumulator."""
+
     def __init__(self, num_input_frames=5, num_color_channels=3):
         super().__init__()
-        if num_input_frames != 5 or num_color_channels != 3:
-            raise NotImplementedError("the hot path uses the 5-frame colour model (NUM_IN_FR_EXT = 5)")
+        if num_input_frames != 5 or num_color_channels not in (1, 3):
+            raise NotImplementedError("5-frame models (NUM_IN_FR_EXT = 5) with 3 (colour) or 1 (gray) channels")
         self.num_input_frames = num_input_frames
         self.num_color_channels = num_color_channels
         self.temp1 = DenBlock(3, num_color_channels)
         self.temp2 = DenBlock(3, num_color_channels)
         self._engine = None
+        self._twin = None
+        self._twin_version = None
+
+    def _colour_twin(self):
+        own = dict(self.state_dict())
+        dev = next(self.parameters()).device
+        if self._twin is None or next(self._twin[0].parameters()).device != dev:
+            self._twin = (FastDVDnet(5, 3).to(dev),)          # in a tuple: NOT a sub-module (state_dict stays the gray model's)
+            self._twin_version = None
+        twin = self._twin[0]
+        twin.train(self.training)
+        version = tuple(int(t._version) for t in own.values()) + tuple(t.data_ptr() for t in own.values())
+        if version != self._twin_version:
+            with torch.no_grad():
+                for k, dst in twin.state_dict().items():
+                    src = own[k]
+                    if src.shape == dst.shape:
+                        dst.copy_(src)
+                    elif k.endswith("inc.convblock.0.weight"):        # per frame group [y, sigma] -> [r, g, b, sigma]
+                        dst.zero_()
+                        dst[:, 0].copy_(src[:, 0])
+                        dst[:, 3].copy_(src[:, 1])
+                    elif k.endswith("outc.convblock.3.weight"):       # 32 -> 1 becomes the first of 32 -> 3
+                        dst.zero_()
+                        dst[0:1].copy_(src)
+                    else:
+                        raise RuntimeError("gray FastDVDnet: unexpected parameter shape for " + k)
+            self._twin_version = version
+        return twin
 
     def engine(self):
         from .engine import FastDVDnetEngine
+        if self.num_color_channels == 1:
+            return self._colour_twin().engine()
         if self._engine is None:
             self._engine = FastDVDnetEngine(self)
         return self._engine
 
     def forward(self, x, noise_map):
-        """x [1,15,H,W] (5 frames stacked frame-major), noise_map [1,1,H,W] constant -> [1,3,H,W]."""
+        """x [1,5*C,H,W] (5 frames stacked frame-major), noise_map [1,1,H,W] constant -> [1,C,H,W]."""
+        if self.num_color_channels == 1:
+            x3 = x.new_zeros((x.shape[0], 15, x.shape[2], x.shape[3]))
+            x3[:, 0::3] = x
+            return self.engine().forward_window(x3, noise_map)[:, 0:1]
         return self.engine().forward_window(x, noise_map)
 
     def __nchannel__(self):

@@ -99,3 +99,28 @@ def ffdnet_rgb_denoise_full_tensor(x, yall, Phiall, sigma, model, useGPU=True, l
         out = _unwrap(model).engine().forward(u, sigma, train=False)
     outv = ops.planar_to_pixlast(out, 3, B).view(H, W, 3, B)
     return (outv, model) if updata_ else outv
+
+
+def ffdnet_vdenoiser(vnoisy, sigma, model=None, useGPU=True):
+    """packages/ffdnet/test_ffdnet_ipol.py:103-181 - frame-wise gray adapter: numpy ``vnoisy`` [M,N,F...] -> float64 numpy
+    of the same shape, every frame ``frame - model(frame, sigma)`` without clipping (:177) with the IPOL-flavour gray model
+    (``ffdnet_ipol_models.FFDNet(1)``, which returns the noise estimate).  The reference feeds the frames one by one; they
+    are independent, so here the F frames are one batch through the native engine.  Like the reference (no odd-size
+    handling, :146-158 commented out) it needs even M and N.  Not on the solvers' path; API parity."""
+    import numpy as np
+    from .ffdnet_ipol_models import FFDNet as FFDNetIPOL
+    if model is None:
+        raise SciError("ffdnet_vdenoiser: pass the gray model (the reference's default models/net_gray.pth is not shipped, "
+                       ".MISSING_LARGE_BLOBS)")
+    if not useGPU:
+        raise SciError("the native engine is CUDA only")
+    net = model.module if hasattr(model, "module") and not isinstance(model, FFDNetIPOL) else model
+    if not isinstance(net, FFDNetIPOL) or net.num_input_channels != 1:
+        raise SciError("ffdnet_vdenoiser expects adaptivepnp_sci_b200.ffdnet_ipol_models.FFDNet(num_input_channels=1)")
+    model.eval()                                                                          # :128
+    vshape = vnoisy.shape
+    v = np.ascontiguousarray(vnoisy, dtype=np.float32).reshape(vshape[0], vshape[1], -1)  # :132-133
+    frames = torch.from_numpy(v).cuda().permute(2, 0, 1).unsqueeze(1).contiguous()        # [F,1,M,N]
+    est = net.engine().forward(frames, float(sigma), train=False)
+    out = (frames - est)[:, 0].permute(1, 2, 0).contiguous()                              # :177, no clamp
+    return out.cpu().numpy().astype(np.float64).reshape(vshape)                           # outv is np.zeros(...): float64

@@ -5,6 +5,8 @@ Test infrastructure.  CPU restatements of
   * ``fastdvdnet_seqdenoise``               packages/fastdvdnet/fastdvdnet.py:82-146
   * ``fastdvdnet_denoiser_full_tensor_v2``  packages/fastdvdnet/test_fastdvdnet.py:325-500
   * ``ddnet_seqdenoise`` / ``test_ddnet``   packages/DDnet/DDnet_test.py:166-321
+  * ``ffdnet_vdenoiser``                    packages/ffdnet/test_ffdnet_ipol.py:103-181   (frame-wise, gray)
+  * ``fastdvdnet_denoiser``                 packages/fastdvdnet/test_fastdvdnet.py:149-235 (frame-wise, inference)
 """
 import numpy as np
 import torch
@@ -56,7 +58,8 @@ def ffdnet_rgb_denoise_full_tensor(x, yall, Phiall, sigma, model, useGPU=True, l
 
 
 def fastdvdnet_seqdenoise(seq, noise_std, windsize, model):
-    """fastdvdnet.py:82-146 — circular temporal window, reflect pad to x4."""
+    """fastdvdnet.py:82-146 — circular temporal window, reflect pad to x4.  (The reference re-pads its noise map inside the
+    frame loop, :129, and therefore fails from the second frame on when H or W is not a multiple of 4; padded once here.)"""
     N, C, H, W = seq.shape
     hw = (windsize - 1) // 2
     out = torch.empty((N, C, H, W))
@@ -216,3 +219,32 @@ def test_ddnet(vnoisy, yall, Phiall, model=None, useGPU=True, args=None, gray=Fa
     if gray:
         outv = outv.squeeze(3)
     return (outv, model) if updata_ else outv
+
+
+def ffdnet_vdenoiser(vnoisy, sigma, model):
+    """test_ffdnet_ipol.py:103-181: numpy [M,N,F...] -> float64 numpy, frame by frame ``frame - model(frame, sigma)``
+    (IPOL-flavour model = noise estimate), no clipping (:177)."""
+    model.eval()
+    vshape = vnoisy.shape
+    v = vnoisy.reshape(*vshape[0:2], -1)
+    outv = np.zeros(v.shape)
+    with torch.no_grad():
+        for k in range(v.shape[-1]):
+            im = torch.Tensor(v[:, :, k][None, None])
+            outv[:, :, k] = (im - model(im, torch.FloatTensor([sigma])))[0, 0].numpy()
+    return outv.reshape(vshape)
+
+
+def fastdvdnet_denoiser(vnoisy, sigma, model, gray=False):
+    """test_fastdvdnet.py:149-235, inference branch (:207-231): numpy [H,W,F,3] (gray: [H,W,F]) -> same shape."""
+    model.eval()
+    v = torch.from_numpy(vnoisy).float()
+    if gray:
+        v = v.unsqueeze(3)
+    v = v.permute(2, 3, 0, 1)
+    with torch.no_grad():
+        out = fastdvdnet_seqdenoise(v, torch.FloatTensor([sigma]), NUM_IN_FR_EXT, model)
+    out = out.permute(2, 3, 0, 1)
+    if gray:
+        out = out.squeeze(3)
+    return out.numpy()

@@ -40,6 +40,36 @@ class FFDNet(nn.Module):
         return x[..., :h, :w]
 
 
+class FFDNetIPOL(nn.Module):
+    """packages/ffdnet/models.py:70-110 + functions.py:16-53 (first layer) / :55-81 (last layer): the IPOL flavour used by
+    the frame-wise gray adapter.  No conv bias, BatchNorm between the inner layers, returns the NOISE estimate.
+    Keys: intermediate_dncnn.itermediate_dncnn.{i}.weight (sic) + BatchNorm entries."""
+
+    def __init__(self, num_input_channels):
+        super().__init__()
+        gray = num_input_channels == 1
+        nf, nl, cin, cout = (64, 15, 5, 4) if gray else (96, 12, 15, 12)            # models.py:76-88
+        layers = [nn.Conv2d(cin, nf, 3, padding=1, bias=False), nn.ReLU(inplace=True)]
+        for _ in range(nl - 2):
+            layers += [nn.Conv2d(nf, nf, 3, padding=1, bias=False), nn.BatchNorm2d(nf), nn.ReLU(inplace=True)]
+        layers.append(nn.Conv2d(nf, cout, 3, padding=1, bias=False))
+        self.intermediate_dncnn = nn.Module()
+        self.intermediate_dncnn.itermediate_dncnn = nn.Sequential(*layers)
+        self.num_input_channels = num_input_channels
+
+    def forward(self, x, noise_sigma):
+        N, C, H, W = x.shape
+        down = torch.zeros((N, 4 * C, H // 2, W // 2), dtype=x.dtype)
+        for idx, (i, j) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):              # functions.py:36,48-50
+            down[:, idx::4] = x[:, :, i::2, j::2]
+        noise_map = noise_sigma.view(N, 1, 1, 1).repeat(1, C, H // 2, W // 2)         # :45
+        h = self.intermediate_dncnn.itermediate_dncnn(torch.cat((noise_map, down), 1))  # :53: the noise planes come FIRST
+        out = torch.zeros((N, C, H, W), dtype=x.dtype)
+        for idx, (i, j) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):              # :76-79
+            out[:, :, i::2, j::2] = h[:, idx::4]
+        return out
+
+
 def _cv(ci, co, stride=1, groups=1):
     return nn.Conv2d(ci, co, 3, padding=1, stride=stride, groups=groups, bias=False)
 

@@ -80,6 +80,11 @@ def _install_shims(cpu=True):
     torch.nn.Module.cuda = lambda self, *a, **k: self
     torch.cuda.empty_cache = lambda: None
     torch.cuda.manual_seed = lambda *a, **k: None
+    _type = torch.Tensor.type
+    # test_fastdvdnet.py:214 / test_ffdnet_ipol.py:164 ask for 'torch.cuda.FloatTensor' by name
+    torch.Tensor.type = lambda self, dtype=None, *a, **k: _type(
+        self, "torch.FloatTensor" if (dtype == "torch.cuda.FloatTensor" or dtype is getattr(torch.cuda, "FloatTensor", None))
+        else dtype, *a, **k)
 
 
 def load(root=None, device="cpu"):
@@ -105,6 +110,7 @@ def load(root=None, device="cpu"):
     ns.fastdvd_adapter = importlib.import_module("packages.fastdvdnet.test_fastdvdnet")
     ns.fastdvd_driver = importlib.import_module("packages.fastdvdnet.fastdvdnet")
     ns.ffdnet_adapter = importlib.import_module("packages.ffdnet.test_ffdnet_ipol")
+    ns.ffdnet_ipol_models = importlib.import_module("packages.ffdnet.models")
     ns.network_demosaicking = importlib.import_module("models.network_demosaicking")
     ns.ddnet_adapter = importlib.import_module("packages.DDnet.DDnet_test")
     import torch

@@ -79,6 +79,42 @@ def fastdvdnet_synthetic_state_dict(seed=4242, out_gain=0.005):
     return sd
 
 
+def fastdvdnet_gray_synthetic_state_dict(seed=4242, out_gain=0.005):
+    """Single-channel FastDVDnet (num_color_channels=1, packages/fastdvdnet/models.py:34-48,77-91): the colour synthetic
+    state with the first layer's [r, sigma] columns of every frame group and the first output filter."""
+    sd = fastdvdnet_synthetic_state_dict(seed, out_gain)
+    for blk in ("temp1", "temp2"):
+        sd[blk + ".inc.convblock.0.weight"] = sd[blk + ".inc.convblock.0.weight"][:, [0, 3]].clone()
+        sd[blk + ".outc.convblock.3.weight"] = sd[blk + ".outc.convblock.3.weight"][0:1].clone()
+    return sd
+
+
+def ffdnet_ipol_synthetic_state_dict(num_input_channels=1, seed=99, out_gain=0.05):
+    """Random state for the IPOL-flavour FFDNet (packages/ffdnet/models.py:70-110; net_gray.pth is not shipped): Kaiming
+    convs, non-trivial BatchNorm running statistics, a small last layer (the network predicts the noise)."""
+    gray = num_input_channels == 1
+    nf, nl, cin, cout = (64, 15, 5, 4) if gray else (96, 12, 15, 12)
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    p = "intermediate_dncnn.itermediate_dncnn."
+    idx = 0
+    for layer in range(nl):
+        ci, co = (cin if layer == 0 else nf), (cout if layer == nl - 1 else nf)
+        gain = out_gain if layer == nl - 1 else 1.0
+        sd[p + "%d.weight" % idx] = torch.randn(co, ci, 3, 3, generator=g) * (float(np.sqrt(2.0 / (ci * 9))) * gain)
+        idx += 1
+        if 0 < layer < nl - 1:
+            sd[p + "%d.weight" % idx] = 1.0 + 0.05 * torch.randn(co, generator=g)
+            sd[p + "%d.bias" % idx] = 0.02 * torch.randn(co, generator=g)
+            sd[p + "%d.running_mean" % idx] = 0.02 * torch.randn(co, generator=g)
+            sd[p + "%d.running_var" % idx] = 1.0 + 0.1 * torch.rand(co, generator=g)
+            sd[p + "%d.num_batches_tracked" % idx] = torch.tensor(0, dtype=torch.long)
+            idx += 1
+        if layer < nl - 1:
+            idx += 1                       # ReLU
+    return sd
+
+
 def ddnet_synthetic_state_dict(seed=777, out_gain=0.002):
     """Random init for DDnet (the trained ``model_zoo/ddnet1.pth`` is absent, .MISSING_LARGE_BLOBS).
     Kaiming-normal convs (models/network_demosaicking.py:402-405), the last conv of every DenBlock and of the

@@ -440,6 +440,49 @@ def stage1_deep(ns):
     np.savez_compressed(os.path.join(HERE, "stage1_deep.npz"), **out)
 
 
+def gray_adapters(ns):
+    """Frame-wise gray adapters: ffdnet_vdenoiser (test_ffdnet_ipol.py:103-181, IPOL-flavour gray FFDNet)
+    and fastdvdnet_denoiser(gray=True) (test_fastdvdnet.py:149-235, single-channel FastDVDnet), inference."""
+    print("gray frame-wise adapters")
+    g = torch.Generator().manual_seed(77)
+    v = torch.rand(32, 48, 6, generator=g).numpy().astype(np.float64)
+    rm = ns.ffdnet_ipol_models.FFDNet(num_input_channels=1)
+    rm.load_state_dict(synthetic.ffdnet_ipol_synthetic_state_dict(1), strict=True)
+    om = networks.FFDNetIPOL(1)
+    om.load_state_dict(synthetic.ffdnet_ipol_synthetic_state_dict(1), strict=True)
+    r = ns.ffdnet_adapter.ffdnet_vdenoiser(v, 20 / 255, model=rm, useGPU=False)
+    o = adapters.ffdnet_vdenoiser(v, 20 / 255, om)
+    _eq(r, o, "ffdnet_vdenoiser")
+    out = {"v": v, "ffd_v": r}
+    rm3 = ns.ffdnet_ipol_models.FFDNet(num_input_channels=3).eval()     # colour flavour of the same class: network forward only
+    rm3.load_state_dict(synthetic.ffdnet_ipol_synthetic_state_dict(3), strict=True)
+    om3 = networks.FFDNetIPOL(3).eval()
+    om3.load_state_dict(synthetic.ffdnet_ipol_synthetic_state_dict(3), strict=True)
+    x3 = torch.rand(2, 3, 32, 48, generator=g)
+    with torch.no_grad():
+        r3 = rm3(x3, torch.FloatTensor([15 / 255, 15 / 255]))
+        o3 = om3(x3, torch.FloatTensor([15 / 255, 15 / 255]))
+    _eq(r3, o3, "IPOL FFDNet colour forward")
+    out.update(ffd_rgb_in=x3.numpy(), ffd_rgb_noise=r3.numpy())
+    sd = {"module." + k: t for k, t in synthetic.fastdvdnet_gray_synthetic_state_dict().items()}
+    rg = torch.nn.DataParallel(ns.fastdvd_models.FastDVDnet(num_input_frames=5, num_color_channels=1))
+    rg.load_state_dict(sd, strict=True)
+    og = networks.Wrapped(networks.FastDVDnet(num_input_frames=5, num_color_channels=1))
+    og.load_state_dict(sd, strict=True)
+    # 32x48: the reference's sequence driver pads its noise map AGAIN for every frame (fastdvdnet.py:129), so it only runs
+    # on sizes that are already multiples of 4 (the oracle and the CUDA path pad once; tests cover 30x46 against the oracle)
+    vg = torch.rand(32, 48, 6, generator=g).numpy().astype(np.float32)
+    r = ns.fastdvd_adapter.fastdvdnet_denoiser(vg, 12 / 255, model=rg.eval(), useGPU=False, gray=True)
+    o = adapters.fastdvdnet_denoiser(vg, 12 / 255, og, gray=True)
+    _eq(r, o, "fastdvdnet_denoiser gray")
+    out.update(vg=vg, fdvd_gray=r)
+    np.savez_compressed(os.path.join(HERE, "gray_adapters.npz"), **out)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "gray_adapters":
+    gray_adapters(ref_harness.load())
+    sys.exit(0)
+
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "stage1_deep":
     stage1_deep(ref_harness.load())
     sys.exit(0)
@@ -464,4 +507,5 @@ if __name__ == "__main__":
     ddnet_(ns)
     closed_form(ns)
     stage1_deep(ns)
+    gray_adapters(ns)
     print("golden vectors written to", HERE)

@@ -152,4 +152,50 @@ def test_fastdvdnet_framewise_adapter(cuda):
         ref = adapters.fastdvdnet_seqdenoise(torch.from_numpy(v).permute(2, 3, 0, 1), torch.FloatTensor([12 / 255]), 5, mo)
     assert np.max(np.abs(out - ref.permute(2, 3, 0, 1).numpy())) < 1e-3
     with pytest.raises(NotImplementedError):
-        fastdvdnet_denoiser(v[..., 0], 12 / 255, m, gray=True)
+        fastdvdnet_denoiser(v, 12 / 255, m, updata_=True)
+
+
+def test_gray_framewise_adapters(cuda, impl):
+    """ffdnet_vdenoiser (test_ffdnet_ipol.py:103-181) with the IPOL-flavour gray FFDNet and
+    fastdvdnet_denoiser(gray=True) (test_fastdvdnet.py:149-235) with the single-channel FastDVDnet, against outputs of the
+    reference's own functions (tests/golden/gray_adapters.npz); odd sizes against the oracle (the reference fails there)."""
+    from adaptivepnp_sci_b200 import synthetic as syn
+    from adaptivepnp_sci_b200.fastdvdnet_adapter import DataParallelLike, fastdvdnet_denoiser
+    from adaptivepnp_sci_b200.fastdvdnet_models import FastDVDnet
+    from adaptivepnp_sci_b200.ffdnet_adapter import ffdnet_vdenoiser
+    from adaptivepnp_sci_b200.ffdnet_ipol_models import FFDNet as FFDNetIPOL
+    from oracle import adapters, networks, synthetic
+    d = np.load(os.path.join(G, "gray_adapters.npz"))
+    m = FFDNetIPOL(1)
+    m.load_state_dict(syn.ffdnet_ipol_synthetic_state_dict(1), strict=True)
+    m = m.cuda()
+    out = ffdnet_vdenoiser(d["v"], 20 / 255, model=m)
+    assert out.shape == d["v"].shape and out.dtype == np.float64
+    assert np.max(np.abs(out - d["ffd_v"])) < TOL[impl]
+    v4 = d["v"].reshape(32, 48, 3, 2)                                  # [M,N,F1,F2] input: frames are the flattened tail (:132-133)
+    assert np.array_equal(ffdnet_vdenoiser(v4, 20 / 255, model=m).reshape(32, 48, 6), out)
+    m3 = FFDNetIPOL(3)                                                  # colour flavour of the class: three noise planes first
+    m3.load_state_dict(syn.ffdnet_ipol_synthetic_state_dict(3), strict=True)
+    m3 = m3.cuda().eval()
+    noise = m3(torch.from_numpy(d["ffd_rgb_in"]).cuda(), torch.full((2,), 15 / 255).cuda())
+    assert float(np.max(np.abs(noise.cpu().numpy() - d["ffd_rgb_noise"]))) < TOL[impl]
+    with pytest.raises(Exception):
+        ffdnet_vdenoiser(d["v"], 20 / 255, model=None)
+
+    sd = {"module." + k: t for k, t in syn.fastdvdnet_gray_synthetic_state_dict().items()}
+    g = DataParallelLike(FastDVDnet(num_input_frames=5, num_color_channels=1))
+    g.load_state_dict(sd, strict=True)
+    g = g.eval().cuda()
+    assert list(g.state_dict().keys()) == list(sd.keys())             # the colour twin is not part of the state
+    got = fastdvdnet_denoiser(d["vg"], 12 / 255, g, gray=True)
+    assert got.shape == d["vg"].shape and got.dtype == np.float32
+    assert np.max(np.abs(got - d["fdvd_gray"])) < TOL[impl] * 5
+    og = networks.Wrapped(networks.FastDVDnet(num_input_frames=5, num_color_channels=1))
+    og.load_state_dict({"module." + k: t for k, t in synthetic.fastdvdnet_gray_synthetic_state_dict().items()}, strict=True)
+    vo = torch.rand(30, 46, 5, generator=torch.Generator().manual_seed(5)).numpy()
+    assert np.max(np.abs(fastdvdnet_denoiser(vo, 12 / 255, g, gray=True) - adapters.fastdvdnet_denoiser(vo, 12 / 255, og, gray=True))) < TOL[impl] * 5
+    # weights changed in place -> the twin follows
+    with torch.no_grad():
+        g.module.temp2.outc.convblock[3].weight.mul_(2.0)
+        og.module.temp2.outc.convblock[3].weight.mul_(2.0)
+    assert np.max(np.abs(fastdvdnet_denoiser(vo, 12 / 255, g, gray=True) - adapters.fastdvdnet_denoiser(vo, 12 / 255, og, gray=True))) < TOL[impl] * 5
