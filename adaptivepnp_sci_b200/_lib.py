@@ -78,6 +78,8 @@ PROTOTYPES = {
     "sci_ffdnet_pack_input": [_p, _f, _p, _i, _i, _i, _i, _i, _i, _p],
     "sci_ffdnet_unpack_output": [_p, _p, _i, _i, _i, _i, _i, _p],
     "sci_ffdnet_unpack_output_grad": [_p, _p, _i, _i, _i, _i, _i, _p],
+    "sci_ffdnet_pack_input_split_half": [_p, _f, _p, _i, _i, _i, _i, _p],
+    "sci_ffdnet_unpack_output_split_half": [_p, _p, _i, _i, _i, _i, _p],
     "sci_dual_update_gray": [_p, _p, _p, _p, _p, _p, _i, _l, _p, _p, _p],
     "sci_fastdvd_pack_input": [_p, _f, _p, _i, _i, _i, _i, _i, _p],
     "sci_fastdvd_output": [_p, _p, _p, _i, _i, _i, _i, _p],

@@ -447,6 +447,11 @@ struct Fwd2Params {
     // MODE 4 (data gradient + activation backward of the layer that PRODUCED this tensor, fused): dz = (conv [+ residual]) *
     // (mask_y > 0); col_s1[c] += sum dz, col_s2[c] += sum dz * mask_y  (bias / BatchNorm gradients), see the epilogue
     const float* mask_y; float* col_s1; float* col_s2; int mask_relu;
+    // split > 0 (HALF, FFDNet inference at ~fp32 accuracy): every activation and weight travels as fp16 value + fp16 remainder
+    // scaled by 2^11; a 64-channel chunk is [32 values | their 32 remainders].  Per chunk the issuer multiplies value x value
+    // into the main accumulator and value x remainder + remainder x value into a second one (columns + Cout), the epilogue
+    // adds them (x 2^-11), applies the layer's epilogue and emits the same split form.  split = value K steps per chunk (1, 2).
+    int split;
     int ks_last;      // K steps (8 fp32 / 16 fp16 channels each) of the LAST channel chunk that can hold non-zero channels (1..4):
                       // zero-padded K columns are not multiplied (12 -> 90: 28 of 64 fp16 channels used -> 2 of 4 steps)
     // fp16 tensors with 32 channels are stored as 64-byte pixel rows (no zero half): operand rows / staging rows of 64 bytes use the
@@ -626,7 +631,22 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             const uint32_t b_lo = desc_lo(p.resident ? smem_base + (uint32_t)(r * 3 * p.k_chunks + kc) * b_bytes : a_addr + (uint32_t)p.a_stage);
                             const uint32_t b_step = p.resident ? (uint32_t)p.k_chunks * b_tile_lo : b_tile_lo;
                             const uint32_t first = (uint32_t)((r | kc) != 0);
-                            if (!(p.dbg & 1)) {
+                            if (HALF && p.split) {
+                                // chunk = [values (K steps 0,1) | remainders * 2^11 (K steps 2,3)] on both operands
+                                const uint32_t d_small = d_base + (uint32_t)p.Cout;
+#pragma unroll
+                                for (int s = 0; s < 3; ++s) {
+#pragma unroll
+                                    for (int k = 0; k < 2; ++k) {
+                                        if (k < p.split) {
+                                            const uint32_t a_v = a_lo + s * tapu + k * 2, b_v = b_lo + s * b_step + k * 2;
+                                            mma_lo<HALF>(d_base, a_v, b_v, idesc, (s | k) ? 1u : first, p.desc_hi);          // value x value
+                                            mma_lo<HALF>(d_small, a_v, b_v + 4, idesc, (s | k) ? 1u : first, p.desc_hi);     // value x weight remainder
+                                            mma_lo<HALF>(d_small, a_v + 4, b_v, idesc, 1u, p.desc_hi);                       // remainder x weight value
+                                        }
+                                    }
+                                }
+                            } else if (!(p.dbg & 1)) {
 #pragma unroll
                                 for (int s = 0; s < 3; ++s) {
 #pragma unroll
@@ -841,6 +861,22 @@ conv_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (MODE == 1) load_res(u + EPI_WG, rnext);
                     const uint32_t t_row = tmem_base + (uint32_t)((acc * p.R + (p.stack ? p.R - 1 - t : t)) * p.acc_stride) + ((uint32_t)(q * 32) << 16);
                     uint32_t hv[32];                                        // 64 fp16 values of this lane's pixel
+                    if (p.split) {
+                        // main + 2^-11 * small -> epilogue -> [32 fp16 values | 32 remainders * 2^11] = one 64-channel stored chunk
+                        float v[32], sm[32];
+                        tmem_ld32(t_row + col0, v);
+                        tmem_ld32(t_row + p.Cout + col0, sm);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            const float a0 = fmaxf(fmaf(fmaf(sm[j], 1.f / 2048.f, v[j]), s_scale[col0 + j], s_shift[col0 + j]), lower);
+                            const float a1 = fmaxf(fmaf(fmaf(sm[j + 1], 1.f / 2048.f, v[j + 1]), s_scale[col0 + j + 1], s_shift[col0 + j + 1]), lower);
+                            const uint32_t h = pack_half2(a0, a1);
+                            const float2 hf = unpack_half2(h);
+                            hv[j >> 1] = h;
+                            hv[16 + (j >> 1)] = pack_half2((a0 - hf.x) * 2048.f, (a1 - hf.y) * 2048.f);
+                        }
+                        cx = 2 * cg;                                        // stored chunk of this 32-column group
+                    } else
 #pragma unroll
                     for (int hb = 0; hb < 2; ++hb) {
                         if (hb * 32 < ncv) {
@@ -1310,6 +1346,15 @@ int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream, int col0, int ncol
         if (rb_out == 64 && p.ucols != 32) return sci_fail(SCI_EUNSUPPORTED, "conv tc v2 fp16: a 32-channel output tensor needs 32-column units");
         if (p.ps && cq != 32 && cq % 64 != 0) return sci_fail(SCI_EUNSUPPORTED, "conv tc v2 fp16: PixelShuffle groups of 32 or k*64 columns");
     }
+    p.split = 0;
+    if (half && d->w_split) {
+        // fp16 value + remainder form (FFDNet inference): d->Cin = 64 * (groups of 32 real input channels), stored output = 2 * Cout
+        if (rb_in != 128 || p.ps || d->residual || p.planar_out || ncols != d->Cout || d->Cout % 32 || d->Cout > 128 || cout_store != 2 * d->Cout)
+            return sci_fail(SCI_EUNSUPPORTED, "conv tc v2 fp16 split: plain layers, Cout % 32 == 0, Cout <= 128, Cout_store == 2 * Cout");
+        p.split = (d->K_used > 0 && d->K_used <= 16 && p.k_chunks == 1) ? 1 : 2;
+        p.ucols = 32;
+        p.ks_last = 4;
+    }
     int mode = p.planar_out ? 2 : (!p.tma_store ? 3 : (d->residual ? 1 : 0));
     p.mask_y = d->mask_y; p.col_s1 = d->col_s1; p.col_s2 = d->col_s2; p.mask_relu = d->mask_relu;
     if (d->mask_y) {
@@ -1348,13 +1393,14 @@ int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream, int col0, int ncol
     int stage_bytes = a_stage + (p.resident ? 0 : 3 * b_bytes);
     p.stages = min(MAX_STAGES, (budget - (p.resident ? w_bytes : 0)) / stage_bytes);
     if (p.stages < 2) return sci_fail(SCI_EUNSUPPORTED, "conv tc v2: pipeline does not fit");
-    p.acc_stride = p.Cout;
+    p.acc_stride = p.split ? 2 * p.Cout : p.Cout;        // split: [main | value x remainder products]
+    if (p.split && 2 * p.acc_stride > 512) return sci_fail(SCI_EUNSUPPORTED, "conv tc v2 fp16 split: accumulators do not fit");
     // super-tiles of R output rows: the R+2 input rows are loaded once and feed up to three output rows each, which
     // cuts the shared-memory fill traffic per output row from 3 rows to (R+2)/R.  Measured (tools/bench_conv.py): the
     // resident-weight layers are bound by ring_bytes / load round-trip latency, i.e. by bytes per output tile.
     // R accumulators x 2 buffers must fit the 512 TMEM columns; streamed weights keep R = 1 (their B tiles are per filter row).
     p.R = 1;
-    if (!p.resident && 2 * 2 * p.acc_stride <= 512 && p.H >= 2 && env_int("SCI_CONV_WPAIR", 1)) {
+    if (!p.resident && !p.split && 2 * 2 * p.acc_stride <= 512 && p.H >= 2 && env_int("SCI_CONV_WPAIR", 1)) {
         // streamed weights: two output rows per tile share every weight tile (a stage then carries two input rows)
         // ... where the image is large enough that halving the tile count does not cost a wave of the 148 persistent CTAs
         // (8x128x128: 1024 one-row tiles = 6.9 waves; 512 two-row tiles would be 3.5 -> 4 waves of twice the work)
@@ -1362,7 +1408,7 @@ int conv_fwd2_tc_launch(const sci_conv_desc* d, void* stream, int col0, int ncol
         const long tiles2 = (long)p.tiles_w * ((p.H + 1) / 2) * p.N;
         if (budget / sb2 >= 2 && tiles2 >= 8L * SCI_NUM_SMS) p.R = 2;
     }
-    if (p.resident) {
+    if (p.resident && !p.split) {             // (the split issuer is written for one output row per tile)
         const int rmax = env_int("SCI_CONV_ROWS", 8);
         while (p.R * 2 <= rmax && 2 * (p.R * 2) * p.acc_stride <= 512 && p.R * 2 <= p.H) p.R *= 2;
     }
@@ -2012,7 +2058,8 @@ int check_conv_desc(const sci_conv_desc* d) {
     SCI_REQUIRE(!d->planar_out || (d->stride == 1 && !d->w_split && !d->emit_lo), "conv: planar output options");
     SCI_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "conv: shape");
     SCI_REQUIRE(d->Cin % 8 == 0 && d->Cout % 4 == 0, "conv: Cin % 8, Cout % 4");
-    SCI_REQUIRE(!d->half_io || ((d->Cin % 64 == 0 || d->Cin == 32) && d->Cout % 32 == 0 && !d->w_split && !d->emit_lo), "conv fp16: Cin % 64 (or 32), Cout % 32, no split options");
+    SCI_REQUIRE(!d->half_io || ((d->Cin % 64 == 0 || d->Cin == 32) && d->Cout % 32 == 0 && !d->emit_lo), "conv fp16: Cin % 64 (or 32), Cout % 32, no emit_lo");
+    SCI_REQUIRE(!(d->half_io && d->w_split) || (d->stride == 1 && d->Cin % 64 == 0), "conv fp16 split form (w_split): stride 1, Cin = 64 per group of 32 channels");
     SCI_REQUIRE(d->stride == 1 || d->stride == 2, "conv: stride");
     SCI_REQUIRE(!d->pixel_shuffle || d->stride == 1, "conv: pixel_shuffle with stride 2");
     return SCI_OK;

@@ -174,6 +174,10 @@ __global__ void dilate2_kernel(const float* __restrict__ in, float* __restrict__
 }
 
 // ---- FFDNet boundary -----------------------------------------------------------------------------
+__device__ __forceinline__ uint4 pack8_h(const __half* v) {
+    auto pk = [](__half a, __half b) -> uint32_t { return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16); };
+    return make_uint4(pk(v[0], v[1]), pk(v[2], v[3]), pk(v[4], v[5]), pk(v[6], v[7]));
+}
 __global__ void ffdnet_pack_kernel(const float* __restrict__ u, float sigma, float* __restrict__ out, int B, int C, int H,
                                    int W, int Cpad, int round_tf32) {
     const int h2 = H >> 1, w2 = W >> 1;
@@ -197,6 +201,46 @@ __global__ void ffdnet_pack_kernel(const float* __restrict__ u, float sigma, flo
         v = (k >= 16) ? rna_tf32(v - hi) : hi;
     }
     out[idx] = v;
+}
+
+// fp16 split form of the same input (inference on conv_fwd2_tc_kernel's `split` path): 64 fp16 channels per pixel,
+// channel k < 32 = fp16(v_k), channel 32 + k = fp16((v_k - fp16(v_k)) * 2^11).  One thread per (pixel, 16-byte chunk).
+__global__ void ffdnet_pack_split_half_kernel(const float* __restrict__ u, float sigma, __half* __restrict__ out, int B, int C,
+                                              int H, int W) {
+    const int h2 = H >> 1, w2 = W >> 1;
+    const long total = (long)B * h2 * w2 * 8;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int ch = (int)(idx & 7);                     // 8 channels: ch < 4 -> hi of channels 8ch.., else remainders of 8(ch-4)..
+    const long p = idx >> 3;
+    const int w = (int)(p % w2), h = (int)((p / w2) % h2), n = (int)(p / ((long)w2 * h2));
+    __half r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int kk = (ch & 3) * 8 + j;
+        float v = 0.f;
+        if (kk < 4 * C) {
+            const int c = kk >> 2, dy = (kk >> 1) & 1, dx = kk & 1;
+            v = u[(((long)n * C + c) * H + 2 * h + dy) * W + 2 * w + dx];
+        } else if (kk == 4 * C) {
+            v = sigma;
+        }
+        const __half hi = __float2half_rn(v);
+        r[j] = (ch < 4) ? hi : __float2half_rn((v - __half2float(hi)) * 2048.f);
+    }
+    reinterpret_cast<uint4*>(out)[idx] = pack8_h(r);
+}
+
+// network output from the split form: y[n][h][w][64] fp16 = [hi 0..31 | remainder * 2^11 0..31] -> xhat planar fp32
+__global__ void ffdnet_unpack_split_half_kernel(const __half* __restrict__ y, float* __restrict__ xhat, int B, int C, int H, int W) {
+    const long total = (long)B * C * H * W;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int wf = (int)(idx % W), hf = (int)((idx / W) % H), c = (int)((idx / ((long)W * H)) % C);
+    const int n = (int)(idx / ((long)C * W * H));
+    const int k = c * 4 + (hf & 1) * 2 + (wf & 1);
+    const __half* row = y + (((long)n * (H >> 1) + (hf >> 1)) * (W >> 1) + (wf >> 1)) * 64;
+    xhat[idx] = fmaf(__half2float(row[32 + k]), 1.f / 2048.f, __half2float(row[k]));
 }
 
 // xhat[n][c][2h+dy][2w+dx] = y[n][h][w][c*4+dy*2+dx]   (nn.PixelShuffle(2), network_ffdnet.py:66)
@@ -393,12 +437,17 @@ __global__ void pack_weights_half_kernel(const float* __restrict__ w, __half* __
     const int col = (int)((idx / Ci_pad) % Co_pad), tap = (int)(idx / ((long)Ci_pad * Co_pad));
     float v = 0.f;
     if (ci_dup > 0 && ci >= ci_dup && ci < ci_dup + Ci) ci -= ci_dup;
+    // ci_dup == -1: split form (conv_fwd2_tc_kernel, `split`): K chunk g of 64 = [fp16(w) of channels 32g..32g+31 | the
+    // remainders (w - fp16(w)) * 2^11 of the same channels]
+    const int part = (ci_dup == -1) ? (ci >> 5) & 1 : 0;
+    if (ci_dup == -1) ci = ((ci >> 6) << 5) | (ci & 31);
     const int q = Co_pad >> 2;
     const int co = ps ? (col % q) * 4 + col / q : col;
     if ((ps ? (col % q) < (Co >> 2) : col < Co) && ci < Ci) {
         const int cig = Ci / groups, cog = Co / groups, g = co / cog;
         if (ci / cig == g) v = w[((long)co * cig + (ci - g * cig)) * 9 + tap];
     }
+    if (part) v = (v - __half2float(__float2half_rn(v))) * 2048.f;
     packed[idx] = __float2half_rn(v);
 }
 
@@ -517,12 +566,15 @@ __device__ __forceinline__ void layer_op_element(const sci_layer_op& d, long idx
         const int col = (int)((idx / d.Ci_pad) % d.Co_pad), tap = (int)(idx / ((long)d.Ci_pad * d.Co_pad));
         float v = 0.f;
         if (d.ci_dup > 0 && ci >= d.ci_dup && ci < d.ci_dup + d.Ci) ci -= d.ci_dup;
+        const int part = (d.ci_dup == -1) ? (ci >> 5) & 1 : 0;      // split form, see pack_weights_half_kernel
+        if (d.ci_dup == -1) ci = ((ci >> 6) << 5) | (ci & 31);
         const int q = d.Co_pad >> 2;
         const int co = d.ps ? (col % q) * 4 + col / q : col;
         if ((d.ps ? (col % q) < (d.Co >> 2) : col < d.Co) && ci < d.Ci) {
             const int cig = d.Ci / d.groups, cog = d.Co / d.groups, g = co / cog;
             if (ci / cig == g) v = w[((long)co * cig + (ci - g * cig)) * 9 + tap];
         }
+        if (part) v = (v - __half2float(__float2half_rn(v))) * 2048.f;
         static_cast<__half*>(d.o0)[idx] = __float2half_rn(v);
         return;
     }
@@ -595,7 +647,8 @@ extern "C" int sci_conv_pack_weights_half(const float* w, void* packed, int Co, 
                                           int ps, int ci_dup, void* stream) {
     SCI_REQUIRE(w && packed && Co > 0 && Ci > 0 && groups > 0 && Co % groups == 0 && Ci % groups == 0, "pack_weights_half");
     SCI_REQUIRE(Co_pad >= Co && Ci_pad >= Ci && Ci_pad % 32 == 0 && (!ps || (Co % 4 == 0 && Co_pad % 4 == 0)), "pack_weights_half: padding");
-    SCI_REQUIRE(ci_dup == 0 || (ci_dup >= Ci && ci_dup + Ci <= Ci_pad), "pack_weights_half: ci_dup block does not fit");
+    SCI_REQUIRE(ci_dup == 0 || (ci_dup == -1 && Ci_pad % 64 == 0 && Ci_pad >= 2 * ((Ci + 31) / 32) * 32) || (ci_dup >= Ci && ci_dup + Ci <= Ci_pad),
+                "pack_weights_half: ci_dup block does not fit");
     const long total = (long)9 * Co_pad * Ci_pad;
     pack_weights_half_kernel<<<grid1d(total), 256, 0, sci_stream(stream)>>>(w, reinterpret_cast<__half*>(packed), Co, Ci, groups,
                                                                             Co_pad, Ci_pad, ps, ci_dup);
@@ -693,6 +746,22 @@ extern "C" int sci_ffdnet_unpack_output(const float* y, float* xhat, int B, int 
     SCI_REQUIRE(y && xhat && B > 0 && (C == 1 || C == 3) && H % 2 == 0 && W % 2 == 0 && Cpad >= 4 * C, "ffdnet_unpack_output");
     ffdnet_unpack_kernel<<<grid1d((long)B * C * H * W), 256, 0, sci_stream(stream)>>>(y, xhat, B, C, H, W, Cpad);
     SCI_CHECK_LAUNCH("ffdnet_unpack_output");
+    return SCI_OK;
+}
+
+extern "C" int sci_ffdnet_pack_input_split_half(const float* u, float sigma, void* out, int B, int C, int H, int W, void* stream) {
+    SCI_REQUIRE(u && out && B > 0 && (C == 1 || C == 3) && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "ffdnet_pack_input_split_half");
+    ffdnet_pack_split_half_kernel<<<grid1d((long)B * (H / 2) * (W / 2) * 8), 256, 0, sci_stream(stream)>>>(
+        u, sigma, reinterpret_cast<__half*>(out), B, C, H, W);
+    SCI_CHECK_LAUNCH("ffdnet_pack_input_split_half");
+    return SCI_OK;
+}
+
+extern "C" int sci_ffdnet_unpack_output_split_half(const void* y, float* xhat, int B, int C, int H, int W, void* stream) {
+    SCI_REQUIRE(y && xhat && B > 0 && (C == 1 || C == 3) && H % 2 == 0 && W % 2 == 0, "ffdnet_unpack_output_split_half");
+    ffdnet_unpack_split_half_kernel<<<grid1d((long)B * C * H * W), 256, 0, sci_stream(stream)>>>(
+        reinterpret_cast<const __half*>(y), xhat, B, C, H, W);
+    SCI_CHECK_LAUNCH("ffdnet_unpack_output_split_half");
     return SCI_OK;
 }
 

@@ -256,10 +256,17 @@ class HalfLayer:
     64 (one 128-byte operand row).  ``cin_store`` / ``cout_store`` are the channels per pixel of the fp16 NHWC tensors it
     reads / writes (96 for the 90-channel tensor, otherwise 64 or 128; tensors with 32 real channels carry 32 zeros)."""
 
-    def __init__(self, base, cin_store, cout_store, ci_dup=0):
+    def __init__(self, base, cin_store, cout_store, ci_dup=0, split=False):
         self.base = base
         self.cin_store, self.cout_store, self.ci_dup = cin_store, cout_store, ci_dup
-        self.K = 32 if cin_store == 32 else _pad(cin_store, 64)     # 32-channel tensors: 64-byte operand rows (SWIZZLE_64B)
+        self.split = split
+        if split:
+            # value + remainder form (sci_conv_desc.w_split with half_io): a 64-channel chunk per 32 real channels on the
+            # input, the weights and the output; ci_dup = -1 selects that weight layout
+            self.ci_dup = -1
+            self.cin_store = 2 * _pad(base.Ci, 32)
+            self.cout_store = 2 * base.Co_pad
+        self.K = 32 if self.cin_store == 32 else _pad(self.cin_store, 64)   # 32-channel tensors: 64-byte operand rows (SWIZZLE_64B)
         self.k_used = (ci_dup + base.Ci) if ci_dup else base.Ci        # leading K columns that can be non-zero
         self.N = base.Co_pad
         self.stride, self.relu, self.ps = base.stride, base.relu, base.ps
@@ -410,7 +417,7 @@ class _EngineBase:
         """fp16 inference conv (tensor-core path only): x / y / residual are torch.float16 NHWC tensors."""
         b = Lh.base
         d = ConvDesc(_dp(x), _dp(Lh.wpk), _dp(b.scale), _dp(b.shift), _dp(residual), _dp(y), N, H, W, Lh.K, Lh.N,
-                     Lh.stride, int(Lh.relu), int(Lh.ps), 0, 0, 0, _dp(planar[0]) if planar else None,
+                     Lh.stride, int(Lh.relu), int(Lh.ps), 0, int(Lh.split), 0, _dp(planar[0]) if planar else None,
                      _dp(planar[1]) if planar else None, int(self.pdl_chain), 1, Lh.cin_store, Lh.cout_store)
         d.K_used = Lh.k_used                         # zero-padded channels of the last 64-channel chunk are not multiplied
         if self.profile is not None:
@@ -511,9 +518,15 @@ class FFDNetEngine(_EngineBase):
         # as tf32 hi + remainder, which brings the conv stack to ~fp32 accuracy (FFDNet has no residual connection, so
         # plain TF32 rounding reaches the output undamped and is then integrated by the ADMM dual variables)
         self.layers_inf = None
-        if self.tf32:
+        if self.tf32 and os.environ.get("SCI_FFDNET_INF_PRODUCTS", "3") == "3":
             self.layers_inf = [ConvLayer(c, bn, relu=(i < len(convs) - 1), first=(i == 0), wsplit=True, dup_in=(i > 0))
                                for i, (c, bn) in enumerate(convs)]
+        # ... and since round 2 as fp16 value + fp16 remainder (x 2^11) per activation and weight on the row-reuse kernel:
+        # the same three products at the fp16 tensor rate and half the bytes (SCI_FFDNET_INF=tf32 restores the 3xTF32 chain)
+        self.layers_h = None
+        if self.tf32 and os.environ.get("SCI_FFDNET_INF", "half") == "half" and all(L.Co_pad <= 128 for L in layers):
+            self.layers_h = [HalfLayer(L, 0, 0, split=True) for L in layers]
+            self.layers_inf = self.layers_h              # (the list prepare() re-packs)
         self.in_nc, self.out_nc = module.in_nc, module.out_nc
         if (self.in_nc, self.out_nc) not in ((3, 3), (1, 1)):
             raise NotImplementedError("native FFDNet engine: colour (3->3) and gray (1->1) models")
@@ -526,6 +539,8 @@ class FFDNetEngine(_EngineBase):
         self.prepare(training=train)
         dev = u.device
         h2, w2 = H // 2, W // 2
+        if not train and self.layers_h is not None:
+            return self._forward_split_half(u, sigma, B, H, W)
         if not train and self.layers_inf is not None:
             return self._forward_precise(u, sigma, B, H, W)
         L0 = self.layers[0]
@@ -541,6 +556,21 @@ class FFDNetEngine(_EngineBase):
         call("sci_ffdnet_unpack_output", ptr(acts[-1]), ptr(xhat), B, self.out_nc, H, W, self.layers[-1].Co_pad, stream())
         if train:
             self._saved = (acts, B, H, W)
+        return xhat
+
+    def _forward_split_half(self, u, sigma, B, H, W):
+        dev = u.device
+        h2, w2 = H // 2, W // 2
+        a = self.ws.get("in_h", (B, h2, w2, 64), dev, dtype=torch.float16)
+        call("sci_ffdnet_pack_input_split_half", ptr(u), float(sigma), ptr(a), B, self.in_nc, H, W, stream())
+        self.n_launch += 1
+        for i, Lh in enumerate(self.layers_h):
+            y = self.ws.get("hpp%d" % (i % 2), (B, h2, w2, Lh.cout_store), dev, dtype=torch.float16)
+            self.conv_h(Lh, a, B, h2, w2, y)
+            a = y
+        xhat = self.ws.get("xhat", (B, self.out_nc, H, W), dev)
+        call("sci_ffdnet_unpack_output_split_half", ptr(a), ptr(xhat), B, self.out_nc, H, W, stream())
+        self.n_launch += 1
         return xhat
 
     def _forward_precise(self, u, sigma, B, H, W):

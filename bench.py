@@ -75,7 +75,8 @@ def config_dict(c, cfg):
         d["finetune"] = "k=9,18; 2 Adam steps; lr 2e-6" if c == 4 else "none (inference schedule; the fine-tune of one 2048x2048x24 frame needs all 8 GPUs)"
     elif cfg["denoiser"].startswith("ffdnet"):
         d["weights"] = "model_zoo/%s.pth (the reference's own file)" % cfg["denoiser"]
-        d["conv"] = "tcgen05 TF32 operands (weights and activations split hi+lo, 3 products), fp32 accumulate"
+        d["conv"] = ("tcgen05: inference passes kind::f16 with every weight and activation as fp16 value + fp16 remainder x 2^11 "
+                     "(3 products, two fp32 accumulators: ~fp32 accuracy); online update kind::tf32 with split weights")
         d["finetune"] = "k=6,12; 2 Adam steps; lr 2e-6"
     return d
 
@@ -559,7 +560,8 @@ def main():
             if os.path.exists(tpath) and cfg["denoiser"] == "fastdvd_color" and c == 4:
                 traffic, tsrc = json.load(open(tpath))["dram_bytes_per_launch"], "profiles/" + name    # ncu --set full capture, per launch
                 break
-        kind = "kind::f16" if cfg["denoiser"] == "fastdvd_color" else "kind::tf32"
+        half_chain = cfg["denoiser"] == "fastdvd_color" or getattr(eng, "layers_h", None) is not None
+        kind = "kind::f16" if half_chain else "kind::tf32"
         roofline = {"bound": "tensor", "kernel": "conv_fwd2_tc_kernel / conv_fwd_tc_kernel (tcgen05.mma %s)" % kind, "achieved": achieved,
                     "peak": peak_bf16, "unit": "TFLOP/s", "frac": achieved / peak_bf16, "traffic": traffic, "traffic_source": tsrc,
                     "peak_kind": pk_kind + " cuBLAS bf16 (sustained)" + ("; fp16 operands run at the bf16 rate" if kind == "kind::f16"
@@ -567,6 +569,10 @@ def main():
                     "frac_of_operand_rate": achieved / (peak_bf16 if kind == "kind::f16" else peak_bf16 / 2),
                     "flops_per_pass": flops, "launches_per_pass": len(prof), "avg_launch_ms": 1e3 * conv_s / len(prof),
                     "pass": "one inference pass over %dx%dx%d (algorithmic flops, temp1 evaluated once per frame)" % (bb, hh, W)}
+        if cfg["denoiser"].startswith("ffdnet"):
+            # FFDNet returns the image itself, so its convolutions run at ~fp32 accuracy: 3 tensor-core products per algorithmic one
+            roofline["executed_products_per_flop"] = 3
+            roofline["frac_executed"] = 3 * roofline["frac_of_operand_rate"]
         del u
     hbm_rows = hbm_kernel_table(min(H, 1024) if c == 5 else H, W, B, dev, pk["hbm_gbs"])
     roofline_hbm = {"peak": pk["hbm_gbs"], "unit": "GB/s", "peak_kind": pk_kind + " copy bandwidth",

@@ -200,7 +200,13 @@ typedef struct sci_conv_desc {
     int round_tf32;         /* 1: round stored outputs to TF32 (they feed the next tensor-core conv) */
     int w_split;            /* TC only. 1: w is [18][Cout][Cin] = tf32(w) in taps 0..8 and the remainder
                                tf32(w - tf32(w)) in taps 9..17 (sci_conv_pack_weights round_tf32 = 2); both are
-                               multiplied, which removes the weight-rounding error of the TF32 path */
+                               multiplied, which removes the weight-rounding error of the TF32 path.
+                               With half_io: the fp16 SPLIT FORM of the FFDNet inference chain (stride 1, Cout <= 128) - x, w and y
+                               carry, per group of 32 channels, a 64-channel chunk [32 fp16 values | their 32 remainders
+                               (v - fp16(v)) * 2^11]: Cin = 64 * groups, Cout_store = 2 * Cout, w from
+                               sci_conv_pack_weights_half(ci_dup = -1).  value x value goes to one accumulator, value x
+                               remainder + remainder x value to a second one, added (x 2^-11) in the epilogue: the
+                               accuracy of the "3xTF32" scheme at the fp16 tensor rate and half the bytes */
     int emit_lo;            /* TC only. 1: y has 2*Cout channels per pixel: [tf32(v) | tf32(v - tf32(v))]; the next
                                layer is packed with ci_dup = Cout so it multiplies both ("3xTF32": ~fp32 accuracy) */
     const float* planar_in1; /* TC only, with planar_out: [N][3][H][W] frames                                   */
@@ -269,7 +275,9 @@ int sci_conv_pack_weights(const float* w, float* packed, int Co, int Ci, int gro
                           int ps, const float* oscale, int transpose_flip, int round_tf32, int ci_dup, void* stream);
 /* fp16 form of the forward packing for sci_conv_desc.half_io layers: packed [9][Co_pad][Ci_pad] IEEE binary16, round to
  * nearest; Ci_pad % 64 == 0 (one 128-byte operand row = 64 channels) or Ci_pad == 32 (64-byte rows).  Same grouped / PixelShuffle / ci_dup rules as above
- * (the fp16 network-boundary packer puts fp16(v) in channel k and fp16(v - fp16(v)) in channel k + ci_dup). */
+ * (the fp16 network-boundary packer puts fp16(v) in channel k and fp16(v - fp16(v)) in channel k + ci_dup).
+ * ci_dup = -1: split form (sci_conv_desc.w_split with half_io): Ci_pad = 64 * ceil(Ci / 32), K chunk g = [fp16(w) of channels
+ * 32g..32g+31 | (w - fp16(w)) * 2^11 of the same channels]. */
 int sci_conv_pack_weights_half(const float* w, void* packed, int Co, int Ci, int groups, int Co_pad, int Ci_pad, int ps,
                                int ci_dup, void* stream);
 /* fp16 form of sci_fastdvd_pack_input (packages/fastdvdnet/models.py:185 input block, circular window fastdvdnet.py:115):
@@ -327,6 +335,11 @@ int sci_ffdnet_pack_input(const float* u, float sigma, float* out, int B, int C,
                           void* stream);
 int sci_ffdnet_unpack_output(const float* y, float* xhat, int B, int C, int H, int W, int Cpad, void* stream);
 int sci_ffdnet_unpack_output_grad(const float* dxhat, float* dy, int B, int C, int H, int W, int Cpad, void* stream);
+/* fp16 split form of the same boundary (inference chain, sci_conv_desc.w_split + half_io): out [B][H/2][W/2][64] binary16 =
+ * [fp16(v_k), k < 32 | fp16((v_k - fp16(v_k)) * 2^11)] with v as in sci_ffdnet_pack_input; unpack reads a tail of the same
+ * form and writes xhat = value + remainder * 2^-11 as planar fp32. */
+int sci_ffdnet_pack_input_split_half(const float* u, float sigma, void* out, int B, int C, int H, int W, void* stream);
+int sci_ffdnet_unpack_output_split_half(const void* y, float* xhat, int B, int C, int H, int W, void* stream);
 
 /* FastDVDnet boundary (packages/fastdvdnet/models.py:185,196,234; fastdvdnet.py:115 circular window):
  * pack:   frames [B][3][H][W] planar -> DenBlock input [B][H][W][Cpad], for block f the channels

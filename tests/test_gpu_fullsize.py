@@ -197,7 +197,9 @@ def test_config3_ffdnet_512_vs_reference(warm512, engine_impl, monkeypatch):
                                    x0_bayer=np2tch_cuda(r1[0]), X_orig=orig, model_denoise=m, model_demosaic=None,
                                    show_iqa=True, demosaic_method='malvar2004', lr_=2e-6, interval_iter=6,
                                    logf=io.StringIO(), update_=True, update_per_iter=2)
-    # MEASURED (tools/ffdnet_dev.py): fp32 engine vs the reference 1.2e-5; tensor-core engine 2.6e-4.  (It was 1.23e-3 - above
+    # MEASURED (tools/ffdnet_dev.py): fp32 engine vs the reference 1.2e-5; tensor-core engine 5.3e-4 with the fp16 value +
+    # remainder inference chain (one pass deviates 1.4e-5 from the fp32 engine, tools/ffdnet_pass.py; the loop's figure is set by
+    # the TF32 fine-tune steps), 2.6e-4 with the "3xTF32" chain (SCI_FFDNET_INF=tf32).  (It was 1.23e-3 - above
     # north_star's bound - while all products of the "3xTF32" scheme accumulated into ONE TMEM accumulator: the tensor core
     # truncates when it accumulates, and FFDNet returns the image itself, so the 16 ADMM iterations integrate that bias through
     # the dual variables.  The small products now have their own accumulator, sci_conv_desc.lo_channel0.)

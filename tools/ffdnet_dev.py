@@ -25,3 +25,16 @@ for upd in (False, True):
     print("update=%s: tc vs fp32 engine max-abs %.3e  mean-abs %.3e" % (upd, d.max(), d.mean()))
 print("fp32 engine (update) vs reference golden sample: %.3e" % np.abs(res[(True, "ref")][::3, ::3] - g["c3_x_s"]).max())
 print("tc engine   (update) vs reference golden sample: %.3e" % np.abs(res[(True, "tc")][::3, ::3] - g["c3_x_s"]).max())
+
+os.environ["SCI_CONV_IMPL"] = "tc"
+m = FFDNet(3, 3, 96, 12, 'R'); m.load_state_dict(torch.load(os.path.join(ROOT, "model_zoo", "ffdnet_color.pth"))); m = m.eval().cuda()
+u = torch.rand(8, 3, 512, 512, device="cuda")
+eng = m.engine()
+for _ in range(3):
+    eng.forward(u, 12 / 255)
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(20):
+    eng.forward(u, 12 / 255)
+b.record(); torch.cuda.synchronize()
+print("FFDNet-colour inference pass 8x512x512: %.3f ms (SCI_FFDNET_INF_PRODUCTS=%s)" % (a.elapsed_time(b) / 20, os.environ.get("SCI_FFDNET_INF_PRODUCTS", "3")))
