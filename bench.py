@@ -121,8 +121,11 @@ class ClockSampler:
                     if v.lower().startswith("active"):
                         reasons.add(name)
         mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": sorted(reasons), "samples": len(sm)}
+        if getattr(self, "extended", False):
+            out["note"] = "timed region < 1 s: the same step kept running (untimed) under the sampler for 1 s more"
+        return out
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -516,6 +519,14 @@ def main():
         step_device()
     clocks = ClockSampler(local_rank) if rank == 0 else None
     ms, launches, out = timed(step_device, args.steps)
+    if clocks is not None and world == 1 and ms < 1000.0:
+        # a timed region shorter than nvidia-smi's start-up (config 1: a few ms per step) would end without a sample: keep the
+        # SAME step running under the sampler for about a second more (untimed) so that the line still carries clocks under load
+        t_end = time.time() + 1.0
+        while time.time() < t_end:
+            step_device()
+        torch.cuda.synchronize()
+        clocks.extended = True
     clk = clocks.stop() if clocks else None
     value = units * args.steps * n_iter / (ms * 1e-3)
     for _ in range(2):          # untimed: page-locked staging buffers, allocator pools and the noise helper reach steady state

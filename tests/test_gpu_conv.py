@@ -185,6 +185,42 @@ def test_networks_vs_golden(cuda, impl):
     assert _rel(y5.cpu(), d["fdvd_y"]) < tol
 
 
+def test_ffdnet_ragged_multi_tile(cuda, impl):
+    """FFDNet inference where the half-resolution width spans several 128-pixel row tiles with a ragged last one (w/2 = 150,
+    131) and odd sizes, colour (KAIR) and gray (KAIR + IPOL flavours), against the oracle networks on the CPU.  On the
+    tensor-core path this is the fp16 value + remainder chain (sci_conv_desc.w_split with half_io)."""
+    from adaptivepnp_sci_b200 import synthetic as syn
+    from adaptivepnp_sci_b200.ffdnet_ipol_models import FFDNet as FFDNetIPOL
+    from adaptivepnp_sci_b200.network_ffdnet import FFDNet
+    from oracle import networks
+    tol = {"ref": 2e-5, "tc": 2e-4}[impl]
+    g = torch.Generator().manual_seed(21)
+    sd = torch.load(os.path.join(ROOT, "model_zoo", "ffdnet_color.pth"))
+    om = networks.FFDNet(3, 3, 96, 12, 'R'); om.load_state_dict(sd, strict=True); om.eval()
+    m = _ffdnet(cuda)
+    for shape in ((2, 3, 36, 300), (1, 3, 19, 261)):
+        x = torch.rand(*shape, generator=g)
+        with torch.no_grad():
+            want = om(x, torch.full((shape[0], 1, 1, 1), 12 / 255))
+        got = m(x.cuda(), torch.full((shape[0], 1, 1, 1), 12 / 255).cuda())
+        assert got.shape == want.shape and float((got.cpu() - want).abs().max()) < tol, shape
+    # gray: KAIR flavour (15 layers x 64 features; random weights, the gray file is not shipped) and the IPOL flavour
+    tg = torch.Generator().manual_seed(5)
+    og = networks.FFDNet(1, 1, 64, 15, 'R')
+    for p in og.parameters():
+        p.data = torch.randn(p.shape, generator=tg) * (0.5 / max(1.0, float(np.sqrt(p[0].numel()))))
+    mg = FFDNet(1, 1, 64, 15, 'R'); mg.load_state_dict(og.state_dict(), strict=True); mg = mg.eval().cuda()
+    x = torch.rand(2, 1, 34, 262, generator=g)
+    with torch.no_grad():
+        want = og.eval()(x, torch.full((2, 1, 1, 1), 20 / 255))
+    assert float((mg(x.cuda(), torch.full((2, 1, 1, 1), 20 / 255).cuda()).cpu() - want).abs().max()) < tol
+    oi = networks.FFDNetIPOL(1); oi.load_state_dict(syn.ffdnet_ipol_synthetic_state_dict(1), strict=True); oi.eval()
+    mi = FFDNetIPOL(1); mi.load_state_dict(syn.ffdnet_ipol_synthetic_state_dict(1), strict=True); mi = mi.eval().cuda()
+    with torch.no_grad():
+        want = oi(x, torch.FloatTensor([20 / 255, 20 / 255]))
+    assert float((mi(x.cuda(), torch.full((2,), 20 / 255).cuda()).cpu() - want).abs().max()) < tol
+
+
 def test_adapters_vs_golden(cuda, impl):
     """Both plug-in adapters, inference and online fine-tune, against the reference's outputs."""
     from adaptivepnp_sci_b200 import fastdvdnet_adapter as fa, ffdnet_adapter as ffa
