@@ -21,6 +21,9 @@ What differs is everything between the boundary and the hardware:
 
 There is no CPU or PyTorch-op fallback: without the CUDA library the import fails.
 """
+import os
+import sys
+
 import numpy as np
 import torch
 
@@ -224,7 +227,8 @@ def _tiled_demosaic_denoise(tile, adapter, halo, x, b, inv_rou, w, tau, x_rgb, u
 
 
 def _tiled_outputs(tile, pb, xhat, theta, sse, X_orig, denoiser, sched, noise_estimate, logf, model_denoise, model_demosaic):
-    """Gather the strips into full-frame results on every rank; PSNR from all-reduced squared errors."""
+    """Gather the strips into full-frame results on every rank (``tile.gather_root_only``: on rank 0 only, the others return
+    None for the two image arrays and an empty SSIM list); PSNR from all-reduced squared errors."""
     B = pb.B
     Ht, W = tile.H_total, tile.W
     psnr_all = []
@@ -233,18 +237,31 @@ def _tiled_outputs(tile, pb, xhat, theta, sse, X_orig, denoiser, sched, noise_es
         psnr_all = list(iqa.psnr_from_sse(sse.cpu().numpy()[:len(sched)], Ht * W * B))
         if tile.rank == 0:
             _log_iterations(denoiser, sched, psnr_all, noise_estimate, logf)
-    theta_full = tile.gather_rows(theta)                                    # [B, Ht, W]
-    xhat_full = tile.gather_rows(xhat)                                      # [B, 3, Ht, W]
-    x_bayer_np = cuda2np(ops.planar_to_pixlast(theta_full.contiguous(), 1, B).view(Ht, W, B))
-    xbgr3_np = cuda2np(ops.planar_to_pixlast(xhat_full.contiguous(), 3, B).view(Ht, W, 3, B))
+    root = bool(tile.gather_root_only)                                      # only rank 0 assembles the frame (others: None)
+    timing = os.environ.get("SCI_TILE_TIMING") and tile.rank == 0
+    if timing:
+        import time
+        torch.cuda.synchronize(); t0 = time.time()
+    theta_full = tile.gather_rows(theta, root)                              # [B, Ht, W]
+    xhat_full = tile.gather_rows(xhat, root)                                # [B, 3, Ht, W]
+    if timing:
+        torch.cuda.synchronize(); t1 = time.time()
+    have = theta_full is not None
+    x_bayer_np = cuda2np(ops.planar_to_pixlast(theta_full.contiguous(), 1, B).view(Ht, W, B)) if have else None
+    xbgr3_np = cuda2np(ops.planar_to_pixlast(xhat_full.contiguous(), 3, B).view(Ht, W, 3, B)) if have else None
+    if timing:
+        torch.cuda.synchronize(); t2 = time.time()
+        print("tiled outputs: gather %.1f ms, remap + device-to-host %.1f ms" % (1e3 * (t1 - t0), 1e3 * (t2 - t1)), file=sys.stderr)
     psnr_, ssim_ = [], []
     if X_orig is not None:
         fsse = torch.zeros(B, dtype=torch.float64, device=theta.device)
         ops.psnr_accum(theta, pb.orig, fsse)
         tile.all_reduce_sum(fsse)
         psnr_ = list(iqa.psnr_from_sse(fsse.cpu().numpy(), Ht * W))
-        orig_full = cuda2np(ops.planar_to_pixlast(tile.gather_rows(pb.orig).contiguous(), 1, B).view(Ht, W, B))
-        ssim_ = [iqa.ssim(orig_full[:, :, t], x_bayer_np[:, :, t], data_range=1.) for t in range(B)]
+        orig_g = tile.gather_rows(pb.orig, root)
+        if orig_g is not None:
+            orig_full = cuda2np(ops.planar_to_pixlast(orig_g.contiguous(), 1, B).view(Ht, W, B))
+            ssim_ = [iqa.ssim(orig_full[:, :, t], x_bayer_np[:, :, t], data_range=1.) for t in range(B)]
     return xbgr3_np, x_bayer_np, psnr_, ssim_, psnr_all, model_denoise, model_demosaic
 
 

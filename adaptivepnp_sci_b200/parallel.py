@@ -175,6 +175,9 @@ class TileContext:
         self.total_pixels = H_total * W
         self.p2p = None
         self.halo_bytes_moved = 0
+        # results: True = only rank 0 assembles (and copies to the host) the full-frame outputs, the other ranks get None
+        # for the two image arrays - what a job that writes ONE result file needs; False = every rank gets the full frame
+        self.gather_root_only = False
 
     def enable_p2p(self, max_planes, max_halo):
         """Peer-to-peer halo exchange over NVLink (``P2PRegion``) for CUDA strips of fp32 planes; every rank must call it with
@@ -241,8 +244,8 @@ class TileContext:
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return t
 
-    def gather_rows(self, strip):
-        """strip [..., rows, W] on every rank -> full [..., H_total, W] on every rank."""
+    def gather_rows(self, strip, root_only=False):
+        """strip [..., rows, W] on every rank -> full [..., H_total, W] on every rank (``root_only``: on rank 0, None elsewhere)."""
         if self.p2p is not None:
             self.p2p.check()
         if self.world == 1:
@@ -251,6 +254,10 @@ class TileContext:
         src = strip.contiguous()
         if self.ctx.backend != "nccl":
             src = src.cpu()
+        if root_only:
+            parts = [torch.empty_like(src) for _ in range(self.world)] if self.rank == 0 else None
+            dist.gather(src, parts, dst=0)
+            return torch.cat(parts, dim=-2).to(strip.device) if self.rank == 0 else None
         parts = [torch.empty_like(src) for _ in range(self.world)]
         dist.all_gather(parts, src)
         return torch.cat(parts, dim=-2).to(strip.device)

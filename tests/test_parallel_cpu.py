@@ -102,3 +102,33 @@ def test_halo_longer_than_strip_is_refused():
         tile.halo_sizes(80)
     one = parallel.TileContext(parallel.Context(0, 1, 0, "gloo"), 64, 64)
     assert one.halo_sizes(80) == (0, 0)
+
+
+def _gather_worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    from adaptivepnp_sci_b200 import parallel
+    ctx = parallel.init(backend="gloo")
+    tile = parallel.TileContext(ctx, 16, 6)                  # 8-row strips
+    full = torch.arange(2 * 16 * 6, dtype=torch.float32).view(2, 16, 6)
+    strip = tile.slice_rows(full.permute(1, 2, 0).numpy())    # the solvers slice [H, W, ...] host arrays
+    mine = torch.from_numpy(strip).permute(2, 0, 1).contiguous()
+    everywhere = tile.gather_rows(mine)
+    root = tile.gather_rows(mine, root_only=True)
+    q.put((rank, bool(torch.equal(everywhere, full)), None if root is None else bool(torch.equal(root, full))))
+    ctx.finalize()
+
+
+def test_strip_gather_all_and_root_only():
+    """TileContext.gather_rows: every rank gets the full frame, or (root_only) rank 0 alone and the others None."""
+    world, port = 2, _free_port()
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    procs = [ctxm.Process(target=_gather_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert out == [(0, True, True), (1, True, None)]
