@@ -567,7 +567,19 @@ def main():
                 t_ms = ev0.elapsed_time(ev1)
                 sys.stderr.write("  %-28s %8.3f ms %8.1f TFLOP/s\n" % (tag, t_ms, fl / t_ms / 1e9))
         flops = sum(p[2] for p in prof)
-        conv_s = sum(p[0].elapsed_time(p[1]) for p in prof) * 1e-3
+        conv_s_serial = sum(p[0].elapsed_time(p[1]) for p in prof) * 1e-3   # an event pair per launch: serialises the chain
+        # the chain as the solver runs it (launches back to back, programmatic dependent launch): CUDA events around whole passes;
+        # the pass also contains its two small boundary kernels (input packing / output unpacking), which makes this conservative
+        for _ in range(3):
+            eng.forward(u, cfg["sigma"][0])
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_pass = 10
+        ev0.record()
+        for _ in range(n_pass):
+            eng.forward(u, cfg["sigma"][0])
+        ev1.record()
+        torch.cuda.synchronize()
+        conv_s = ev0.elapsed_time(ev1) * 1e-3 / n_pass
         achieved = flops / conv_s / 1e12
         peak_bf16 = pk["bf16_tflops_sustained"]
         traffic, tsrc = None, None
@@ -584,6 +596,8 @@ def main():
                                                                         else "; TF32 operands run at half the bf16 rate"),
                     "frac_of_operand_rate": achieved / (peak_bf16 if kind == "kind::f16" else peak_bf16 / 2),
                     "flops_per_pass": flops, "launches_per_pass": len(prof), "avg_launch_ms": 1e3 * conv_s / len(prof),
+                    "timing": "CUDA events around %d back-to-back passes on the launching stream (as the solver runs them)" % n_pass,
+                    "achieved_with_an_event_pair_per_launch": flops / conv_s_serial / 1e12,
                     "pass": "one inference pass over %dx%dx%d (algorithmic flops, temp1 evaluated once per frame)" % (bb, hh, W)}
         if cfg["denoiser"].startswith("ffdnet"):
             # FFDNet returns the image itself, so its convolutions run at ~fp32 accuracy: 3 tensor-core products per algorithmic one
