@@ -107,3 +107,61 @@ def test_matlab_v73_reader_roundtrip(tmp_path):
     with __import__("pytest").raises(ValueError):
         (d / "bad.mat").write_bytes(b"MATLAB 5.0 MAT-file" + b"\0" * 2000)
         h5lite.File(str(d / "bad.mat"))
+
+
+def test_gray_fastdvdnet_embedding_is_exact():
+    """The single-channel FastDVDnet runs on the colour engine through a zero embedding (fastdvdnet_models.FastDVDnet,
+    num_color_channels=1).  CPU check of the claim itself: the colour-shaped twin's weights, loaded into the ORACLE colour
+    network, reproduce the oracle gray network on the first plane (the other planes stay zero), and the twin follows in-place
+    weight changes without entering the gray model's state_dict."""
+    import torch
+    from adaptivepnp_sci_b200 import synthetic as syn
+    from adaptivepnp_sci_b200.fastdvdnet_models import FastDVDnet
+    from oracle import networks, synthetic
+    sd = syn.fastdvdnet_gray_synthetic_state_dict()
+    assert all(torch.equal(sd[k], v) for k, v in synthetic.fastdvdnet_gray_synthetic_state_dict().items())
+    m = FastDVDnet(num_input_frames=5, num_color_channels=1)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    twin = m._colour_twin()
+    assert list(m.state_dict().keys()) == list(sd.keys())               # the twin is not a sub-module
+    oc = networks.FastDVDnet(5, 3); oc.load_state_dict(twin.state_dict(), strict=True); oc.eval()
+    og = networks.FastDVDnet(5, 1); og.load_state_dict(sd, strict=True); og.eval()
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(1, 5, 24, 32, generator=g)
+    x3 = torch.zeros(1, 15, 24, 32); x3[:, 0::3] = x
+    nm = torch.full((1, 1, 24, 32), 12 / 255)
+    with torch.no_grad():
+        want, got = og(x, nm), oc(x3, nm)
+    assert float((got[:, 0:1] - want).abs().max()) < 1e-6 and float(got[:, 1:].abs().max()) == 0.0
+    with torch.no_grad():
+        m.temp1.inc.convblock[0].weight.mul_(1.5)
+    w_gray, w_twin = m.temp1.inc.convblock[0].weight.detach(), m._colour_twin().temp1.inc.convblock[0].weight.detach()
+    assert torch.equal(w_twin[:, 0], w_gray[:, 0]) and torch.equal(w_twin[:, 3], w_gray[:, 1]) and float(w_twin[:, 1:3].abs().max()) == 0.0
+
+
+def test_ipol_ffdnet_first_layer_reordering():
+    """IPOL-flavour FFDNet on the FFDNet engine: the engine's input kernel lays the down-sampled stack out as
+    [4C sub-images | sigma]; the module hands it a first convolution with its input columns in that order (the C noise
+    columns, which all see sigma, added up).  CPU check against the oracle network with the reference's [noise | sub-images] order."""
+    import torch
+    import torch.nn.functional as F
+    from adaptivepnp_sci_b200 import synthetic as syn
+    from adaptivepnp_sci_b200.ffdnet_ipol_models import FFDNet
+    from oracle import networks
+    for C in (1, 3):
+        sd = syn.ffdnet_ipol_synthetic_state_dict(C)
+        m = FFDNet(C); m.load_state_dict(sd, strict=True); m.eval()
+        layers = m.conv_layers()
+        assert len(layers) == (15 if C == 1 else 12) and layers[0][1] is None and layers[1][1] is not None and layers[-1][1] is None
+        o = networks.FFDNetIPOL(C); o.load_state_dict(sd, strict=True); o.eval()
+        g = torch.Generator().manual_seed(C)
+        down = torch.rand(2, 4 * C, 10, 12, generator=g)                 # the 4C sub-images of some frame
+        sigma = 20 / 255
+        ours = F.conv2d(torch.cat((down, torch.full((2, 1, 10, 12), sigma)), 1), layers[0][0].weight, padding=1)
+        ref = F.conv2d(torch.cat((torch.full((2, C, 10, 12), sigma), down), 1), o.intermediate_dncnn.itermediate_dncnn[0].weight, padding=1)
+        assert float((ours - ref).abs().max()) < 1e-5
+    import pytest
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m.engine()
