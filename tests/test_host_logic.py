@@ -158,8 +158,9 @@ def test_ipol_ffdnet_first_layer_reordering():
         g = torch.Generator().manual_seed(C)
         down = torch.rand(2, 4 * C, 10, 12, generator=g)                 # the 4C sub-images of some frame
         sigma = 20 / 255
-        ours = F.conv2d(torch.cat((down, torch.full((2, 1, 10, 12), sigma)), 1), layers[0][0].weight, padding=1)
-        ref = F.conv2d(torch.cat((torch.full((2, C, 10, 12), sigma), down), 1), o.intermediate_dncnn.itermediate_dncnn[0].weight, padding=1)
+        with torch.no_grad():
+            ours = F.conv2d(torch.cat((down, torch.full((2, 1, 10, 12), sigma)), 1), layers[0][0].weight, padding=1)
+            ref = F.conv2d(torch.cat((torch.full((2, C, 10, 12), sigma), down), 1), o.intermediate_dncnn.itermediate_dncnn[0].weight, padding=1)
         assert float((ours - ref).abs().max()) < 1e-5
     import pytest
     m.train()
