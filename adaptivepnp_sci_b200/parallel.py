@@ -136,8 +136,14 @@ class P2PRegion:
             raise RuntimeError("P2P halo exchange: neighbour %s did not deliver within 10 s" % ("above" if e == 1 else "below"))
 
     def close(self):
+        """Collective (every rank closes its region at the same point, like ``enable_p2p``): a neighbour's stream may still hold
+        stores into this region, so all devices drain and all ranks meet before anything is unmapped or freed."""
         from ._lib import call
         import ctypes
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        if self.ctx.world > 1 and dist.is_initialized():
+            dist.barrier()
         for q in self.peer.values():
             call("sci_p2p_close_handle", ctypes.c_void_p(q))
         self.peer = {}
