@@ -166,3 +166,35 @@ def test_ipol_ffdnet_first_layer_reordering():
     m.train()
     with pytest.raises(NotImplementedError):
         m.engine()
+
+
+def test_matlab_v73_reader_fuzz(tmp_path):
+    """Property test of the HDF5-subset reader against its spec-following writer: random ranks (1-4), extents, element types,
+    contiguous / chunked (+ shuffle + deflate) layouts with ragged edge chunks, user-block sizes."""
+    from hypothesis import HealthCheck, given, settings, strategies as st
+    from adaptivepnp_sci_b200 import h5lite
+    dtypes = st.sampled_from([np.uint8, np.int8, np.int16, np.uint16, np.int32, np.uint32, np.int64, np.float32, np.float64])
+
+    @st.composite
+    def arrays(draw):
+        shape = tuple(draw(st.integers(1, 9)) for _ in range(draw(st.integers(1, 4))))
+        a = (np.random.default_rng(draw(st.integers(0, 1000))).random(shape) * 200 - 50).astype(draw(dtypes))
+        return a, (tuple(draw(st.integers(1, s)) for s in shape) if draw(st.booleans()) else None)
+
+    count = [0]
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    @given(st.lists(arrays(), min_size=1, max_size=4), st.sampled_from([0, 512, 1024]))
+    def roundtrip(items, userblock):
+        count[0] += 1
+        arrs = {"v%d" % i: a for i, (a, c) in enumerate(items)}
+        chunks = {"v%d" % i: c for i, (a, c) in enumerate(items) if c is not None}
+        p = str(tmp_path / ("t%d.mat" % count[0]))
+        h5lite.write_mat73(p, arrs, chunks=chunks, userblock=userblock)
+        f = h5lite.File(p)
+        assert sorted(f.keys()) == sorted(arrs)
+        for k, v in arrs.items():
+            r = f[k]
+            assert r.shape == v.shape and r.dtype == v.dtype and np.array_equal(r, v), (k, v.shape, v.dtype, chunks.get(k))
+
+    roundtrip()
